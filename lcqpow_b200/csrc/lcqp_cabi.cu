@@ -1,0 +1,729 @@
+// lcqp_cabi.cu -- kernels + the extern "C" layer declared in include/lcqp_cuda.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC (see build.py)
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "lcqp_device.cuh"
+
+namespace lcqp {
+
+constexpr int kThreads = 256;
+constexpr size_t kSmemMax = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t kSinvSmemBudget = 96 * 1024; // keep S^-1 in shared memory when the whole CTA fits in this
+
+struct KernelArgs {
+    Dims d;
+    lcqp_cuda_options o;
+    const double* arr[LCQP_NUM_ARRAYS];
+    unsigned long long stride[LCQP_NUM_ARRAYS];  // 0 when shared
+    int batch;
+    int mats_shared;
+    int sinv_in_smem;
+    Prep shared_prep;
+    signed char* shared_ctype;   // m, written by prepare_shared_kernel
+    int* shared_status;          // 0 ok, 1 factorisation failed
+    double* workspace;           // per-CTA scratch
+    unsigned long long ws_stride;      // doubles per CTA
+    unsigned long long ws_prep_doubles; // doubles of the per-instance Prep block (0 when shared)
+    double* xout;
+    double* yout;
+    lcqp_cuda_stats* stats;
+    unsigned int* counter;
+    unsigned long long instance_offset;  // global index of instance 0 (perturbStep RNG key under sharding)
+};
+
+__device__ __forceinline__ Inst make_inst(const KernelArgs& a, int b)
+{
+    Inst in;
+    const double** p = reinterpret_cast<const double**>(&in);
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) p[k] = a.arr[k] ? a.arr[k] + a.stride[k] * (unsigned long long)b : nullptr;
+    return in;
+}
+
+__device__ __forceinline__ Prep carve_prep(double* base, const Dims& d)
+{
+    Prep pr;
+    const size_t n = d.n, m = d.m;
+    pr.P = base; base += n * n;
+    pr.A = base; base += m * n;
+    pr.D = base; base += n;
+    pr.E = base; base += m;
+    pr.Hinv = base; base += n * n;
+    pr.G = base; base += m * m;
+    pr.Minv = base; base += n * n;
+    pr.T = base;
+    return pr;
+}
+
+static size_t prep_doubles(const Dims& d)
+{
+    const size_t n = d.n, m = d.m;
+    return 3 * n * n + 2 * m * n + n + m + m * m;
+}
+
+// Operands shared by the whole batch are prepared once by a single CTA.
+__global__ void __launch_bounds__(kThreads) prepare_shared_kernel(const __grid_constant__ KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    QP s;
+    s.d = a.d;
+    s.o = &a.o;
+    s.pr = a.shared_prep;
+    carve(s.w, a.d, smem, a.sinv_in_smem ? nullptr : a.workspace + a.ws_prep_doubles);
+    const Inst in = make_inst(a, 0);
+    prepare_scale(a.d, in, s.pr, s.w);
+    qp_set_bounds(s, in);
+    for (int i = LCQ_TID; i < a.d.m; i += LCQ_NT) a.shared_ctype[i] = s.w.ctype[i];
+    __syncthreads();
+    const int rc = prepare_factor(a.d, s.pr, s.w.ctype, a.o, s.w);
+    if (threadIdx.x == 0) *a.shared_status = rc;
+}
+
+// The solver: persistent CTAs, one LCQP instance at a time per CTA.
+__global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_constant__ KernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    QP s;
+    s.d = a.d;
+    s.o = &a.o;
+    double* ws = a.workspace + a.ws_stride * blockIdx.x;
+    s.pr = a.mats_shared ? a.shared_prep : carve_prep(ws, a.d);
+    carve(s.w, a.d, smem, a.sinv_in_smem ? nullptr : ws + a.ws_prep_doubles);
+    const int nD = a.d.n + a.d.mA;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s.w.sc->bidx = (int)atomicAdd(a.counter, 1u);
+        __syncthreads();
+        const int b = s.w.sc->bidx;
+        if (b >= a.batch) break;
+        const Inst in = make_inst(a, b);
+        s.nw = 0; s.have_W = 0; s.sinv_valid = 0; s.eqp_res = 0; s.n_admm = 0; s.n_eqp = 0; s.n_changes = 0;
+        LoopOut out;
+        out.ret = 0; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
+        double* xo = a.xout + (size_t)b * a.d.n;
+        double* yo = a.yout + (size_t)b * nD;
+        bool skip = false;
+
+        // initializeSolver checks (LCQProblem.cpp:930-957): the OSQP-style layout has no box constraints
+        if (a.o.qpSolver == 2 && (in.lb || in.ub)) { out.ret = RET_INVALID_OSQP_BOX; skip = true; }
+        if (!skip) {
+            int prep_rc = 0;
+            if (!a.mats_shared) prepare_scale(a.d, in, s.pr, s.w);
+            const int bflags = qp_set_bounds(s, in);
+            if (bflags & 2) { out.ret = RET_INVALID_LOWER_COMP; skip = true; }  // loadLCQP fails (:747,:767)
+            const bool infeasible = (bflags & 1) != 0;
+            if (!skip && !infeasible) {
+                if (!a.mats_shared) prep_rc = prepare_factor(a.d, s.pr, s.w.ctype, a.o, s.w);
+                else {
+                    int diff = (*a.shared_status != 0);
+                    for (int i = LCQ_TID; i < a.d.m; i += LCQ_NT) diff |= (s.w.ctype[i] != a.shared_ctype[i]);
+                    prep_rc = block_max((double)diff, s.w.sc) > 0.5;
+                }
+            }
+            if (!skip) {
+                if (prep_rc) { out.ret = RET_SUBPROBLEM; out.exitFlag = 38; skip = true; }
+                else lcqp_loop(s, in, a.instance_offset + (unsigned long long)b, infeasible, xo, yo, out);
+            }
+        }
+        if (skip) {
+            for (int j = LCQ_TID; j < a.d.n; j += LCQ_NT) xo[j] = in.x0 ? in.x0[j] : 0.0;
+            for (int j = LCQ_TID; j < nD; j += LCQ_NT) yo[j] = 0.0;
+        }
+        if (threadIdx.x == 0) {
+            lcqp_cuda_stats st;
+            st.ret = out.ret; st.status = out.status; st.iterTotal = out.iterTotal; st.iterOuter = out.iterOuter;
+            st.subproblemIter = out.subIter; st.qpExitFlag = out.exitFlag;
+            st.nDuals = (a.o.qpSolver == 2) ? a.d.mA : nD; st.pad = 0;
+            st.rhoOpt = out.rhoOpt; st.reserved = (double)s.n_eqp;
+            a.stats[b] = st;
+        }
+    }
+}
+
+// ---- plugin door: one QP with persistent state ----------------------------------------------------
+struct QPState {
+    int nw, have_W, sinv_valid, prepared;
+    int infeasible, iterations, flag, pad;
+};
+
+struct QPKernelArgs {
+    Dims d;
+    lcqp_cuda_options o;
+    Inst in;            // Q, A (nC = nCtot rows), lbA, ubA, lb, ub, x0, y0, g  (device staging)
+    Prep pr;
+    double* sinv;
+    unsigned char* saved_smem;
+    unsigned long long smem_bytes;
+    QPState* state;
+    double* xout;  // n
+    double* yout;  // n + mA
+    int initial;
+};
+
+__global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_constant__ QPKernelArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    QP s;
+    s.d = a.d;
+    s.o = &a.o;
+    s.pr = a.pr;
+    carve(s.w, a.d, smem, a.sinv);
+    s.eqp_res = 0; s.n_admm = 0; s.n_eqp = 0; s.n_changes = 0;
+    if (!a.initial) {
+        for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
+            reinterpret_cast<double*>(smem)[k] = reinterpret_cast<const double*>(a.saved_smem)[k];
+        s.nw = a.state->nw; s.have_W = a.state->have_W; s.sinv_valid = a.state->sinv_valid;
+    } else {
+        s.nw = 0; s.have_W = 0; s.sinv_valid = 0;
+    }
+    __syncthreads();
+    int infeasible = a.initial ? 0 : a.state->infeasible;
+    int flag = 0, iters = 0;
+    if (a.initial) {
+        prepare_scale(a.d, a.in, s.pr, s.w);
+        const int bflags = qp_set_bounds(s, a.in);
+        infeasible = bflags & 1;
+        if (!infeasible && prepare_factor(a.d, s.pr, s.w.ctype, a.o, s.w)) flag = 38;
+    }
+    if (flag == 0) {
+        const double* y0A = a.in.y0 ? a.in.y0 + a.d.n : nullptr;
+        const double* y0box = (a.in.y0 && a.d.has_box) ? a.in.y0 : nullptr;
+        flag = qp_solve(s, a.initial != 0, a.in.g, a.in.x0, y0A, y0box, &iters, infeasible != 0);
+    }
+    if (flag == 0) {
+        for (int j = LCQ_TID; j < a.d.n; j += LCQ_NT) {
+            a.xout[j] = s.w.xs[j];
+            a.yout[j] = a.d.has_box ? s.w.ys[a.d.mA + j] : 0.0;
+        }
+        for (int i = LCQ_TID; i < a.d.mA; i += LCQ_NT) a.yout[a.d.n + i] = s.w.ys[i];
+    }
+    __syncthreads();
+    for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
+        reinterpret_cast<double*>(a.saved_smem)[k] = reinterpret_cast<const double*>(smem)[k];
+    if (threadIdx.x == 0) {
+        a.state->nw = s.nw; a.state->have_W = s.have_W; a.state->sinv_valid = s.sinv_valid;
+        a.state->infeasible = infeasible; a.state->iterations = iters; a.state->flag = flag;
+    }
+}
+
+}  // namespace lcqp
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace lcqp;
+
+struct lcqp_cuda_handle_s {
+    int nV, nC, nComp, capacity, device;
+    lcqp_cuda_options opts;
+    int batch = 0;
+    unsigned shared_mask = 0;
+    bool loaded = false, ran = false, owns_inputs = false;
+    const double* dev_in[LCQP_NUM_ARRAYS] = {};
+    double* own_in[LCQP_NUM_ARRAYS] = {};
+    size_t own_in_cap[LCQP_NUM_ARRAYS] = {};
+    double* xout = nullptr;
+    double* yout = nullptr;
+    lcqp_cuda_stats* stats = nullptr;
+    unsigned int* counter = nullptr;
+    double* shared_prep = nullptr;
+    size_t shared_prep_cap = 0;
+    signed char* shared_ctype = nullptr;
+    int* shared_status = nullptr;
+    double* workspace = nullptr;
+    size_t workspace_cap = 0;
+    int num_sms = 0;
+    long long launches = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+    cudaStream_t last_stream = nullptr;
+    unsigned long long instance_offset = 0;
+    std::string err;
+};
+
+static size_t field_len(int k, int n, int c, int p)
+{
+    switch (k) {
+        case LCQP_Q: return (size_t)n * n;
+        case LCQP_G: return n;
+        case LCQP_L: case LCQP_R: return (size_t)p * n;
+        case LCQP_LBL: case LCQP_UBL: case LCQP_LBR: case LCQP_UBR: return p;
+        case LCQP_A: return (size_t)c * n;
+        case LCQP_LBA: case LCQP_UBA: return c;
+        case LCQP_LB: case LCQP_UB: case LCQP_X0: return n;
+        case LCQP_Y0: return (size_t)n + c + 2 * (size_t)p;
+    }
+    return 0;
+}
+
+static int fail(lcqp_cuda_handle h, int code, const char* what, cudaError_t e = cudaSuccess)
+{
+    if (h) {
+        h->err = what;
+        if (e != cudaSuccess) { h->err += ": "; h->err += cudaGetErrorString(e); }
+    }
+    return code;
+}
+
+#define CK(call, code) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, code, #call, e_); } while (0)
+
+extern "C" {
+
+int lcqp_cuda_abi_version(void) { return LCQP_CUDA_ABI_VERSION; }
+
+void lcqp_cuda_default_options(lcqp_cuda_options* o)
+{
+    memset(o, 0, sizeof(*o));
+    o->complementarityTolerance = 1.0e3 * kEPS;  // Options.cpp:297-298
+    o->stationarityTolerance = 1.0e6 * kEPS;
+    o->initialPenaltyParameter = 0.01;
+    o->penaltyUpdateFactor = 2.0;
+    o->solveZeroPenaltyFirst = 1;
+    o->perturbStep = 1;
+    o->maxIterations = 1000;
+    o->maxPenaltyParameter = 1e8;
+    o->nDynamicPenalty = 3;
+    o->etaDynamicPenalty = 0.9;
+    o->qpSolver = 0;
+    o->qp_rho = 0.1;
+    o->qp_sigma = 1e-6;
+    o->qp_alpha = 1.6;
+    o->qp_delta = 1e-6;
+    o->qp_feas_tol = 1e-12;
+    o->qp_dual_tol = 1e-14;
+    o->qp_max_iter = 4000;
+    o->qp_check_interval = 10;
+    o->qp_refine_iter = 10;
+    o->qp_adaptive_rho = 0;
+    o->perturb_seed = 1;
+}
+
+int lcqp_cuda_create(int nV, int nC, int nComp, int batch_capacity, int device, lcqp_cuda_handle* out)
+{
+    if (!out) return LCQP_CUDA_BAD_ARGUMENT;
+    *out = nullptr;
+    if (nV <= 0 || nComp <= 0) return 106;  // INVALID_NUMBER_OF_OPTIM_VARS (LCQProblem.cpp:46-56)
+    if (nC < 0) return 108;                 // INVALID_NUMBER_OF_CONSTRAINT_VARS (:58-63)
+    if (batch_capacity <= 0) return LCQP_CUDA_BAD_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return LCQP_CUDA_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LCQP_CUDA_NO_DEVICE;
+    if (prop.major != 10) return LCQP_CUDA_NO_DEVICE;  // sm_100a cubin only
+    lcqp_cuda_handle h = new (std::nothrow) lcqp_cuda_handle_s();
+    if (!h) return LCQP_CUDA_OUT_OF_MEMORY;
+    h->nV = nV; h->nC = nC; h->nComp = nComp; h->capacity = batch_capacity; h->device = device;
+    h->num_sms = prop.multiProcessorCount;
+    lcqp_cuda_default_options(&h->opts);
+    if (cudaSetDevice(device) != cudaSuccess) { delete h; return LCQP_CUDA_NO_DEVICE; }
+    const size_t nD = (size_t)nV + nC + 2 * (size_t)nComp;
+    bool ok = cudaMalloc(&h->xout, sizeof(double) * nV * (size_t)batch_capacity) == cudaSuccess &&
+              cudaMalloc(&h->yout, sizeof(double) * nD * (size_t)batch_capacity) == cudaSuccess &&
+              cudaMalloc(&h->stats, sizeof(lcqp_cuda_stats) * (size_t)batch_capacity) == cudaSuccess &&
+              cudaMalloc(&h->counter, sizeof(unsigned int)) == cudaSuccess &&
+              cudaMalloc(&h->shared_status, sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&h->shared_ctype, nD + (size_t)nV + 16) == cudaSuccess &&
+              cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess &&
+              cudaEventCreate(&h->ev2) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); lcqp_cuda_destroy(h); return LCQP_CUDA_OUT_OF_MEMORY; }
+    *out = h;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_destroy(lcqp_cuda_handle h)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    cudaSetDevice(h->device);
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) if (h->own_in[k]) cudaFree(h->own_in[k]);
+    cudaFree(h->xout); cudaFree(h->yout); cudaFree(h->stats); cudaFree(h->counter);
+    cudaFree(h->shared_prep); cudaFree(h->shared_ctype); cudaFree(h->shared_status); cudaFree(h->workspace);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev2) cudaEventDestroy(h->ev2);
+    delete h;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_set_options(lcqp_cuda_handle h, const lcqp_cuda_options* o)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!o) return LCQP_CUDA_BAD_ARGUMENT;
+    // the validations of Options' setters (/root/reference/src/Options.cpp:85-259)
+    if (o->stationarityTolerance <= kEPS) return 105;
+    if (o->complementarityTolerance <= kEPS) return 102;
+    if (o->initialPenaltyParameter <= 1.0e-25) return 103;
+    if (o->penaltyUpdateFactor <= 1) return 101;
+    if (o->maxIterations <= 0) return 104;
+    if (o->maxPenaltyParameter <= 1.0e-25) return 121;
+    if (o->etaDynamicPenalty <= 0 || o->etaDynamicPenalty >= 1) return 119;
+    if (o->qpSolver < 0 || o->qpSolver > 2) return 109;
+    if (o->nDynamicPenalty > kMaxLeyffer) return LCQP_CUDA_BAD_ARGUMENT;
+    h->opts = *o;
+    return LCQP_CUDA_OK;
+}
+
+static int load_common(lcqp_cuda_handle h, int batch, unsigned shared_mask, const double* const* ptr, bool device_ptrs)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (batch <= 0 || batch > h->capacity) return fail(h, LCQP_CUDA_BAD_ARGUMENT, "batch out of range");
+    // loadLCQP argument checks (LCQProblem.cpp:87-144, :563-626, LCQProblem.ipp:39-50)
+    if (!ptr[LCQP_Q]) return fail(h, LCQP_CUDA_BAD_ARGUMENT, "Q is NULL");
+    if (!ptr[LCQP_G]) return 116;                                    // INVALID_OBJECTIVE_LINEAR_TERM
+    if (!ptr[LCQP_A] && h->nC > 0) return 117;                       // INVALID_CONSTRAINT_MATRIX
+    if (!ptr[LCQP_L] || !ptr[LCQP_R]) return 118;                    // INVALID_COMPLEMENTARITY_MATRIX
+    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) {
+        const size_t len = field_len(k, h->nV, h->nC, h->nComp);
+        if (!ptr[k] || len == 0) { h->dev_in[k] = nullptr; continue; }
+        const size_t count = ((shared_mask >> k) & 1u) ? len : len * (size_t)batch;
+        if (device_ptrs) { h->dev_in[k] = ptr[k]; continue; }
+        if (h->own_in_cap[k] < count) {
+            if (h->own_in[k]) cudaFree(h->own_in[k]);
+            h->own_in[k] = nullptr; h->own_in_cap[k] = 0;
+            const size_t want = ((shared_mask >> k) & 1u) ? count : len * (size_t)h->capacity;
+            if (cudaMalloc(&h->own_in[k], want * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(input)"); }
+            h->own_in_cap[k] = want;
+        }
+        CK(cudaMemcpyAsync(h->own_in[k], ptr[k], count * sizeof(double), cudaMemcpyHostToDevice, 0), LCQP_CUDA_LAUNCH_FAILED);
+        h->dev_in[k] = h->own_in[k];
+    }
+    h->batch = batch;
+    h->shared_mask = shared_mask;
+    h->loaded = true;
+    h->ran = false;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_load(lcqp_cuda_handle h, int batch, unsigned shared_mask,
+                   const double* Q, const double* g, const double* L, const double* R,
+                   const double* lbL, const double* ubL, const double* lbR, const double* ubR,
+                   const double* A, const double* lbA, const double* ubA,
+                   const double* lb, const double* ub, const double* x0, const double* y0)
+{
+    const double* p[LCQP_NUM_ARRAYS] = {Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0};
+    return load_common(h, batch, shared_mask, p, false);
+}
+
+int lcqp_cuda_load_device(lcqp_cuda_handle h, int batch, unsigned shared_mask,
+                          const double* Q, const double* g, const double* L, const double* R,
+                          const double* lbL, const double* ubL, const double* lbR, const double* ubR,
+                          const double* A, const double* lbA, const double* ubA,
+                          const double* lb, const double* ub, const double* x0, const double* y0)
+{
+    const double* p[LCQP_NUM_ARRAYS] = {Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0};
+    return load_common(h, batch, shared_mask, p, true);
+}
+
+int lcqp_cuda_set_instance_offset(lcqp_cuda_handle h, unsigned long long off)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    h->instance_offset = off;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!h->loaded) return fail(h, LCQP_CUDA_NOT_LOADED, "run before load");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+
+    KernelArgs a;
+    memset(&a, 0, sizeof(a));
+    Dims& d = a.d;
+    d.n = h->nV; d.nC = h->nC; d.nComp = h->nComp; d.mA = h->nC + 2 * h->nComp;
+    d.has_box = (h->opts.qpSolver != 2) && (h->dev_in[LCQP_LB] || h->dev_in[LCQP_UB]);
+    d.m = d.mA + (d.has_box ? d.n : 0);
+    d.cap = d.m < d.n + 16 ? d.m : d.n + 16;
+    a.o = h->opts;
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) {
+        a.arr[k] = h->dev_in[k];
+        a.stride[k] = ((h->shared_mask >> k) & 1u) ? 0ull : (unsigned long long)field_len(k, h->nV, h->nC, h->nComp);
+    }
+    a.batch = h->batch;
+    const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (h->nC > 0 ? (1u << LCQP_A) : 0u);
+    a.mats_shared = ((h->shared_mask & mat_bits) == mat_bits) || h->batch == 1;
+    a.sinv_in_smem = work_bytes(d, true) <= kSinvSmemBudget;
+    const size_t smem = work_bytes(d, a.sinv_in_smem != 0);
+    if (smem > kSmemMax) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
+
+    // grid: persistent CTAs, as many as are co-resident
+    CK(cudaFuncSetAttribute(lcqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaFuncSetAttribute(prepare_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_solve_kernel, kThreads, smem), LCQP_CUDA_LAUNCH_FAILED);
+    if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
+    int grid = per_sm * h->num_sms;
+    if (grid > h->batch) grid = h->batch;
+
+    // workspaces
+    const size_t pd = prep_doubles(d);
+    a.ws_prep_doubles = a.mats_shared ? 0 : pd;
+    a.ws_stride = a.ws_prep_doubles + (a.sinv_in_smem ? 0 : (size_t)d.cap * d.cap);
+    const size_t ws_total = a.ws_stride * (size_t)grid + (size_t)d.cap * d.cap;  // + one S^-1 for the prepare CTA
+    if (ws_total > h->workspace_cap) {
+        if (h->workspace) cudaFree(h->workspace);
+        h->workspace = nullptr; h->workspace_cap = 0;
+        if (cudaMalloc(&h->workspace, (ws_total ? ws_total : 1) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(workspace)"); }
+        h->workspace_cap = ws_total;
+    }
+    a.workspace = h->workspace;
+    if (a.mats_shared) {
+        if (pd > h->shared_prep_cap) {
+            if (h->shared_prep) cudaFree(h->shared_prep);
+            h->shared_prep = nullptr; h->shared_prep_cap = 0;
+            if (cudaMalloc(&h->shared_prep, pd * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(shared prep)"); }
+            h->shared_prep_cap = pd;
+        }
+        double* base = h->shared_prep;
+        const size_t n = d.n, m = d.m;
+        a.shared_prep.P = base; base += n * n;
+        a.shared_prep.A = base; base += m * n;
+        a.shared_prep.D = base; base += n;
+        a.shared_prep.E = base; base += m;
+        a.shared_prep.Hinv = base; base += n * n;
+        a.shared_prep.G = base; base += m * m;
+        a.shared_prep.Minv = base; base += n * n;
+        a.shared_prep.T = base;
+    }
+    a.shared_ctype = h->shared_ctype;
+    a.shared_status = h->shared_status;
+    a.xout = h->xout; a.yout = h->yout; a.stats = h->stats; a.counter = h->counter;
+    a.instance_offset = h->instance_offset;
+
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaMemsetAsync(h->shared_status, 0, sizeof(int), stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
+    if (a.mats_shared) {
+        KernelArgs ap = a;
+        // the prepare CTA uses the tail of the workspace for its S^-1 scratch when that is not in shared memory
+        ap.workspace = h->workspace + a.ws_stride * (size_t)grid;
+        ap.ws_prep_doubles = 0;
+        prepare_shared_kernel<<<1, kThreads, smem, stream>>>(ap);
+        h->launches++;
+    }
+    CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
+    lcqp_solve_kernel<<<grid, kThreads, smem, stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
+    h->last_stream = stream;
+    h->ran = true;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_synchronize(lcqp_cuda_handle h)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+    CK(cudaStreamSynchronize(h->last_stream), LCQP_CUDA_LAUNCH_FAILED);
+    return LCQP_CUDA_OK;
+}
+
+static int get_common(lcqp_cuda_handle h, void* dst, const void* src, size_t bytes)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!h->ran) return fail(h, LCQP_CUDA_NOT_RUN, "get before run");
+    if (!dst) return LCQP_CUDA_BAD_ARGUMENT;
+    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->last_stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaStreamSynchronize(h->last_stream), LCQP_CUDA_LAUNCH_FAILED);
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_get_primal(lcqp_cuda_handle h, double* x)
+{
+    return h ? get_common(h, x, h->xout, sizeof(double) * h->nV * (size_t)h->batch) : LCQP_CUDA_BAD_HANDLE;
+}
+
+int lcqp_cuda_get_dual(lcqp_cuda_handle h, double* y)
+{
+    return h ? get_common(h, y, h->yout, sizeof(double) * ((size_t)h->nV + h->nC + 2 * (size_t)h->nComp) * (size_t)h->batch) : LCQP_CUDA_BAD_HANDLE;
+}
+
+int lcqp_cuda_get_stats(lcqp_cuda_handle h, lcqp_cuda_stats* st)
+{
+    return h ? get_common(h, st, h->stats, sizeof(lcqp_cuda_stats) * (size_t)h->batch) : LCQP_CUDA_BAD_HANDLE;
+}
+
+int lcqp_cuda_get_device_results(lcqp_cuda_handle h, const double** x, const double** y, const lcqp_cuda_stats** st)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!h->ran) return fail(h, LCQP_CUDA_NOT_RUN, "get before run");
+    if (x) *x = h->xout;
+    if (y) *y = h->yout;
+    if (st) *st = h->stats;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_num_duals(lcqp_cuda_handle h)
+{
+    if (!h) return -1;
+    const int mA = h->nC + 2 * h->nComp;
+    return h->opts.qpSolver == 2 ? mA : h->nV + mA;  // LCQProblem.cpp:889, :934
+}
+
+long long lcqp_cuda_launch_count(lcqp_cuda_handle h) { return h ? h->launches : -1; }
+
+int lcqp_cuda_last_run_ms(lcqp_cuda_handle h, float* solve_ms, float* total_ms)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!h->ran) return fail(h, LCQP_CUDA_NOT_RUN, "timing before run");
+    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+    CK(cudaEventSynchronize(h->ev2), LCQP_CUDA_LAUNCH_FAILED);
+    if (solve_ms) CK(cudaEventElapsedTime(solve_ms, h->ev1, h->ev2), LCQP_CUDA_LAUNCH_FAILED);
+    if (total_ms) CK(cudaEventElapsedTime(total_ms, h->ev0, h->ev2), LCQP_CUDA_LAUNCH_FAILED);
+    return LCQP_CUDA_OK;
+}
+
+const char* lcqp_cuda_last_error(lcqp_cuda_handle h) { return h ? h->err.c_str() : "bad handle"; }
+
+// ---- plugin door ---------------------------------------------------------------------------------
+struct lcqp_cuda_qp_s {
+    int nV, nCtot, device;
+    lcqp_cuda_options opts;
+    double *Q = nullptr, *A = nullptr;
+    double* stage = nullptr;  // g n | lbA mA | ubA mA | lb n | ub n | x0 n | y0 n+mA
+    double* prep = nullptr;
+    double* sinv = nullptr;
+    unsigned char* saved = nullptr;
+    QPState* state = nullptr;
+    double* xout = nullptr;
+    double* yout = nullptr;
+    int has_box = 0;
+    bool initialised = false;
+    long long launches = 0;
+};
+
+int lcqp_cuda_qp_create(int nV, int nCtot, const double* Q, const double* A, int device, lcqp_cuda_qp* out)
+{
+    if (!out) return LCQP_CUDA_BAD_ARGUMENT;
+    *out = nullptr;
+    if (nV <= 0 || nCtot < 0 || !Q || (nCtot > 0 && !A)) return LCQP_CUDA_BAD_ARGUMENT;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return LCQP_CUDA_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) return LCQP_CUDA_NO_DEVICE;
+    lcqp_cuda_qp q = new (std::nothrow) lcqp_cuda_qp_s();
+    if (!q) return LCQP_CUDA_OUT_OF_MEMORY;
+    q->nV = nV; q->nCtot = nCtot; q->device = device;
+    lcqp_cuda_default_options(&q->opts);
+    cudaSetDevice(device);
+    const size_t n = nV, mA = nCtot, m = mA + n;
+    Dims d; d.n = nV; d.nC = nCtot; d.nComp = 0; d.mA = nCtot; d.has_box = 1; d.m = (int)m; d.cap = (int)(m < n + 16 ? m : n + 16);
+    bool ok = cudaMalloc(&q->Q, n * n * 8) == cudaSuccess && cudaMalloc(&q->A, (mA * n + 1) * 8) == cudaSuccess &&
+              cudaMalloc(&q->stage, (5 * n + 3 * mA + 8) * 8) == cudaSuccess &&
+              cudaMalloc(&q->prep, prep_doubles(d) * 8) == cudaSuccess &&
+              cudaMalloc(&q->sinv, (size_t)d.cap * d.cap * 8) == cudaSuccess &&
+              cudaMalloc(&q->saved, work_bytes(d, false) + 64) == cudaSuccess &&
+              cudaMalloc(&q->state, sizeof(QPState)) == cudaSuccess &&
+              cudaMalloc(&q->xout, n * 8) == cudaSuccess && cudaMalloc(&q->yout, (n + mA) * 8) == cudaSuccess;
+    if (ok) ok = cudaMemcpy(q->Q, Q, n * n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && mA) ok = cudaMemcpy(q->A, A, mA * n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) ok = cudaMemset(q->state, 0, sizeof(QPState)) == cudaSuccess;
+    if (!ok) { cudaGetLastError(); lcqp_cuda_qp_destroy(q); return LCQP_CUDA_OUT_OF_MEMORY; }
+    *out = q;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_qp_destroy(lcqp_cuda_qp q)
+{
+    if (!q) return LCQP_CUDA_BAD_HANDLE;
+    cudaSetDevice(q->device);
+    cudaFree(q->Q); cudaFree(q->A); cudaFree(q->stage); cudaFree(q->prep); cudaFree(q->sinv);
+    cudaFree(q->saved); cudaFree(q->state); cudaFree(q->xout); cudaFree(q->yout);
+    delete q;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_qp_set_options(lcqp_cuda_qp q, const lcqp_cuda_options* o)
+{
+    if (!q) return LCQP_CUDA_BAD_HANDLE;
+    if (!o) return LCQP_CUDA_BAD_ARGUMENT;
+    q->opts = *o;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_qp_solve(lcqp_cuda_qp q, int initialSolve, int* iterations, int* exit_flag,
+                       const double* g, const double* lbA, const double* ubA,
+                       const double* x0, const double* y0, const double* lb, const double* ub)
+{
+    if (!q) return LCQP_CUDA_BAD_HANDLE;
+    if (!g || !iterations || !exit_flag) return LCQP_CUDA_BAD_ARGUMENT;
+    if (!initialSolve && !q->initialised) return LCQP_CUDA_BAD_ARGUMENT;
+    if (cudaSetDevice(q->device) != cudaSuccess) return LCQP_CUDA_NO_DEVICE;
+    const size_t n = q->nV, mA = q->nCtot;
+    if (initialSolve) q->has_box = (lb || ub) ? 1 : 0;
+    QPKernelArgs a;
+    memset(&a, 0, sizeof(a));
+    Dims& d = a.d;
+    d.n = q->nV; d.nC = q->nCtot; d.nComp = 0; d.mA = q->nCtot; d.has_box = q->has_box;
+    d.m = d.mA + (d.has_box ? d.n : 0);
+    d.cap = d.m < d.n + 16 ? d.m : d.n + 16;
+    a.o = q->opts;
+    double* st = q->stage;
+    double* d_g = st; st += n;
+    double* d_lbA = st; st += mA;
+    double* d_ubA = st; st += mA;
+    double* d_lb = st; st += n;
+    double* d_ub = st; st += n;
+    double* d_x0 = st; st += n;
+    double* d_y0 = st;
+    bool ok = cudaMemcpy(d_g, g, n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+    auto up = [&](double* dst, const double* src, size_t cnt) { if (src && cnt) ok = ok && cudaMemcpy(dst, src, cnt * 8, cudaMemcpyHostToDevice) == cudaSuccess; };
+    if (initialSolve) { up(d_lbA, lbA, mA); up(d_ubA, ubA, mA); up(d_lb, lb, n); up(d_ub, ub, n); up(d_x0, x0, n); up(d_y0, y0, n + mA); }
+    if (!ok) { cudaGetLastError(); return LCQP_CUDA_LAUNCH_FAILED; }
+    memset(&a.in, 0, sizeof(a.in));
+    a.in.Q = q->Q; a.in.A = q->A; a.in.g = d_g;
+    // the QP's bounds are those given at the initial solve (LCQPow never changes them between calls)
+    if (initialSolve) { a.in.lbA = lbA ? d_lbA : nullptr; a.in.ubA = ubA ? d_ubA : nullptr; a.in.lb = lb ? d_lb : nullptr; a.in.ub = ub ? d_ub : nullptr;
+                        a.in.x0 = x0 ? d_x0 : nullptr; a.in.y0 = y0 ? d_y0 : nullptr; }
+    {
+        double* base = q->prep;
+        const size_t m = d.m;
+        a.pr.P = base; base += n * n;
+        a.pr.A = base; base += m * n;
+        a.pr.D = base; base += n;
+        a.pr.E = base; base += m;
+        a.pr.Hinv = base; base += n * n;
+        a.pr.G = base; base += m * m;
+        a.pr.Minv = base; base += n * n;
+        a.pr.T = base;
+    }
+    a.sinv = q->sinv;
+    a.saved_smem = q->saved;
+    const size_t smem = work_bytes(d, false);
+    if (smem > kSmemMax) return LCQP_CUDA_TOO_LARGE;
+    a.smem_bytes = (smem + 7) / 8 * 8;
+    a.state = q->state;
+    a.xout = q->xout; a.yout = q->yout;
+    a.initial = initialSolve ? 1 : 0;
+    if (cudaFuncSetAttribute(qp_plugin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes) != cudaSuccess) { cudaGetLastError(); return LCQP_CUDA_LAUNCH_FAILED; }
+    qp_plugin_kernel<<<1, kThreads, a.smem_bytes>>>(a);
+    q->launches++;
+    QPState hs;
+    if (cudaMemcpy(&hs, q->state, sizeof(hs), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return LCQP_CUDA_LAUNCH_FAILED; }
+    q->initialised = true;
+    *iterations = hs.iterations;
+    *exit_flag = hs.flag;
+    return hs.flag == 0 ? 0 : 203;  // SUBPROBLEM_SOLVER_ERROR (SubsolverQPOASES.cpp:165-166)
+}
+
+int lcqp_cuda_qp_get_solution(lcqp_cuda_qp q, double* x, double* y)
+{
+    if (!q) return LCQP_CUDA_BAD_HANDLE;
+    if (!q->initialised) return LCQP_CUDA_NOT_RUN;
+    if (cudaSetDevice(q->device) != cudaSuccess) return LCQP_CUDA_NO_DEVICE;
+    bool ok = true;
+    if (x) ok = ok && cudaMemcpy(x, q->xout, (size_t)q->nV * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (y) ok = ok && cudaMemcpy(y, q->yout, ((size_t)q->nV + q->nCtot) * 8, cudaMemcpyDeviceToHost) == cudaSuccess;
+    return ok ? LCQP_CUDA_OK : LCQP_CUDA_LAUNCH_FAILED;
+}
+
+}  // extern "C"

@@ -52,6 +52,7 @@
 #define MIN_SCALING 1e-4        /* constants.h:94 */
 #define MAX_SCALING 1e4
 #define SCALING_ITERS 10        /* constants.h:56 */
+#define RES_TOL 1e-9            /* residual of an EQP solve that still counts as solved */
 
 enum { RET_OK = 0, RET_INVALID_OSQP_BOX = 110, RET_INVALID_LOWER_COMP = 120, RET_MAX_ITER = 200, RET_MAX_PEN = 201,
        RET_SUBPROBLEM = 203, RET_OSQP_GUESS = 208 };
@@ -286,6 +287,7 @@ typedef struct {
     int* W;              /* working set of the accepted solution: 0 inactive, 1 at lower, 2 at upper */
     int* Wtry;
     int* Wfail;
+    int* pin;            /* rows exempt from the multiplier sign test (anti-cycling) */
     int have_W, have_fail;
     double* xs;          /* accepted solution, unscaled (n) */
     double* ys;          /* accepted multipliers, unscaled, qpOASES sign (m) */
@@ -452,7 +454,7 @@ static void qp_inst_free(qp_inst* q)
 {
     if (!q) return;
     free(q->l); free(q->u); free(q->ctype); free(q->rho_vec); free(q->x); free(q->z); free(q->y); free(q->q);
-    free(q->W); free(q->Wtry); free(q->Wfail); free(q->xs); free(q->ys);
+    free(q->W); free(q->Wtry); free(q->Wfail); free(q->pin); free(q->xs); free(q->ys);
     free(q->w); free(q->rhs); free(q->xt); free(q->zt); free(q->px); free(q->lam); free(q->t1); free(q->t2);
     free(q->zt2); free(q->xe); free(q->xa); free(q->S); free(q->r1); free(q->r2); free(q->dl); free(q->dx); free(q->idx);
     free(q);
@@ -475,6 +477,7 @@ static qp_inst* qp_inst_create(qp_mats* M, const lcqp_oracle_options* o, const d
     q->W = (int*)xcalloc((size_t)m, sizeof(int));
     q->Wtry = (int*)xcalloc((size_t)m, sizeof(int));
     q->Wfail = (int*)xcalloc((size_t)m, sizeof(int));
+    q->pin = (int*)xcalloc((size_t)m, sizeof(int));
     q->xs = (double*)xcalloc((size_t)n, sizeof(double));
     q->ys = (double*)xcalloc((size_t)m, sizeof(double));
     q->w = (double*)xcalloc((size_t)m, sizeof(double));
@@ -653,12 +656,12 @@ static int kkt_check(qp_inst* q, const int* W, int nw, int* worst)
     }
     double rs = 0;
     for (int j = 0; j < n; j++) if (fabs(q->r1[j]) > rs) rs = fabs(q->r1[j]);
-    if (!(rs <= ftol * (1.0 + ln))) return 2;
+    if (!(rs <= RES_TOL * (1.0 + ln))) return 2;
     csr_matvec(M, x, q->zt);
     for (int a = 0; a < nw; a++) {
         const int i = q->idx[a];
         const double b = (W[i] == 1 ? q->l[i] : q->u[i]);
-        if (!(fabs(b - q->zt[i]) <= ftol * (1.0 + fabs(b)))) return 3;
+        if (!(fabs(b - q->zt[i]) <= RES_TOL * (1.0 + fabs(b)))) return 3;
     }
     for (int i = 0; i < m; i++) {
         const double tol = ftol * (1.0 + fabs(q->zt[i]));
@@ -668,7 +671,7 @@ static int kkt_check(qp_inst* q, const int* W, int nw, int* worst)
     int reason = 0;
     for (int a = 0; a < nw; a++) {
         const int i = q->idx[a];
-        if (q->ctype[i] == 1) continue;
+        if (q->ctype[i] == 1 || q->pin[i]) continue;
         const double v = (W[i] == 1) ? lam[a] : -lam[a]; /* OSQP sign: lower-active needs lam <= 0 */
         if (v > wv) { wv = v; reason = (W[i] == 1) ? 5 : 6; if (worst) *worst = i; }
     }
@@ -742,6 +745,7 @@ static int active_set(qp_inst* q, double* x, int* W, int* changes)
     const int cap = 20 * (n + m) + 100;
     double* Axv = q->w;   /* A x  */
     double* Apv = q->zt2; /* A p  */
+    int last_dropped = -1;
     for (int it = 0; it < cap; it++) {
         int nw = eqp_solve(q, W);
         if (nw < 0) return 1;
@@ -770,6 +774,10 @@ static int active_set(qp_inst* q, double* x, int* W, int* changes)
         if (block >= 0) {
             for (int j = 0; j < n; j++) x[j] += alpha * q->dx[j];
             W[block] = bside;
+            /* a row that comes straight back after a zero-length step was dropped on multiplier noise: it
+             * is weakly active; exempt it from the sign test for the rest of this QP (anti-cycling) */
+            if (block == last_dropped && alpha * (1.0 + apn) <= 1e-12) q->pin[block] = 1;
+            last_dropped = -1;
             (*changes)++;
             if (dbg() > 1) fprintf(stderr, "    as it=%d nw=%d add row %d side %d alpha=%.3e |p|=%.3e res=%.1e\n", it, nw, block, bside, alpha, pn, q->eqp_res);
             continue;
@@ -782,6 +790,7 @@ static int active_set(qp_inst* q, double* x, int* W, int* changes)
         if ((reason == 5 || reason == 6) && worst >= 0) {
             if (dbg() > 1) fprintf(stderr, "    as it=%d nw=%d drop row %d (reason %d) res=%.1e\n", it, nw, worst, reason, q->eqp_res);
             W[worst] = 0;
+            last_dropped = worst;
             (*changes)++;
             continue;
         }
@@ -837,6 +846,7 @@ static int qp_solve(qp_inst* q, int initial, const double* g, const double* x0, 
     if (q->infeasible_bounds) return 37; /* qpOASES RET_INIT_FAILED_INFEASIBILITY class */
     if (!q->Minv) return 38;
     for (int j = 0; j < n; j++) q->q[j] = M->c * M->D[j] * g[j]; /* osqp.c:752-779 */
+    memset(q->pin, 0, (size_t)m * sizeof(int));
 
     int changes = 0;
     if (initial) {
@@ -1161,12 +1171,12 @@ void lcqp_oracle_default_options(lcqp_oracle_options* o)
     o->qp_sigma = 1e-6;
     o->qp_alpha = 1.6;
     o->qp_delta = 1e-6;
-    o->qp_feas_tol = 1e-9;
-    o->qp_dual_tol = 1e-9;
+    o->qp_feas_tol = 1e-12;
+    o->qp_dual_tol = 1e-14;
     o->qp_max_iter = 4000;
     o->qp_check_interval = 10;
     o->qp_refine_iter = 10;
-    o->qp_adaptive_rho = 1;
+    o->qp_adaptive_rho = 0;
     o->perturb_seed = 1;
 }
 

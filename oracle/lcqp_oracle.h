@@ -28,12 +28,12 @@ typedef struct {
     double qp_sigma;          /* ADMM sigma (constants.h:46)                     default 1e-6 */
     double qp_alpha;          /* relaxation (constants.h:58)                     default 1.6  */
     double qp_delta;          /* polish regularisation (constants.h:76)          default 1e-6 */
-    double qp_feas_tol;       /* KKT verification: primal feasibility (scaled)   default 1e-9 */
-    double qp_dual_tol;       /* KKT verification: dual sign (scaled)            default 1e-9 */
+    double qp_feas_tol;       /* KKT verification: primal feasibility (scaled)   default 1e-12 */
+    double qp_dual_tol;       /* KKT verification: dual sign (scaled)            default 1e-14 */
     int qp_max_iter;          /* ADMM iteration cap per QP (constants.h:61)      default 4000 */
     int qp_check_interval;    /* ADMM iterations between active-set probes       default 10   */
     int qp_refine_iter;       /* max refinement passes per polish                default 10   */
-    int qp_adaptive_rho;      /* 1: move along the rho ladder (x5 steps)         default 1    */
+    int qp_adaptive_rho;      /* 1: move along the rho ladder (x5 steps)         default 0    */
     unsigned long long perturb_seed; /* counter-based RNG key for perturbStep     default 1    */
 } lcqp_oracle_options;
 
