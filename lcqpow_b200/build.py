@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblcqp_cuda.so")
 SOURCES = [os.path.join(CSRC, "lcqp_cabi.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, "lcqp_device.cuh"), os.path.join(HERE, "..", "include", "lcqp_cuda.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
               "-shared", "-Xcompiler", "-fPIC"]
 
 
