@@ -332,8 +332,8 @@ def main():
 
     # max over ranks
     tt = torch.tensor([elapsed_ms, e2e_s * 1e3, float(k_ms)], device=dev, dtype=torch.float64)
-    solved = torch.tensor([float((st["ret"] == 0).sum()), float(st["reserved"].sum()), float(st["iterTotal"].sum()),
-                           float(st["subproblemIter"].sum())], device=dev, dtype=torch.float64)
+    solved = torch.tensor([float((st["ret"] == 0).sum()), float(st["kktSolves"].sum()) + float(st["admmIters"].sum()),
+                           float(st["iterTotal"].sum()), float(st["subproblemIter"].sum())], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(solved, op=dist.ReduceOp.SUM)

@@ -85,9 +85,9 @@ typedef struct {
     int subproblemIter;
     int qpExitFlag;
     int nDuals;
-    int pad;
+    int kktSolves;       /* regularised KKT solves (active-set passes) spent on this instance */
     double rhoOpt;
-    double reserved;
+    double admmIters;    /* ADMM iterations spent on this instance (phase 1 of the first QP, fall-backs) */
 } lcqp_cuda_stats;
 
 typedef struct lcqp_cuda_handle_s* lcqp_cuda_handle;
@@ -136,6 +136,8 @@ int lcqp_cuda_num_duals(lcqp_cuda_handle h);                      /* LCQProblem:
 /* kernels launched by this handle so far (bench.py's gpu_launches) and device time of the last run */
 long long lcqp_cuda_launch_count(lcqp_cuda_handle h);
 int lcqp_cuda_last_run_ms(lcqp_cuda_handle h, float* solve_kernel_ms, float* total_ms);
+/* launch geometry of the last run: CTAs, dynamic shared memory per CTA, order of the static equality block */
+int lcqp_cuda_last_launch_info(lcqp_cuda_handle h, int* grid, int* smem_bytes, int* equality_rows);
 const char* lcqp_cuda_last_error(lcqp_cuda_handle h);
 
 /* ---- (2) plugin door: one convex QP, SubsolverBase semantics ---------------------------------- */

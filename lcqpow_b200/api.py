@@ -36,7 +36,7 @@ EXPORTS = (
     "lcqp_cuda_set_options", "lcqp_cuda_load", "lcqp_cuda_load_device", "lcqp_cuda_set_instance_offset",
     "lcqp_cuda_run", "lcqp_cuda_synchronize", "lcqp_cuda_get_primal", "lcqp_cuda_get_dual",
     "lcqp_cuda_get_stats", "lcqp_cuda_get_device_results", "lcqp_cuda_num_duals", "lcqp_cuda_launch_count",
-    "lcqp_cuda_last_run_ms", "lcqp_cuda_last_error", "lcqp_cuda_qp_create", "lcqp_cuda_qp_destroy",
+    "lcqp_cuda_last_run_ms", "lcqp_cuda_last_launch_info", "lcqp_cuda_last_error", "lcqp_cuda_qp_create", "lcqp_cuda_qp_destroy",
     "lcqp_cuda_qp_set_options", "lcqp_cuda_qp_solve", "lcqp_cuda_qp_get_solution",
 )
 
@@ -55,8 +55,8 @@ class CudaOptions(C.Structure):
 
 
 STATS_DTYPE = np.dtype([("ret", "i4"), ("status", "i4"), ("iterTotal", "i4"), ("iterOuter", "i4"),
-                        ("subproblemIter", "i4"), ("qpExitFlag", "i4"), ("nDuals", "i4"), ("pad", "i4"),
-                        ("rhoOpt", "f8"), ("reserved", "f8")])
+                        ("subproblemIter", "i4"), ("qpExitFlag", "i4"), ("nDuals", "i4"), ("kktSolves", "i4"),
+                        ("rhoOpt", "f8"), ("admmIters", "f8")])
 
 _lib = None
 
@@ -94,6 +94,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
     lib.lcqp_cuda_launch_count.argtypes = [vp]
     lib.lcqp_cuda_launch_count.restype = C.c_longlong
     lib.lcqp_cuda_last_run_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.lcqp_cuda_last_launch_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lcqp_cuda_last_error.argtypes = [vp]
     lib.lcqp_cuda_last_error.restype = C.c_char_p
     lib.lcqp_cuda_qp_create.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, C.POINTER(vp)]
@@ -303,6 +304,14 @@ class LCQProblemBatch:
 
     def launchCount(self) -> int:
         return int(self.lib.lcqp_cuda_launch_count(self.h))
+
+    def lastLaunchInfo(self):
+        """(CTAs, dynamic shared memory per CTA in bytes, order of the static equality block) of the last run."""
+        g, sm, me = C.c_int(), C.c_int(), C.c_int()
+        rc = self.lib.lcqp_cuda_last_launch_info(self.h, C.byref(g), C.byref(sm), C.byref(me))
+        if rc != 0:
+            raise LCQPError(rc, "lcqp_cuda_last_launch_info")
+        return g.value, sm.value, me.value
 
     def lastRunMs(self):
         a, b = C.c_float(), C.c_float()

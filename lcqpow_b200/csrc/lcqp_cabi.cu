@@ -13,9 +13,10 @@
 
 namespace lcqp {
 
-constexpr int kThreads = 256;
-constexpr size_t kSmemMax = 227 * 1024;       // opt-in dynamic shared memory per CTA on sm_100
-constexpr size_t kSinvSmemBudget = 96 * 1024; // keep S^-1 in shared memory when the whole CTA fits in this
+constexpr int kThreads = 256;           // solver CTA
+constexpr int kPrepThreads = 1024;      // batch-level preparation CTA
+constexpr size_t kSmemMax = 227 * 1024; // opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t kSmemSM = 228 * 1024;  // shared memory per SM (1 KB per resident CTA is reserved)
 
 struct KernelArgs {
     Dims d;
@@ -23,14 +24,16 @@ struct KernelArgs {
     const double* arr[LCQP_NUM_ARRAYS];
     unsigned long long stride[LCQP_NUM_ARRAYS];  // 0 when shared
     int batch;
-    int mats_shared;
-    int sinv_in_smem;
-    Prep shared_prep;
-    signed char* shared_ctype;   // m, written by prepare_shared_kernel
-    int* shared_status;          // 0 ok, 1 factorisation failed
-    double* workspace;           // per-CTA scratch
-    unsigned long long ws_stride;      // doubles per CTA
-    unsigned long long ws_prep_doubles; // doubles of the per-instance Prep block (0 when shared)
+    unsigned shared_mask;        // loadLCQP arguments shared by the batch
+    int mats_shared;             // Q, L, R, A all shared: one preparation for the batch
+    SmemPlan plan;
+    Mats* shared_mats;           // prepared operands of the batch (device struct, written by prepare_shared_kernel)
+    RawOps* shared_raw;          // CSR / dense operators on the unscaled shared matrices
+    double* shared_mats_store;   // backing store of shared_mats
+    CsrPool pool;
+    double* workspace;                   // per-CTA scratch: [Mats block when not shared][what did not fit in shared memory]
+    unsigned long long ws_stride;        // doubles per CTA
+    unsigned long long ws_mats_doubles;  // doubles of the per-CTA Mats block (0 when shared)
     double* xout;
     double* yout;
     lcqp_cuda_stats* stats;
@@ -46,56 +49,67 @@ __device__ __forceinline__ Inst make_inst(const KernelArgs& a, int b)
     return in;
 }
 
-__device__ __forceinline__ Prep carve_prep(double* base, const Dims& d)
-{
-    Prep pr;
-    const size_t n = d.n, m = d.m;
-    pr.P = base; base += n * n;
-    pr.A = base; base += m * n;
-    pr.D = base; base += n;
-    pr.E = base; base += m;
-    pr.Hinv = base; base += n * n;
-    pr.G = base; base += m * m;
-    pr.Minv = base; base += n * n;
-    pr.T = base;
-    return pr;
-}
-
-static size_t prep_doubles(const Dims& d)
-{
-    const size_t n = d.n, m = d.m;
-    return 3 * n * n + 2 * m * n + n + m + m * m;
-}
-
-// Operands shared by the whole batch are prepared once by a single CTA.
-__global__ void __launch_bounds__(kThreads) prepare_shared_kernel(const __grid_constant__ KernelArgs a)
+// Operands shared by the whole batch are prepared once by a single CTA: CSR copies of the shared unscaled
+// matrices (outer loop) and, when Q, L, R and A are all shared, scaling + factorisations + their operators.
+__global__ void __launch_bounds__(kPrepThreads) prepare_shared_kernel(const __grid_constant__ KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    QP s;
-    s.d = a.d;
-    s.o = &a.o;
-    s.pr = a.shared_prep;
-    carve(s.w, a.d, smem, a.sinv_in_smem ? nullptr : a.workspace + a.ws_prep_doubles);
-    const Inst in = make_inst(a, 0);
-    prepare_scale(a.d, in, s.pr, s.w);
-    qp_set_bounds(s, in);
-    for (int i = LCQ_TID; i < a.d.m; i += LCQ_NT) a.shared_ctype[i] = s.w.ctype[i];
+    __shared__ Mats mt;
+    __shared__ RawOps ro;
+    __shared__ Scalars sc;
+    const Dims& d = a.d;
+    double* v1 = reinterpret_cast<double*>(smem);
+    double* v2 = v1 + d.n;
+    double* e1 = v2 + d.n;
+    double* e2 = e1 + d.m;
+    double* e3 = e2 + d.m;
+    double* lo = e3 + d.m;
+    double* up = lo + d.m;
+    signed char* ctype = reinterpret_cast<signed char*>(up + d.m);
+    CsrPool pool = a.pool;
+    if (threadIdx.x == 0) { pool.used[0] = 0; pool.used[1] = 0; }
     __syncthreads();
-    const int rc = prepare_factor(a.d, s.pr, s.w.ctype, a.o, s.w);
-    if (threadIdx.x == 0) *a.shared_status = rc;
+    const Inst in = make_inst(a, 0);
+    raw_build_ops(d, in, ro, a.shared_mask, pool, &sc);
+    if (threadIdx.x == 0) *a.shared_raw = ro;
+    if (a.mats_shared) {
+        if (threadIdx.x == 0) { carve_mats(mt, a.shared_mats_store, d); mt.status = 1; }
+        __syncthreads();
+        prepare_scale(d, in, mt, v1, e1);
+        mats_build_ops_pre(d, mt, pool, &sc);
+        const int bflags = set_bounds(d, in, mt.E, lo, up, ctype, &sc);
+        int rc = 1;
+        if (!(bflags & 1)) rc = prepare_factor(d, mt, ctype, a.o, v1, v2, e1, e2, e3, &sc);
+        else {
+            // instance 0 has inconsistent bounds: prepare with its row types anyway (other instances may be fine)
+            rc = prepare_factor(d, mt, ctype, a.o, v1, v2, e1, e2, e3, &sc);
+        }
+        if (rc == 0) mats_build_ops_post(d, mt, pool, &sc);
+        __syncthreads();
+        if (threadIdx.x == 0) { mt.status = rc; *a.shared_mats = mt; }
+    }
 }
 
 // The solver: persistent CTAs, one LCQP instance at a time per CTA.
 __global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_constant__ KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ Mats mt;
+    __shared__ RawOps ro;
     QP s;
     s.d = a.d;
     s.o = &a.o;
     double* ws = a.workspace + a.ws_stride * blockIdx.x;
-    s.pr = a.mats_shared ? a.shared_prep : carve_prep(ws, a.d);
-    carve(s.w, a.d, smem, a.sinv_in_smem ? nullptr : ws + a.ws_prep_doubles);
+    carve(s.w, a.d, a.plan, smem, ws + a.ws_mats_doubles);
+    if (threadIdx.x == 0) {
+        if (a.mats_shared) mt = *a.shared_mats;
+        else carve_mats(mt, ws, a.d);
+        ro = *a.shared_raw;
+    }
+    __syncthreads();
     const int nD = a.d.n + a.d.mA;
+    const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (1u << LCQP_A);
+    const bool raw_all_shared = (a.shared_mask & mat_bits) == mat_bits || (a.d.nC == 0 && (a.shared_mask & mat_bits) == (mat_bits & ~(1u << LCQP_A)));
 
     for (;;) {
         __syncthreads();
@@ -104,44 +118,21 @@ __global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_co
         const int b = s.w.sc->bidx;
         if (b >= a.batch) break;
         const Inst in = make_inst(a, b);
-        s.nw = 0; s.have_W = 0; s.sinv_valid = 0; s.eqp_res = 0; s.n_admm = 0; s.n_eqp = 0; s.n_changes = 0;
+        if (!raw_all_shared) {
+            if (threadIdx.x == 0) raw_dense_ops(a.d, in, ro, a.shared_mask);
+            __syncthreads();
+        }
         LoopOut out;
-        out.ret = 0; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
         double* xo = a.xout + (size_t)b * a.d.n;
         double* yo = a.yout + (size_t)b * nD;
-        bool skip = false;
-
-        // initializeSolver checks (LCQProblem.cpp:930-957): the OSQP-style layout has no box constraints
-        if (a.o.qpSolver == 2 && (in.lb || in.ub)) { out.ret = RET_INVALID_OSQP_BOX; skip = true; }
-        if (!skip) {
-            int prep_rc = 0;
-            if (!a.mats_shared) prepare_scale(a.d, in, s.pr, s.w);
-            const int bflags = qp_set_bounds(s, in);
-            if (bflags & 2) { out.ret = RET_INVALID_LOWER_COMP; skip = true; }  // loadLCQP fails (:747,:767)
-            const bool infeasible = (bflags & 1) != 0;
-            if (!skip && !infeasible) {
-                if (!a.mats_shared) prep_rc = prepare_factor(a.d, s.pr, s.w.ctype, a.o, s.w);
-                else {
-                    int diff = (*a.shared_status != 0);
-                    for (int i = LCQ_TID; i < a.d.m; i += LCQ_NT) diff |= (s.w.ctype[i] != a.shared_ctype[i]);
-                    prep_rc = block_max((double)diff, s.w.sc) > 0.5;
-                }
-            }
-            if (!skip) {
-                if (prep_rc) { out.ret = RET_SUBPROBLEM; out.exitFlag = 38; skip = true; }
-                else lcqp_loop(s, in, a.instance_offset + (unsigned long long)b, infeasible, xo, yo, out);
-            }
-        }
-        if (skip) {
-            for (int j = LCQ_TID; j < a.d.n; j += LCQ_NT) xo[j] = in.x0 ? in.x0[j] : 0.0;
-            for (int j = LCQ_TID; j < nD; j += LCQ_NT) yo[j] = 0.0;
-        }
+        run_instance(s, mt, a.mats_shared != 0, in, ro, a.instance_offset + (unsigned long long)b, xo, yo, out);
         if (threadIdx.x == 0) {
             lcqp_cuda_stats st;
             st.ret = out.ret; st.status = out.status; st.iterTotal = out.iterTotal; st.iterOuter = out.iterOuter;
             st.subproblemIter = out.subIter; st.qpExitFlag = out.exitFlag;
-            st.nDuals = (a.o.qpSolver == 2) ? a.d.mA : nD; st.pad = 0;
-            st.rhoOpt = out.rhoOpt; st.reserved = (double)s.n_eqp;
+            st.nDuals = (a.o.qpSolver == 2) ? a.d.mA : nD;
+            st.kktSolves = (int)s.n_pass;
+            st.rhoOpt = out.rhoOpt; st.admmIters = (double)s.n_admm;
             a.stats[b] = st;
         }
     }
@@ -149,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_co
 
 // ---- plugin door: one QP with persistent state ----------------------------------------------------
 struct QPState {
-    int nw, have_W, sinv_valid, prepared;
+    int nw, have_W, tinv_valid, prepared;
     int infeasible, iterations, flag, pad;
 };
 
@@ -157,8 +148,10 @@ struct QPKernelArgs {
     Dims d;
     lcqp_cuda_options o;
     Inst in;            // Q, A (nC = nCtot rows), lbA, ubA, lb, ub, x0, y0, g  (device staging)
-    Prep pr;
-    double* sinv;
+    SmemPlan plan;
+    double* mats_store;
+    Mats* mats;         // persistent device copy of the Mats struct
+    double* gl;         // global scratch for what does not fit in shared memory
     unsigned char* saved_smem;
     unsigned long long smem_bytes;
     QPState* state;
@@ -170,27 +163,36 @@ struct QPKernelArgs {
 __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_constant__ QPKernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ Mats mt;
     QP s;
     s.d = a.d;
     s.o = &a.o;
-    s.pr = a.pr;
-    carve(s.w, a.d, smem, a.sinv);
-    s.eqp_res = 0; s.n_admm = 0; s.n_eqp = 0; s.n_changes = 0;
+    carve(s.w, a.d, a.plan, smem, a.gl);
+    s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
     if (!a.initial) {
         for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
             reinterpret_cast<double*>(smem)[k] = reinterpret_cast<const double*>(a.saved_smem)[k];
-        s.nw = a.state->nw; s.have_W = a.state->have_W; s.sinv_valid = a.state->sinv_valid;
+        s.nw = a.state->nw; s.have_W = a.state->have_W; s.tinv_valid = a.state->tinv_valid;
+        if (threadIdx.x == 0) mt = *a.mats;
     } else {
-        s.nw = 0; s.have_W = 0; s.sinv_valid = 0;
+        s.nw = 0; s.have_W = 0; s.tinv_valid = 0;
+        if (threadIdx.x == 0) { carve_mats(mt, a.mats_store, a.d); mats_dense_ops(a.d, mt); }
     }
     __syncthreads();
+    s.mt = &mt;
     int infeasible = a.initial ? 0 : a.state->infeasible;
     int flag = 0, iters = 0;
     if (a.initial) {
-        prepare_scale(a.d, a.in, s.pr, s.w);
-        const int bflags = qp_set_bounds(s, a.in);
+        prepare_scale(a.d, a.in, mt, s.w.u, s.w.zx);
+        const int bflags = set_bounds(a.d, a.in, mt.E, s.w.l, s.w.ub, s.w.ctype, s.w.sc);
         infeasible = bflags & 1;
-        if (!infeasible && prepare_factor(a.d, s.pr, s.w.ctype, a.o, s.w)) flag = 38;
+        if (!infeasible) {
+            if (prepare_factor(a.d, mt, s.w.ctype, a.o, s.w.u, s.w.t, s.w.zx, s.w.zp, s.w.w, s.w.sc)) flag = 38;
+            else {
+                for (int i = LCQ_TID; i < a.d.m; i += LCQ_NT) s.w.ctype[i] = mt.ctype[i];
+                __syncthreads();
+            }
+        }
     }
     if (flag == 0) {
         const double* y0A = a.in.y0 ? a.in.y0 + a.d.n : nullptr;
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
     }
     if (flag == 0) {
         for (int j = LCQ_TID; j < a.d.n; j += LCQ_NT) {
-            a.xout[j] = s.w.xs[j];
+            a.xout[j] = mt.D[j] * s.w.x[j];
             a.yout[j] = a.d.has_box ? s.w.ys[a.d.mA + j] : 0.0;
         }
         for (int i = LCQ_TID; i < a.d.mA; i += LCQ_NT) a.yout[a.d.n + i] = s.w.ys[i];
@@ -208,7 +210,8 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
     for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
         reinterpret_cast<double*>(a.saved_smem)[k] = reinterpret_cast<const double*>(smem)[k];
     if (threadIdx.x == 0) {
-        a.state->nw = s.nw; a.state->have_W = s.have_W; a.state->sinv_valid = s.sinv_valid;
+        *a.mats = mt;
+        a.state->nw = s.nw; a.state->have_W = s.have_W; a.state->tinv_valid = s.tinv_valid;
         a.state->infeasible = infeasible; a.state->iterations = iters; a.state->flag = flag;
     }
 }
@@ -225,7 +228,7 @@ struct lcqp_cuda_handle_s {
     lcqp_cuda_options opts;
     int batch = 0;
     unsigned shared_mask = 0;
-    bool loaded = false, ran = false, owns_inputs = false;
+    bool loaded = false, ran = false;
     const double* dev_in[LCQP_NUM_ARRAYS] = {};
     double* own_in[LCQP_NUM_ARRAYS] = {};
     size_t own_in_cap[LCQP_NUM_ARRAYS] = {};
@@ -233,10 +236,15 @@ struct lcqp_cuda_handle_s {
     double* yout = nullptr;
     lcqp_cuda_stats* stats = nullptr;
     unsigned int* counter = nullptr;
-    double* shared_prep = nullptr;
-    size_t shared_prep_cap = 0;
-    signed char* shared_ctype = nullptr;
-    int* shared_status = nullptr;
+    double* shared_store = nullptr;
+    size_t shared_store_cap = 0;
+    Mats* shared_mats = nullptr;
+    RawOps* shared_raw = nullptr;
+    int* pool_i = nullptr;
+    double* pool_d = nullptr;
+    size_t pool_cap = 0;
+    int* pool_used = nullptr;
+    Mats* host_mats = nullptr;  // pinned read-back of the prepared header (mE, status)
     double* workspace = nullptr;
     size_t workspace_cap = 0;
     int num_sms = 0;
@@ -244,6 +252,7 @@ struct lcqp_cuda_handle_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
     cudaStream_t last_stream = nullptr;
     unsigned long long instance_offset = 0;
+    int last_grid = 0, last_smem = 0, last_mE = 0;
     std::string err;
 };
 
@@ -272,6 +281,8 @@ static int fail(lcqp_cuda_handle h, int code, const char* what, cudaError_t e = 
 }
 
 #define CK(call, code) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(h, code, #call, e_); } while (0)
+
+static size_t prep_smem_bytes(const Dims& d) { return (2ull * d.n + 5ull * d.m) * sizeof(double) + d.m + 64; }
 
 extern "C" {
 
@@ -327,8 +338,10 @@ int lcqp_cuda_create(int nV, int nC, int nComp, int batch_capacity, int device, 
               cudaMalloc(&h->yout, sizeof(double) * nD * (size_t)batch_capacity) == cudaSuccess &&
               cudaMalloc(&h->stats, sizeof(lcqp_cuda_stats) * (size_t)batch_capacity) == cudaSuccess &&
               cudaMalloc(&h->counter, sizeof(unsigned int)) == cudaSuccess &&
-              cudaMalloc(&h->shared_status, sizeof(int)) == cudaSuccess &&
-              cudaMalloc(&h->shared_ctype, nD + (size_t)nV + 16) == cudaSuccess &&
+              cudaMalloc(&h->shared_mats, sizeof(Mats)) == cudaSuccess &&
+              cudaMalloc(&h->shared_raw, sizeof(RawOps)) == cudaSuccess &&
+              cudaMalloc(&h->pool_used, 2 * sizeof(int)) == cudaSuccess &&
+              cudaMallocHost(&h->host_mats, sizeof(Mats)) == cudaSuccess &&
               cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess &&
               cudaEventCreate(&h->ev2) == cudaSuccess;
     if (!ok) { cudaGetLastError(); lcqp_cuda_destroy(h); return LCQP_CUDA_OUT_OF_MEMORY; }
@@ -342,7 +355,9 @@ int lcqp_cuda_destroy(lcqp_cuda_handle h)
     cudaSetDevice(h->device);
     for (int k = 0; k < LCQP_NUM_ARRAYS; k++) if (h->own_in[k]) cudaFree(h->own_in[k]);
     cudaFree(h->xout); cudaFree(h->yout); cudaFree(h->stats); cudaFree(h->counter);
-    cudaFree(h->shared_prep); cudaFree(h->shared_ctype); cudaFree(h->shared_status); cudaFree(h->workspace);
+    cudaFree(h->shared_store); cudaFree(h->shared_mats); cudaFree(h->shared_raw);
+    cudaFree(h->pool_i); cudaFree(h->pool_d); cudaFree(h->pool_used); cudaFree(h->workspace);
+    if (h->host_mats) cudaFreeHost(h->host_mats);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
@@ -437,36 +452,85 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     KernelArgs a;
     memset(&a, 0, sizeof(a));
     Dims& d = a.d;
-    d.n = h->nV; d.nC = h->nC; d.nComp = h->nComp; d.mA = h->nC + 2 * h->nComp;
-    d.has_box = (h->opts.qpSolver != 2) && (h->dev_in[LCQP_LB] || h->dev_in[LCQP_UB]);
-    d.m = d.mA + (d.has_box ? d.n : 0);
-    d.cap = d.m < d.n + 16 ? d.m : d.n + 16;
+    d = make_dims(h->nV, h->nC, h->nComp, (h->opts.qpSolver != 2) && (h->dev_in[LCQP_LB] || h->dev_in[LCQP_UB]));
     a.o = h->opts;
     for (int k = 0; k < LCQP_NUM_ARRAYS; k++) {
         a.arr[k] = h->dev_in[k];
         a.stride[k] = ((h->shared_mask >> k) & 1u) ? 0ull : (unsigned long long)field_len(k, h->nV, h->nC, h->nComp);
     }
     a.batch = h->batch;
+    const unsigned all_bits = (1u << LCQP_NUM_ARRAYS) - 1u;
+    a.shared_mask = (h->batch == 1) ? all_bits : h->shared_mask;
     const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (h->nC > 0 ? (1u << LCQP_A) : 0u);
-    a.mats_shared = ((h->shared_mask & mat_bits) == mat_bits) || h->batch == 1;
-    a.sinv_in_smem = work_bytes(d, true) <= kSinvSmemBudget;
-    const size_t smem = work_bytes(d, a.sinv_in_smem != 0);
-    if (smem > kSmemMax) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
+    a.mats_shared = ((a.shared_mask & mat_bits) == mat_bits);
 
-    // grid: persistent CTAs, as many as are co-resident
+    // batch-level store: Mats backing store + CSR pool
+    const size_t md = mats_doubles(d);
+    if (md > h->shared_store_cap) {
+        if (h->shared_store) cudaFree(h->shared_store);
+        h->shared_store = nullptr; h->shared_store_cap = 0;
+        if (cudaMalloc(&h->shared_store, md * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(shared store)"); }
+        h->shared_store_cap = md;
+    }
+    const size_t pool_cap = (size_t)d.n * d.n + (size_t)d.m * d.n + (size_t)d.nComp * d.n + (size_t)d.nC * d.n / 4 + 32ull * (d.m + d.n) + 1024;
+    if (pool_cap > h->pool_cap) {
+        if (h->pool_i) cudaFree(h->pool_i);
+        if (h->pool_d) cudaFree(h->pool_d);
+        h->pool_i = nullptr; h->pool_d = nullptr; h->pool_cap = 0;
+        if (cudaMalloc(&h->pool_i, pool_cap * sizeof(int)) != cudaSuccess || cudaMalloc(&h->pool_d, pool_cap * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(csr pool)");
+        }
+        h->pool_cap = pool_cap;
+    }
+    a.shared_mats = h->shared_mats;
+    a.shared_raw = h->shared_raw;
+    a.shared_mats_store = h->shared_store;
+    a.pool.ibuf = h->pool_i; a.pool.dbuf = h->pool_d; a.pool.icap = (int)h->pool_cap; a.pool.dcap = (int)h->pool_cap; a.pool.used = h->pool_used;
+    a.xout = h->xout; a.yout = h->yout; a.stats = h->stats; a.counter = h->counter;
+    a.instance_offset = h->instance_offset;
+
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
+    {
+        const size_t psm = prep_smem_bytes(d);
+        if (psm > kSmemMax) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget (prepare)");
+        CK(cudaFuncSetAttribute(prepare_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm), LCQP_CUDA_LAUNCH_FAILED);
+        prepare_shared_kernel<<<1, kPrepThreads, psm, stream>>>(a);
+        h->launches++;
+        CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
+    }
+    int mE = -1;
+    if (a.mats_shared) {
+        // the order of the static equality block decides the shared-memory plan: read the header back
+        CK(cudaMemcpyAsync(h->host_mats, h->shared_mats, sizeof(Mats), cudaMemcpyDeviceToHost, stream), LCQP_CUDA_LAUNCH_FAILED);
+        CK(cudaStreamSynchronize(stream), LCQP_CUDA_LAUNCH_FAILED);
+        mE = h->host_mats->mE;
+        if (h->host_mats->status == 0) shrink_dims(d, mE);
+    }
+    h->last_mE = mE;
+    CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
+
+    // shared-memory plan: aim at two resident CTAs per SM, fall back to one
+    SmemPlan plan = make_plan(d, kSmemSM / 2 - 1024);
+    if (!(plan.tinv_in_smem && plan.outer_in_smem)) {
+        const SmemPlan p1 = make_plan(d, kSmemMax);
+        if (p1.tinv_in_smem && !plan.tinv_in_smem) plan = p1;
+    }
+    if (plan.bytes > kSmemMax) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
+    a.plan = plan;
+    const size_t smem = plan.bytes;
     CK(cudaFuncSetAttribute(lcqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
-    CK(cudaFuncSetAttribute(prepare_shared_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_solve_kernel, kThreads, smem), LCQP_CUDA_LAUNCH_FAILED);
     if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
     int grid = per_sm * h->num_sms;
     if (grid > h->batch) grid = h->batch;
 
-    // workspaces
-    const size_t pd = prep_doubles(d);
-    a.ws_prep_doubles = a.mats_shared ? 0 : pd;
-    a.ws_stride = a.ws_prep_doubles + (a.sinv_in_smem ? 0 : (size_t)d.cap * d.cap);
-    const size_t ws_total = a.ws_stride * (size_t)grid + (size_t)d.cap * d.cap;  // + one S^-1 for the prepare CTA
+    // per-CTA global scratch
+    a.ws_mats_doubles = a.mats_shared ? 0 : md;
+    a.ws_stride = a.ws_mats_doubles + plan.gl_doubles;
+    const size_t ws_total = a.ws_stride * (size_t)grid;
     if (ws_total > h->workspace_cap) {
         if (h->workspace) cudaFree(h->workspace);
         h->workspace = nullptr; h->workspace_cap = 0;
@@ -474,46 +538,14 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
         h->workspace_cap = ws_total;
     }
     a.workspace = h->workspace;
-    if (a.mats_shared) {
-        if (pd > h->shared_prep_cap) {
-            if (h->shared_prep) cudaFree(h->shared_prep);
-            h->shared_prep = nullptr; h->shared_prep_cap = 0;
-            if (cudaMalloc(&h->shared_prep, pd * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(shared prep)"); }
-            h->shared_prep_cap = pd;
-        }
-        double* base = h->shared_prep;
-        const size_t n = d.n, m = d.m;
-        a.shared_prep.P = base; base += n * n;
-        a.shared_prep.A = base; base += m * n;
-        a.shared_prep.D = base; base += n;
-        a.shared_prep.E = base; base += m;
-        a.shared_prep.Hinv = base; base += n * n;
-        a.shared_prep.G = base; base += m * m;
-        a.shared_prep.Minv = base; base += n * n;
-        a.shared_prep.T = base;
-    }
-    a.shared_ctype = h->shared_ctype;
-    a.shared_status = h->shared_status;
-    a.xout = h->xout; a.yout = h->yout; a.stats = h->stats; a.counter = h->counter;
-    a.instance_offset = h->instance_offset;
 
-    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream), LCQP_CUDA_LAUNCH_FAILED);
-    CK(cudaMemsetAsync(h->shared_status, 0, sizeof(int), stream), LCQP_CUDA_LAUNCH_FAILED);
-    CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
-    if (a.mats_shared) {
-        KernelArgs ap = a;
-        // the prepare CTA uses the tail of the workspace for its S^-1 scratch when that is not in shared memory
-        ap.workspace = h->workspace + a.ws_stride * (size_t)grid;
-        ap.ws_prep_doubles = 0;
-        prepare_shared_kernel<<<1, kThreads, smem, stream>>>(ap);
-        h->launches++;
-    }
-    CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
     lcqp_solve_kernel<<<grid, kThreads, smem, stream>>>(a);
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
     h->last_stream = stream;
+    h->last_grid = grid;
+    h->last_smem = (int)smem;
     h->ran = true;
     return LCQP_CUDA_OK;
 }
@@ -582,6 +614,16 @@ int lcqp_cuda_last_run_ms(lcqp_cuda_handle h, float* solve_ms, float* total_ms)
     return LCQP_CUDA_OK;
 }
 
+int lcqp_cuda_last_launch_info(lcqp_cuda_handle h, int* grid, int* smem_bytes, int* equality_rows)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!h->ran) return fail(h, LCQP_CUDA_NOT_RUN, "launch info before run");
+    if (grid) *grid = h->last_grid;
+    if (smem_bytes) *smem_bytes = h->last_smem;
+    if (equality_rows) *equality_rows = h->last_mE;
+    return LCQP_CUDA_OK;
+}
+
 const char* lcqp_cuda_last_error(lcqp_cuda_handle h) { return h ? h->err.c_str() : "bad handle"; }
 
 // ---- plugin door ---------------------------------------------------------------------------------
@@ -590,8 +632,9 @@ struct lcqp_cuda_qp_s {
     lcqp_cuda_options opts;
     double *Q = nullptr, *A = nullptr;
     double* stage = nullptr;  // g n | lbA mA | ubA mA | lb n | ub n | x0 n | y0 n+mA
-    double* prep = nullptr;
-    double* sinv = nullptr;
+    double* mats_store = nullptr;
+    Mats* mats = nullptr;
+    double* gl = nullptr;
     unsigned char* saved = nullptr;
     QPState* state = nullptr;
     double* xout = nullptr;
@@ -600,6 +643,18 @@ struct lcqp_cuda_qp_s {
     bool initialised = false;
     long long launches = 0;
 };
+
+static Dims qp_dims(int nV, int nCtot, int has_box)
+{
+    Dims d = make_dims(nV, 0, 0, has_box);
+    d.nC = nCtot; d.mA = nCtot;
+    d.m = d.mA + (has_box ? d.n : 0);
+    d.ldE = d.m < d.n ? d.m : d.n;
+    d.capE = d.ldE > 0 ? d.ldE : 1;
+    d.cap = d.m < d.n + 8 ? d.m : d.n + 8;
+    if (d.cap < 1) d.cap = 1;
+    return d;
+}
 
 int lcqp_cuda_qp_create(int nV, int nCtot, const double* Q, const double* A, int device, lcqp_cuda_qp* out)
 {
@@ -615,13 +670,15 @@ int lcqp_cuda_qp_create(int nV, int nCtot, const double* Q, const double* A, int
     q->nV = nV; q->nCtot = nCtot; q->device = device;
     lcqp_cuda_default_options(&q->opts);
     cudaSetDevice(device);
-    const size_t n = nV, mA = nCtot, m = mA + n;
-    Dims d; d.n = nV; d.nC = nCtot; d.nComp = 0; d.mA = nCtot; d.has_box = 1; d.m = (int)m; d.cap = (int)(m < n + 16 ? m : n + 16);
+    const size_t n = nV, mA = nCtot;
+    const Dims d = qp_dims(nV, nCtot, 1);  // the larger of the two layouts
+    const SmemPlan plan = make_plan(d, 0);  // everything optional goes to global scratch
     bool ok = cudaMalloc(&q->Q, n * n * 8) == cudaSuccess && cudaMalloc(&q->A, (mA * n + 1) * 8) == cudaSuccess &&
               cudaMalloc(&q->stage, (5 * n + 3 * mA + 8) * 8) == cudaSuccess &&
-              cudaMalloc(&q->prep, prep_doubles(d) * 8) == cudaSuccess &&
-              cudaMalloc(&q->sinv, (size_t)d.cap * d.cap * 8) == cudaSuccess &&
-              cudaMalloc(&q->saved, work_bytes(d, false) + 64) == cudaSuccess &&
+              cudaMalloc(&q->mats_store, mats_doubles(d) * 8) == cudaSuccess &&
+              cudaMalloc(&q->mats, sizeof(Mats)) == cudaSuccess &&
+              cudaMalloc(&q->gl, (plan.gl_doubles + 1) * 8) == cudaSuccess &&
+              cudaMalloc(&q->saved, plan.bytes + 64) == cudaSuccess &&
               cudaMalloc(&q->state, sizeof(QPState)) == cudaSuccess &&
               cudaMalloc(&q->xout, n * 8) == cudaSuccess && cudaMalloc(&q->yout, (n + mA) * 8) == cudaSuccess;
     if (ok) ok = cudaMemcpy(q->Q, Q, n * n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -636,7 +693,7 @@ int lcqp_cuda_qp_destroy(lcqp_cuda_qp q)
 {
     if (!q) return LCQP_CUDA_BAD_HANDLE;
     cudaSetDevice(q->device);
-    cudaFree(q->Q); cudaFree(q->A); cudaFree(q->stage); cudaFree(q->prep); cudaFree(q->sinv);
+    cudaFree(q->Q); cudaFree(q->A); cudaFree(q->stage); cudaFree(q->mats_store); cudaFree(q->mats); cudaFree(q->gl);
     cudaFree(q->saved); cudaFree(q->state); cudaFree(q->xout); cudaFree(q->yout);
     delete q;
     return LCQP_CUDA_OK;
@@ -662,10 +719,7 @@ int lcqp_cuda_qp_solve(lcqp_cuda_qp q, int initialSolve, int* iterations, int* e
     if (initialSolve) q->has_box = (lb || ub) ? 1 : 0;
     QPKernelArgs a;
     memset(&a, 0, sizeof(a));
-    Dims& d = a.d;
-    d.n = q->nV; d.nC = q->nCtot; d.nComp = 0; d.mA = q->nCtot; d.has_box = q->has_box;
-    d.m = d.mA + (d.has_box ? d.n : 0);
-    d.cap = d.m < d.n + 16 ? d.m : d.n + 16;
+    a.d = qp_dims(q->nV, q->nCtot, q->has_box);
     a.o = q->opts;
     double* st = q->stage;
     double* d_g = st; st += n;
@@ -684,23 +738,13 @@ int lcqp_cuda_qp_solve(lcqp_cuda_qp q, int initialSolve, int* iterations, int* e
     // the QP's bounds are those given at the initial solve (LCQPow never changes them between calls)
     if (initialSolve) { a.in.lbA = lbA ? d_lbA : nullptr; a.in.ubA = ubA ? d_ubA : nullptr; a.in.lb = lb ? d_lb : nullptr; a.in.ub = ub ? d_ub : nullptr;
                         a.in.x0 = x0 ? d_x0 : nullptr; a.in.y0 = y0 ? d_y0 : nullptr; }
-    {
-        double* base = q->prep;
-        const size_t m = d.m;
-        a.pr.P = base; base += n * n;
-        a.pr.A = base; base += m * n;
-        a.pr.D = base; base += n;
-        a.pr.E = base; base += m;
-        a.pr.Hinv = base; base += n * n;
-        a.pr.G = base; base += m * m;
-        a.pr.Minv = base; base += n * n;
-        a.pr.T = base;
-    }
-    a.sinv = q->sinv;
+    a.plan = make_plan(a.d, 0);
+    if (a.plan.bytes > kSmemMax) return LCQP_CUDA_TOO_LARGE;
+    a.mats_store = q->mats_store;
+    a.mats = q->mats;
+    a.gl = q->gl;
     a.saved_smem = q->saved;
-    const size_t smem = work_bytes(d, false);
-    if (smem > kSmemMax) return LCQP_CUDA_TOO_LARGE;
-    a.smem_bytes = (smem + 7) / 8 * 8;
+    a.smem_bytes = (a.plan.bytes + 7) / 8 * 8;
     a.state = q->state;
     a.xout = q->xout; a.yout = q->yout;
     a.initial = initialSolve ? 1 : 0;

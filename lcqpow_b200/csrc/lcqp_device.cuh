@@ -3,9 +3,10 @@
 // One CTA owns one LCQP instance from loadLCQP to the stationarity classification: the whole
 // penalty-homotopy loop of LCQProblem::runSolver (/root/reference/src/LCQProblem.cpp:444-560) and the
 // convex QP under it run inside one persistent kernel; instances are pulled from a global work counter.
-// Per-instance iterates, bounds, working set and (when it fits) the inverse Schur complement live in
-// shared memory; matrices are streamed from global memory, where the operands shared by a batch
-// (Q, A, L, R and everything prepared from them) stay L2-resident.
+// Per-instance iterates, bounds, working set and the inverse Schur complement of the working set live in
+// shared memory; the operators (matrices) are applied from global memory, where everything that a batch
+// shares (Q, A, L, R and all that is prepared from them) stays L2-resident and -- when it is sparse --
+// is applied in CSR form.
 //
 // The convex QP  min 1/2 x'Px + q'x  s.t. l <= Ahat x <= u  is solved EXACTLY (the contract of the
 // reference's qpOASES subsolver):
@@ -13,18 +14,22 @@
 //       (P + sigma I + A'RA) xt = sigma x - q + A'(R z - y),  zt = A xt        (osqp auxil.c:161-225)
 //     with the matrix inverted once per instance (or once per batch when Q/A/L/R are shared), probing
 //     the active set every qp_check_interval iterations                        (osqp polish.c:33-49);
-//   phase 2: primal active-set iteration on the regularised KKT system
-//       [P + dI, Aw'; Aw, -dI]                                                 (osqp polish.c:232-300)
-//     solved by block elimination through Hinv = (P+dI)^-1 and S = G[W,W] + dI, G = A Hinv A'; both
-//     Hinv and G are working-set independent, so a working-set change is a gather from G plus an
-//     O(|W|^2) bordering update of the explicit S^-1; every solve is iteratively refined against the
-//     unregularised system                                                     (osqp polish.c:134-181);
-//   later QPs of the instance hot-start phase 2 from the previous optimum and working set (the
-//   analogue of qpOASES' hotstart, /root/reference/src/SubsolverQPOASES.cpp:154-160).
+//   phase 2: primal active-set iteration.  Every pass solves the regularised KKT system
+//       [P + dI, Aw'; Aw, -dI] [dx; dlam] = residual of the unregularised system (osqp polish.c:134-181, :232-300)
+//     from the CURRENT point, tests the step against the inactive rows (ratio test) and either adds the
+//     blocking row or takes the step; at a converged point the multiplier signs decide (drop or accept).
+//     The KKT solve is a block elimination with three levels, all but the last working-set independent:
+//       Hinv = (P+dI)^-1                      (n x n, prepared once)
+//       SEinv = (A_E Hinv A_E' + dI)^-1       (rows E that are equalities l = u: always active, prepared once)
+//       Tinv  = (T[W,W] + dI)^-1,  T = A_I Hk A_I',  Hk = Hinv - Hinv A_E' SEinv A_E Hinv
+//     Only Tinv (order = number of active INEQUALITY rows) is per instance; it is kept as an explicit packed
+//     symmetric inverse in shared memory and updated by bordering in O(|W|^2) per working-set change.
+//   later QPs of the instance hot-start phase 2 from the previous optimum, multipliers and working set
+//   (the analogue of qpOASES' hotstart, /root/reference/src/SubsolverQPOASES.cpp:154-160).
 // A QP solution is only accepted when it satisfies the KKT conditions of the full QP.
 //
-// The file also compiles as plain single-threaded C++ (LCQP_HOST_EMU) -- a debugging aid used from
-// scratch builds in the GPU-less dev container; the product never builds or calls that variant.
+// The file also compiles as plain single-threaded C++ (LCQP_HOST_EMU): tests/emu builds that variant so
+// that the CPU test-suite covers the kernel's logic; the product never builds or calls it.
 #pragma once
 
 #include <math.h>
@@ -36,8 +41,9 @@
 #endif
 
 #ifdef LCQP_HOST_EMU
-#define LCQ_DEV
-#define LCQ_DEVN
+#define LCQ_DEV static inline
+#define LCQ_DEVN static
+#define LCQ_HD
 #define LCQ_TID 0
 #define LCQ_NT 1
 #define LCQ_LANE 0
@@ -48,6 +54,7 @@
 #else
 #define LCQ_DEV __device__ __forceinline__
 #define LCQ_DEVN __device__ __noinline__
+#define LCQ_HD __host__ __device__
 #define LCQ_TID ((int)threadIdx.x)
 #define LCQ_NT ((int)blockDim.x)
 #define LCQ_LANE ((int)(threadIdx.x & 31))
@@ -71,20 +78,63 @@ constexpr double kMaxScaling = 1e4;
 constexpr int kScalingIters = 10;        // constants.h:56
 constexpr int kMaxLeyffer = 16;
 constexpr double kResTol = 1e-9;         // residual of an EQP solve that still counts as solved
+constexpr int kLongRow = 32;             // CSR rows longer than this are reduced by a warp
 
 enum { RET_OK = 0, RET_INVALID_OSQP_BOX = 110, RET_INVALID_LOWER_COMP = 120, RET_MAX_ITER = 200, RET_MAX_PEN = 201,
        RET_SUBPROBLEM = 203, RET_OSQP_GUESS = 208 };
 
-// Prepared (scaled) operands of the QP: depend on Q, A_full and the row types only.
-struct Prep {
-    double* P;     // n*n   D Q D
-    double* A;     // m*n   E Ahat D
-    double* D;     // n
-    double* E;     // m
-    double* Hinv;  // n*n   (P + delta I)^-1
-    double* G;     // m*m   A Hinv A'
-    double* Minv;  // n*n   (P + sigma I + A' R A)^-1
-    double* T;     // m*n   scratch (A Hinv)
+// ------------------------------------------------------------------------------------------------
+// A linear operator y = M v, M logically rows x cols.
+//   rp != null : CSR (rp[rows+1], ci, va); rows with more than kLongRow entries are also listed in lrows
+//   else trans == 0 : dense row-major, M[r][c] = dense[r*ld + c]
+//   else            : the transpose of a dense row-major matrix, M[r][c] = dense[c*ld + r]
+// ------------------------------------------------------------------------------------------------
+struct Op {
+    const double* dense;
+    const int* rp;
+    const int* ci;
+    const double* va;
+    const int* lrows;
+    int rows, cols, ld, trans, nlong;
+};
+
+LCQ_DEV Op dense_op(const double* M, int rows, int cols, int ld, int trans)
+{
+    Op o;
+    o.dense = M; o.rp = nullptr; o.ci = nullptr; o.va = nullptr; o.lrows = nullptr;
+    o.rows = rows; o.cols = cols; o.ld = ld; o.trans = trans; o.nlong = 0;
+    return o;
+}
+
+// Prepared (scaled) operands of the QP: depend on Q, A_full, the row types and the options only.
+struct Mats {
+    double* P;      // n*n   D Q D
+    double* A;      // m*n   E Ahat D
+    double* D;      // n
+    double* E;      // m
+    double* Hinv;   // n*n   (P + delta I)^-1
+    double* AH;     // m*n   A Hinv
+    double* T;      // m*m   A Hinv A', then the equality rows eliminated (see prepare_factor)
+    double* Minv;   // n*n   (P + sigma I + A' R A)^-1
+    double* SEinv;  // ldE*ldE (leading dimension d.ldE), order mE
+    int* eidx;      // equality rows that are always in the working set (mE of them)
+    signed char* ctype;  // m: -1 free row, 0 inequality, 1 equality, 2 equality found dependent (never active)
+    int mE;
+    int status;     // 0 ok, 1 factorisation failed
+    Op oP, oA, oAt, oHinv, oAH, oAHt, oMinv;
+};
+
+// Operators on the UNSCALED matrices, used by the outer loop.
+struct RawOps {
+    Op Q, L, R, Lt, Rt, At;   // At: nV x nC
+};
+
+// Bump allocator over global memory for the CSR copies built on the device.
+struct CsrPool {
+    int* ibuf;
+    double* dbuf;
+    int icap, dcap;
+    int* used;   // [0] ints used, [1] doubles used
 };
 
 // Unscaled instance data (global memory), loadLCQP argument order.
@@ -93,33 +143,58 @@ struct Inst {
 };
 
 struct Dims {
-    int n, nC, nComp, mA, m, has_box, cap;
+    int n, nC, nComp, mA, m, has_box;
+    int cap;    // capacity of the inequality working set (order of Tinv)
+    int ldE;    // capacity / leading dimension of the static equality block SEinv
+    int capE;   // entries of the shared-memory vectors over the equality block (mE when known, else ldE)
 };
+
+// Dimensions of a problem with nV variables, nC general rows, nComp complementarity pairs (and box rows).
+inline LCQ_HD Dims make_dims(int nV, int nC, int nComp, int has_box)
+{
+    Dims d;
+    d.n = nV; d.nC = nC; d.nComp = nComp; d.mA = nC + 2 * nComp; d.has_box = has_box;
+    d.m = d.mA + (has_box ? nV : 0);
+    d.ldE = d.m < d.n ? d.m : d.n;
+    d.capE = d.ldE > 0 ? d.ldE : 1;
+    d.cap = d.m < d.n + 8 ? d.m : d.n + 8;   // a linearly independent working set has at most n rows
+    if (d.cap < 1) d.cap = 1;
+    return d;
+}
+
+// Once the order mE of the static equality block is known the per-instance buffers shrink.
+inline LCQ_HD void shrink_dims(Dims& d, int mE)
+{
+    if (mE < 0 || mE > d.ldE) return;
+    d.capE = mE > 0 ? mE : 1;
+    const int capI = d.n - mE + 8, mI = d.m - mE;
+    d.cap = capI < mI ? capI : mI;
+    if (d.cap < 1) d.cap = 1;
+}
 
 // block-shared scalars
 struct Scalars {
-    double red[40];
-    int ired[40];
-    double bval;
+    double red[64];
+    int ired[32];
     int bidx;
     int flag;
-    int nw;
+    int pad[2];
 };
 
-// Shared-memory working set of one instance.
+// Working set of one instance (shared memory, except the outer-loop vectors and Tinv when they do not fit).
 struct Work {
     // QP (scaled space)
-    double *q, *x, *xe, *xa, *px, *r1, *t1, *t2, *dx;            // n
-    double *z, *y, *l, *u, *rhov, *lam, *r2, *dl, *dl2, *zt, *zt2, *w; // m
-    signed char *W, *Wtry, *Wfail, *ctype, *pin;                // m
-    int* idx;                                                   // m
-    double* Sinv;                                               // cap*cap (shared or global)
-    // accepted QP solution, unscaled
-    double* xs;  // n
-    double* ys;  // m   qpOASES sign
+    double *q, *x, *xa, *px, *r1, *u, *t, *dx;                      // n
+    double *z, *y, *l, *ub, *lam, *dlam, *r2, *zx, *zp, *w, *yf;    // m
+    double *dI, *lI;                                                // cap
+    double *cE, *vE;                                                // mE
+    signed char *W, *Wtry, *Wfail, *ctype, *pin;                    // m
+    int* idx;                                                       // cap: rows of the inequality working set
+    double* Tinv;                                                   // packed lower triangle, cap*(cap+1)/2
+    double* ys;                                                     // m  accepted multipliers, unscaled, qpOASES sign
     // outer loop (unscaled)
-    double *xk, *pk, *gk, *gt, *gphi, *stat, *tn;               // n
-    double *Lx, *Rx;                                            // nComp
+    double *xk, *pk, *gk, *gt, *gphi, *stat, *tn;                   // n
+    double *Lx, *Rx;                                                // nComp
     Scalars* sc;
 };
 
@@ -165,7 +240,30 @@ LCQ_DEV double block_max(double v, Scalars* sc)
     return s;
 }
 
-// block-wide argmax with deterministic tie-break (smallest index); v must be >= threshold to count.
+// two sums with one pair of barriers
+LCQ_DEV void block_sum2(double& a, double& b, Scalars* sc)
+{
+    a = warp_sum(a);
+    b = warp_sum(b);
+    LCQ_SYNC();
+    if (LCQ_LANE == 0) { sc->red[LCQ_WARP] = a; sc->red[32 + LCQ_WARP] = b; }
+    LCQ_SYNC();
+    double s = 0, t = 0;
+    for (int k = 0; k < LCQ_NWARP; k++) { s += sc->red[k]; t += sc->red[32 + k]; }
+    a = s; b = t;
+}
+
+// block-wide OR of small non-negative ints
+LCQ_DEV int block_or(int v, Scalars* sc)
+{
+#ifndef LCQP_HOST_EMU
+    v = __syncthreads_or(v);
+#endif
+    (void)sc;
+    return v;
+}
+
+// block-wide argmax with deterministic tie-break (smallest index); entries with i < 0 do not count.
 // Returns index (or -1) to all threads and the value through *vout.
 LCQ_DEV int block_argmax(double v, int i, double* vout, Scalars* sc)
 {
@@ -190,8 +288,69 @@ LCQ_DEV int block_argmax(double v, int i, double* vout, Scalars* sc)
     return bi;
 }
 
-// out[r] = sum_c M[r*ld + c] v[c]   (one warp per row, lanes over columns: coalesced row reads)
-LCQ_DEV void mv_rows(const double* __restrict__ M, int rows, int cols, int ld, const double* v, double* out)
+// ------------------------------------------------------------------------------------------------
+// operator application
+// ------------------------------------------------------------------------------------------------
+// out[r] = (init ? init[r] : 0) + scale * sum_c M[r][c] v[c]      (no barrier inside)
+LCQ_DEV void op_mv(const Op& op, const double* v, const double* init, double scale, double* out)
+{
+    if (op.rp) {
+        for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
+            const int k0 = op.rp[r], k1 = op.rp[r + 1];
+            if (k1 - k0 > kLongRow && LCQ_LANES > 1) continue;
+            double s = 0;
+            for (int k = k0; k < k1; k++) s += op.va[k] * v[op.ci[k]];
+            out[r] = (init ? init[r] : 0.0) + scale * s;
+        }
+        if (LCQ_LANES > 1)
+            for (int a = LCQ_WARP; a < op.nlong; a += LCQ_NWARP) {
+                const int r = op.lrows[a];
+                double s = 0;
+                for (int k = op.rp[r] + LCQ_LANE; k < op.rp[r + 1]; k += LCQ_LANES) s += op.va[k] * v[op.ci[k]];
+                s = warp_sum(s);
+                if (LCQ_LANE == 0) out[r] = (init ? init[r] : 0.0) + scale * s;
+            }
+    } else if (!op.trans) {
+        for (int r = LCQ_WARP; r < op.rows; r += LCQ_NWARP) {
+            const double* row = op.dense + (size_t)r * op.ld;
+            double s = 0;
+            for (int c = LCQ_LANE; c < op.cols; c += LCQ_LANES) s += row[c] * v[c];
+            s = warp_sum(s);
+            if (LCQ_LANE == 0) out[r] = (init ? init[r] : 0.0) + scale * s;
+        }
+    } else {
+        for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
+            double s = 0;
+            for (int c = 0; c < op.cols; c++) s += op.dense[(size_t)c * op.ld + r] * v[c];
+            out[r] = (init ? init[r] : 0.0) + scale * s;
+        }
+    }
+}
+
+// out[a] = sum_c M[idx[a]][c] v[c] - (sub ? sub[idx[a]] : 0)   for a < na   (rows selected by idx; op not transposed)
+LCQ_DEV void op_mv_rows(const Op& op, const int* idx, int na, const double* v, const double* sub, double* out)
+{
+    if (op.rp) {
+        for (int a = LCQ_TID; a < na; a += LCQ_NT) {
+            const int r = idx[a];
+            double s = 0;
+            for (int k = op.rp[r]; k < op.rp[r + 1]; k++) s += op.va[k] * v[op.ci[k]];
+            out[a] = s - (sub ? sub[r] : 0.0);
+        }
+    } else {
+        for (int a = LCQ_WARP; a < na; a += LCQ_NWARP) {
+            const int r = idx[a];
+            const double* row = op.dense + (size_t)r * op.ld;
+            double s = 0;
+            for (int c = LCQ_LANE; c < op.cols; c += LCQ_LANES) s += row[c] * v[c];
+            s = warp_sum(s);
+            if (LCQ_LANE == 0) out[a] = s - (sub ? sub[r] : 0.0);
+        }
+    }
+}
+
+// plain dense mat-vec with a leading dimension (one warp per row)
+LCQ_DEV void mv_dense(const double* __restrict__ M, int rows, int cols, int ld, const double* v, double* out)
 {
     for (int r = LCQ_WARP; r < rows; r += LCQ_NWARP) {
         const double* row = M + (size_t)r * ld;
@@ -202,35 +361,17 @@ LCQ_DEV void mv_rows(const double* __restrict__ M, int rows, int cols, int ld, c
     }
 }
 
-// out[c] = init[c] (or 0) + scale * sum_r M[r*ld + c] w[r]   (one thread per column: coalesced across threads)
-LCQ_DEV void mv_cols(const double* __restrict__ M, int rows, int cols, int ld, const double* w, const double* init, double scale, double* out)
-{
-    for (int c = LCQ_TID; c < cols; c += LCQ_NT) {
-        double s = 0;
-        for (int r = 0; r < rows; r++) s += M[(size_t)r * ld + c] * w[r];
-        out[c] = (init ? init[c] : 0.0) + scale * s;
-    }
-}
+// ---- packed symmetric matrix (lower triangle, row-major): S(a,b), b <= a, at a(a+1)/2 + b ----------------
+LCQ_DEV size_t pidx(int a, int b) { return a >= b ? (size_t)a * (a + 1) / 2 + b : (size_t)b * (b + 1) / 2 + a; }
 
-// out[a] = sum_c M[idx[a]*ld + c] v[c]  for a < na  (rows selected by idx)
-LCQ_DEV void mv_rows_idx(const double* __restrict__ M, const int* idx, int na, int cols, int ld, const double* v, double* out)
+// out[a] = sum_b S(a,b) v[b]
+LCQ_DEV void sym_mv(const double* S, int nw, const double* v, double* out)
 {
-    for (int a = LCQ_WARP; a < na; a += LCQ_NWARP) {
-        const double* row = M + (size_t)idx[a] * ld;
+    for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
         double s = 0;
-        for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) s += row[c] * v[c];
+        for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) s += S[pidx(a, b)] * v[b];
         s = warp_sum(s);
         if (LCQ_LANE == 0) out[a] = s;
-    }
-}
-
-// out[c] = init[c] + scale * sum_a M[idx[a]*ld + c] w[a]
-LCQ_DEV void mv_cols_idx(const double* __restrict__ M, const int* idx, int na, int cols, int ld, const double* w, const double* init, double scale, double* out)
-{
-    for (int c = LCQ_TID; c < cols; c += LCQ_NT) {
-        double s = 0;
-        for (int a = 0; a < na; a++) s += M[(size_t)idx[a] * ld + c] * w[a];
-        out[c] = (init ? init[c] : 0.0) + scale * s;
     }
 }
 
@@ -242,8 +383,9 @@ LCQ_DEV double limit_scaling(double v)
 }
 
 // In-place inversion of the SPD n x n matrix M (row-major, global memory) by Gauss-Jordan without
-// pivoting; colbuf/rowbuf are n-vectors in shared memory.  Returns 0, or 1 on a non-positive pivot.
-LCQ_DEVN int spd_invert_inplace(double* M, int n, double* colbuf, double* rowbuf, Scalars* sc)
+// pivoting; colbuf/rowbuf are n-vectors.  Returns 0, or 1 on a non-positive pivot.  Rows whose entry in
+// the pivot column is zero are left alone, so a block-diagonal matrix keeps its exact zeros.
+LCQ_DEVN int spd_invert_inplace(double* M, int n, double* colbuf, double* rowbuf)
 {
     for (int k = 0; k < n; k++) {
         LCQ_SYNC();
@@ -254,29 +396,88 @@ LCQ_DEVN int spd_invert_inplace(double* M, int n, double* colbuf, double* rowbuf
             rowbuf[j] = (j == k ? 1.0 : M[(size_t)k * n + j]) / p;
         }
         LCQ_SYNC();
-        for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
-            const int i = e / n, j = e - i * n;
-            double v;
-            if (i == k) v = rowbuf[j];
-            else v = (j == k ? 0.0 : M[e]) - colbuf[i] * rowbuf[j];
-            M[e] = v;
+        for (int i = LCQ_WARP; i < n; i += LCQ_NWARP) {
+            double* row = M + (size_t)i * n;
+            if (i == k) {
+                for (int j = LCQ_LANE; j < n; j += LCQ_LANES) row[j] = rowbuf[j];
+            } else {
+                const double ci = colbuf[i];
+                if (ci == 0.0) continue;
+                for (int j = LCQ_LANE; j < n; j += LCQ_LANES) row[j] = (j == k ? 0.0 : row[j]) - ci * rowbuf[j];
+            }
         }
     }
     LCQ_SYNC();
-    (void)sc;
     return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
-// prepare(): Ruiz equilibration (osqp scaling.c:44-156 without the q-dependent cost scale, c = 1),
-// Hinv, Minv, G.  Row types (for rho_vec, auxil.c:76-98) come from `ctype`.
-// Uses Work vectors t1,t2 (n) and zt (m) as scratch.
+// CSR construction on the device (block-cooperative).  M is rows x cols; trans: M[r][c] = src[c*ld + r].
+// Falls back to the dense operator when the matrix is not sparse enough or the pool is exhausted.
 // ------------------------------------------------------------------------------------------------
-LCQ_DEVN void prepare_scale(const Dims& d, const Inst& in, const Prep& pr, Work& w)
+LCQ_DEVN Op build_op(const double* src, int rows, int cols, int ld, int trans, CsrPool& pool, Scalars* sc)
+{
+    Op op = dense_op(src, rows, cols, ld, trans);
+    LCQ_SYNC();
+    if (LCQ_TID == 0) {
+        int off = pool.used[0];
+        if (pool.ibuf && off + rows + 1 <= pool.icap) { sc->ired[0] = off; pool.used[0] = off + rows + 1; }
+        else sc->ired[0] = -1;
+    }
+    LCQ_SYNC();
+    const int rpoff = sc->ired[0];
+    if (rpoff < 0) return op;
+    int* rp = pool.ibuf + rpoff;
+    for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
+        int c = 0;
+        for (int j = 0; j < cols; j++) c += ((trans ? src[(size_t)j * ld + r] : src[(size_t)r * ld + j]) != 0.0);
+        rp[r + 1] = c;
+    }
+    LCQ_SYNC();
+    if (LCQ_TID == 0) {
+        int tot = 0, nl = 0;
+        rp[0] = 0;
+        for (int r = 0; r < rows; r++) { const int c = rp[r + 1]; nl += (c > kLongRow); tot += c; rp[r + 1] = tot; }
+        const int io = pool.used[0], dof = pool.used[1];
+        const bool sparse = (long long)tot * 4 <= (long long)rows * cols && io + tot + nl <= pool.icap && dof + tot <= pool.dcap;
+        if (sparse) {
+            pool.used[0] = io + tot + nl;
+            pool.used[1] = dof + tot;
+            sc->ired[1] = io; sc->ired[2] = dof; sc->ired[3] = nl;
+            int* lr = pool.ibuf + io + tot;
+            int k = 0;
+            for (int r = 0; r < rows; r++) if (rp[r + 1] - rp[r] > kLongRow) lr[k++] = r;
+        } else {
+            sc->ired[1] = -1;
+            pool.used[0] = rpoff;  // give the row pointers back
+        }
+    }
+    LCQ_SYNC();
+    const int io = sc->ired[1], dof = sc->ired[2], nl = sc->ired[3];
+    if (io < 0) { LCQ_SYNC(); return op; }
+    int* ci = pool.ibuf + io;
+    double* va = pool.dbuf + dof;
+    for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
+        int k = rp[r];
+        for (int j = 0; j < cols; j++) {
+            const double v = trans ? src[(size_t)j * ld + r] : src[(size_t)r * ld + j];
+            if (v != 0.0) { ci[k] = j; va[k] = v; k++; }
+        }
+    }
+    LCQ_SYNC();
+    op.rp = rp; op.ci = ci; op.va = va; op.lrows = ci + rp[rows]; op.nlong = nl;
+    return op;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prepare: Ruiz equilibration (osqp scaling.c:44-156 without the q-dependent cost scale, c = 1), row types,
+// Hinv, Minv, AH, T, the static equality block.  Scratch: vectors n (v1, v2), m (e1, e2).
+// ------------------------------------------------------------------------------------------------
+LCQ_DEVN void prepare_scale(const Dims& d, const Inst& in, Mats& mt, double* v1, double* e1)
 {
     const int n = d.n, m = d.m, mA = d.mA, nC = d.nC, nComp = d.nComp;
     // P = Q, A = [A; L; R; I]
-    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) pr.P[e] = in.Q[e];
+    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) mt.P[e] = in.Q[e];
     for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
         const int i = e / n, j = e - i * n;
         double v;
@@ -284,103 +485,46 @@ LCQ_DEVN void prepare_scale(const Dims& d, const Inst& in, const Prep& pr, Work&
         else if (i < nC + nComp) v = in.L[(size_t)(i - nC) * n + j];
         else if (i < mA) v = in.R[(size_t)(i - nC - nComp) * n + j];
         else v = (i - mA == j) ? 1.0 : 0.0;
-        pr.A[e] = v;
+        mt.A[e] = v;
     }
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) pr.D[j] = 1.0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) pr.E[i] = 1.0;
-    double* Dt = w.t1;
-    double* Et = w.zt;
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) mt.D[j] = 1.0;
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) mt.E[i] = 1.0;
+    double* Dt = v1;
+    double* Et = e1;
     for (int it = 0; it < kScalingIters; it++) {
         LCQ_SYNC();
         for (int j = LCQ_TID; j < n; j += LCQ_NT) {
             double v = 0;
-            for (int i = 0; i < n; i++) v = fmax(v, fabs(pr.P[(size_t)i * n + j]));
-            for (int i = 0; i < m; i++) v = fmax(v, fabs(pr.A[(size_t)i * n + j]));
+            for (int i = 0; i < n; i++) v = fmax(v, fabs(mt.P[(size_t)i * n + j]));
+            for (int i = 0; i < m; i++) v = fmax(v, fabs(mt.A[(size_t)i * n + j]));
             Dt[j] = 1.0 / sqrt(limit_scaling(v));
         }
         for (int i = LCQ_WARP; i < m; i += LCQ_NWARP) {
             double v = 0;
-            for (int j = LCQ_LANE; j < n; j += LCQ_LANES) v = fmax(v, fabs(pr.A[(size_t)i * n + j]));
+            for (int j = LCQ_LANE; j < n; j += LCQ_LANES) v = fmax(v, fabs(mt.A[(size_t)i * n + j]));
             v = warp_max(v);
             if (LCQ_LANE == 0) Et[i] = 1.0 / sqrt(limit_scaling(v));
         }
         LCQ_SYNC();
         for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
             const int i = e / n, j = e - i * n;
-            pr.P[e] *= Dt[i] * Dt[j];
+            mt.P[e] *= Dt[i] * Dt[j];
         }
         for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
             const int i = e / n, j = e - i * n;
-            pr.A[e] *= Et[i] * Dt[j];
+            mt.A[e] *= Et[i] * Dt[j];
         }
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) pr.D[j] *= Dt[j];
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) pr.E[i] *= Et[i];
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) mt.D[j] *= Dt[j];
+        for (int i = LCQ_TID; i < m; i += LCQ_NT) mt.E[i] *= Et[i];
     }
     LCQ_SYNC();
 }
-
-LCQ_DEVN int prepare_factor(const Dims& d, const Prep& pr, const signed char* ctype, const lcqp_cuda_options& o, Work& w)
-{
-    const int n = d.n, m = d.m;
-    // Hinv
-    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
-        const int i = e / n, j = e - i * n;
-        pr.Hinv[e] = pr.P[e] + (i == j ? o.qp_delta : 0.0);
-    }
-    if (spd_invert_inplace(pr.Hinv, n, w.t1, w.t2, w.sc)) return 1;
-    // Minv
-    for (int i = LCQ_TID; i < m; i += LCQ_NT)
-        w.zt[i] = ctype[i] < 0 ? kRhoMin : (ctype[i] == 1 ? kRhoEqOverIneq * o.qp_rho : o.qp_rho);
-    LCQ_SYNC();
-    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
-        const int i = e / n, j = e - i * n;
-        double s = pr.P[e] + (i == j ? o.qp_sigma : 0.0);
-        for (int r = 0; r < m; r++) s += w.zt[r] * pr.A[(size_t)r * n + i] * pr.A[(size_t)r * n + j];
-        pr.Minv[e] = s;
-    }
-    if (spd_invert_inplace(pr.Minv, n, w.t1, w.t2, w.sc)) return 1;
-    // T = A Hinv, G = T A'
-    for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
-        const int i = e / n, j = e - i * n;
-        double s = 0;
-        for (int k = 0; k < n; k++) s += pr.A[(size_t)i * n + k] * pr.Hinv[(size_t)k * n + j];
-        pr.T[e] = s;
-    }
-    LCQ_SYNC();
-    for (int e = LCQ_TID; e < m * m; e += LCQ_NT) {
-        const int i = e / m, r = e - i * m;
-        if (r > i) continue;
-        double s = 0;
-        for (int k = 0; k < n; k++) s += pr.T[(size_t)i * n + k] * pr.A[(size_t)r * n + k];
-        pr.G[(size_t)i * m + r] = s;
-        pr.G[(size_t)r * m + i] = s;
-    }
-    LCQ_SYNC();
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// QP solver state machine
-// ------------------------------------------------------------------------------------------------
-struct QP {
-    Dims d;
-    Prep pr;
-    Work w;
-    const lcqp_cuda_options* o;
-    int nw;           // rows in the working set = order of Sinv (idx[0..nw))
-    int have_W;
-    int sinv_valid;   // Sinv matches idx/W
-    double eqp_res;
-    long long n_admm, n_eqp, n_changes;
-};
 
 // Bounds of A_full = [A; L; R] (+ box rows) as setConstraints / setComplementarityBounds build them
 // (/root/reference/src/LCQProblem.cpp:584-608, 745-782), scaled by E, with OSQP's row types
 // (auxil.c:76-98).  Returns bit0: some l > u, bit1: a complementarity lower bound is -inf (:747,:767).
-LCQ_DEVN int qp_set_bounds(QP& s, const Inst& in)
+LCQ_DEVN int set_bounds(const Dims& d, const Inst& in, const double* E, double* l, double* u, signed char* ctype, Scalars* sc)
 {
-    const Dims& d = s.d;
-    Work& w = s.w;
     int bad = 0;
     for (int i = LCQ_TID; i < d.m; i += LCQ_NT) {
         double lo, up;
@@ -396,41 +540,275 @@ LCQ_DEVN int qp_set_bounds(QP& s, const Inst& in)
         } else { lo = in.lb ? in.lb[i - d.mA] : -INFINITY; up = in.ub ? in.ub[i - d.mA] : INFINITY; }
         if (lo > up) bad |= 1;
         const bool linf = !(lo > -kQPInf), uinf = !(up < kQPInf);
-        const double E = s.pr.E[i];
-        w.l[i] = linf ? -INFINITY : lo * E;
-        w.u[i] = uinf ? INFINITY : up * E;
+        const double Ei = E[i];
+        l[i] = linf ? -INFINITY : lo * Ei;
+        u[i] = uinf ? INFINITY : up * Ei;
         signed char t = 0;
         if (linf && uinf) t = -1;
-        else if (!linf && !uinf && w.u[i] - w.l[i] < kRhoTol) t = 1;
-        w.ctype[i] = t;
-        w.rhov[i] = t < 0 ? kRhoMin : (t == 1 ? kRhoEqOverIneq * s.o->qp_rho : s.o->qp_rho);
+        else if (!linf && !uinf && u[i] - l[i] < kRhoTol) t = 1;
+        ctype[i] = t;
     }
-    const int b0 = block_max((double)(bad & 1), w.sc) > 0.5;
-    const int b1 = block_max((double)((bad >> 1) & 1), w.sc) > 0.5;
-    return b0 | (b1 << 1);
+    (void)sc;
+    return block_or(bad, sc);
 }
+
+LCQ_DEV double rho_of(signed char t, double rho)
+{
+    return t < 0 ? kRhoMin : (t >= 1 ? kRhoEqOverIneq * rho : rho);  // auxil.c:76-98
+}
+
+// Everything that follows the scaling.  ctype (m, row types of this instance / of instance 0 of a sharing
+// batch) is copied into mt.ctype, where equality rows found linearly dependent are re-typed 2.
+// Scratch: v1, v2 (n), e1, e2, e3 (m).
+LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, const lcqp_cuda_options& o,
+                            double* v1, double* v2, double* e1, double* e2, double* e3, Scalars* sc)
+{
+    const int n = d.n, m = d.m;
+    const double delta = o.qp_delta;
+    // Hinv
+    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
+        const int i = e / n, j = e - i * n;
+        mt.Hinv[e] = mt.P[e] + (i == j ? delta : 0.0);
+    }
+    if (spd_invert_inplace(mt.Hinv, n, v1, v2)) return 1;
+    // Minv
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) { e1[i] = rho_of(ctype[i], o.qp_rho); mt.ctype[i] = ctype[i]; }
+    LCQ_SYNC();
+    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
+        const int i = e / n, j = e - i * n;
+        mt.Minv[e] = mt.P[e] + (i == j ? o.qp_sigma : 0.0);
+    }
+    LCQ_SYNC();
+    if (mt.oA.rp) {
+        // A' R A accumulated row by row of A (rows are short); one thread per row pair product would race, so
+        // rows are processed one after the other and the (a, b) pairs of a row in parallel
+        const Op& oa = mt.oA;
+        for (int r = 0; r < m; r++) {
+            const int k0 = oa.rp[r], len = oa.rp[r + 1] - k0;
+            for (int e = LCQ_TID; e < len * len; e += LCQ_NT) {
+                const int a = e / len, b = e - a * len;
+                mt.Minv[(size_t)oa.ci[k0 + a] * n + oa.ci[k0 + b]] += e1[r] * oa.va[k0 + a] * oa.va[k0 + b];
+            }
+            LCQ_SYNC();
+        }
+    } else {
+        for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
+            const int i = e / n, j = e - i * n;
+            if (j > i) continue;
+            double s = 0;
+            for (int r = 0; r < m; r++) s += e1[r] * mt.A[(size_t)r * n + i] * mt.A[(size_t)r * n + j];
+            mt.Minv[e] += s;
+            if (j != i) mt.Minv[(size_t)j * n + i] += s;
+        }
+    }
+    if (spd_invert_inplace(mt.Minv, n, v1, v2)) return 1;
+    // AH = A Hinv, G = AH A' (into T); through the CSR rows of A when they exist (mt.oA is set by the caller)
+    const Op& oA = mt.oA;
+    for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
+        const int i = e / n, j = e - i * n;
+        double s = 0;
+        if (oA.rp) {
+            for (int k = oA.rp[i]; k < oA.rp[i + 1]; k++) s += oA.va[k] * mt.Hinv[(size_t)oA.ci[k] * n + j];
+        } else {
+            const double* ar = mt.A + (size_t)i * n;
+            for (int k = 0; k < n; k++) s += ar[k] * mt.Hinv[(size_t)k * n + j];
+        }
+        mt.AH[e] = s;
+    }
+    LCQ_SYNC();
+    if (oA.rp) {
+        for (int e = LCQ_TID; e < m * m; e += LCQ_NT) {
+            const int i = e / m, r = e - i * m;
+            if (r > i) continue;
+            const double* ah = mt.AH + (size_t)i * n;
+            double s = 0;
+            for (int k = oA.rp[r]; k < oA.rp[r + 1]; k++) s += ah[oA.ci[k]] * oA.va[k];
+            mt.T[(size_t)i * m + r] = s;
+            mt.T[(size_t)r * m + i] = s;
+        }
+    } else {
+        for (int e = LCQ_WARP; e < m * m; e += LCQ_NWARP) {
+            const int i = e / m, r = e - i * m;
+            if (r > i) continue;
+            const double* ah = mt.AH + (size_t)i * n;
+            const double* ar = mt.A + (size_t)r * n;
+            double s = 0;
+            for (int k = LCQ_LANE; k < n; k += LCQ_LANES) s += ah[k] * ar[k];
+            s = warp_sum(s);
+            if (LCQ_LANE == 0) { mt.T[(size_t)i * m + r] = s; mt.T[(size_t)r * m + i] = s; }
+        }
+    }
+    LCQ_SYNC();
+    // static equality block: greedy, in row order; SEinv by bordering (full storage, ld = mEcap).  A row whose
+    // Schur pivot is at the level of the regularisation is a combination of the rows before it: it is never
+    // put into a working set (type 2); its bounds are still checked by the KKT test.
+    const int mEcap = d.ldE;
+    int mE = 0;
+    double* Si = mt.SEinv;
+    double* sv = e1;   // G[j, E]
+    double* uu = e2;   // SEinv sv
+    for (int j = 0; j < m; j++) {
+        if (ctype[j] != 1) continue;
+        const double* Gj = mt.T + (size_t)j * m;
+        for (int a = LCQ_TID; a < mE; a += LCQ_NT) sv[a] = Gj[mt.eidx[a]];
+        LCQ_SYNC();
+        mv_dense(Si, mE, mE, mEcap, sv, uu);
+        LCQ_SYNC();
+        double p1 = 0, p2 = 0;
+        for (int a = LCQ_TID; a < mE; a += LCQ_NT) { p1 += sv[a] * uu[a]; p2 += uu[a] * uu[a]; }
+        block_sum2(p1, p2, sc);
+        const double kappa = Gj[j] + delta - p1;
+        if (mE >= mEcap || !(kappa > 10.0 * delta * (1.0 + p2))) {
+            if (LCQ_TID == 0) mt.ctype[j] = 2;
+            LCQ_SYNC();
+            continue;
+        }
+        const double ik = 1.0 / kappa;
+        for (int e = LCQ_TID; e < mE * mE; e += LCQ_NT) {
+            const int a = e / mE, b = e - a * mE;
+            Si[(size_t)a * mEcap + b] += uu[a] * uu[b] * ik;
+        }
+        for (int a = LCQ_TID; a < mE; a += LCQ_NT) {
+            Si[(size_t)a * mEcap + mE] = -uu[a] * ik;
+            Si[(size_t)mE * mEcap + a] = -uu[a] * ik;
+        }
+        if (LCQ_TID == 0) { Si[(size_t)mE * mEcap + mE] = ik; mt.eidx[mE] = j; }
+        mE++;
+        LCQ_SYNC();
+    }
+    // T <- G - G[:,E] SEinv G[E,:]   (only entries with both rows outside E are used afterwards)
+    if (mE > 0) {
+        // X = G[:,E] SEinv, row by row, kept in e3; then T[i,:] -= X[i,:] G[E,:]
+        for (int i = 0; i < m; i++) {
+            if (mt.ctype[i] == 1) continue;
+            double* Ti = mt.T + (size_t)i * m;
+            for (int a = LCQ_TID; a < mE; a += LCQ_NT) sv[a] = Ti[mt.eidx[a]];
+            LCQ_SYNC();
+            int any = 0;
+            for (int a = LCQ_TID; a < mE; a += LCQ_NT) any |= (sv[a] != 0.0);
+            any = block_or(any, sc);
+            if (!any) continue;  // row decoupled from the equality block
+            mv_dense(Si, mE, mE, mEcap, sv, e3);
+            LCQ_SYNC();
+            for (int r = LCQ_TID; r < m; r += LCQ_NT) {
+                if (mt.ctype[r] == 1) continue;
+                double s = 0;
+                for (int a = 0; a < mE; a++) s += e3[a] * mt.T[(size_t)mt.eidx[a] * m + r];
+                Ti[r] -= s;
+            }
+            LCQ_SYNC();
+        }
+    }
+    if (LCQ_TID == 0) { mt.mE = mE; mt.status = 0; }
+    LCQ_SYNC();
+    (void)uu;
+    return 0;
+}
+
+// dense operators over the prepared matrices (per-instance preparation; one thread writes) ...
+LCQ_DEV void mats_dense_ops(const Dims& d, Mats& mt)
+{
+    const int n = d.n, m = d.m;
+    mt.oP = dense_op(mt.P, n, n, n, 0);
+    mt.oA = dense_op(mt.A, m, n, n, 0);
+    mt.oAt = dense_op(mt.A, n, m, n, 1);
+    mt.oHinv = dense_op(mt.Hinv, n, n, n, 0);
+    mt.oAH = dense_op(mt.AH, m, n, n, 0);
+    mt.oAHt = dense_op(mt.AH, n, m, n, 1);
+    mt.oMinv = dense_op(mt.Minv, n, n, n, 0);
+}
+
+// ... or CSR copies where the matrix is sparse (shared preparation, done once per batch): the scaled
+// problem matrices before the factorisation (which uses oA), the prepared ones after it.  `mt` must be
+// block-shared or thread-local-identical: every thread receives the same Op values.
+LCQ_DEVN void mats_build_ops_pre(const Dims& d, Mats& mt, CsrPool& pool, Scalars* sc)
+{
+    const int n = d.n, m = d.m;
+    const Op a = build_op(mt.P, n, n, n, 0, pool, sc);
+    const Op b = build_op(mt.A, m, n, n, 0, pool, sc);
+    const Op c = build_op(mt.A, n, m, n, 1, pool, sc);
+    if (LCQ_TID == 0) { mt.oP = a; mt.oA = b; mt.oAt = c; }
+    LCQ_SYNC();
+}
+
+LCQ_DEVN void mats_build_ops_post(const Dims& d, Mats& mt, CsrPool& pool, Scalars* sc)
+{
+    const int n = d.n, m = d.m;
+    const Op a = build_op(mt.Hinv, n, n, n, 0, pool, sc);
+    const Op b = build_op(mt.AH, m, n, n, 0, pool, sc);
+    const Op c = build_op(mt.AH, n, m, n, 1, pool, sc);
+    const Op e = build_op(mt.Minv, n, n, n, 0, pool, sc);
+    if (LCQ_TID == 0) { mt.oHinv = a; mt.oAH = b; mt.oAHt = c; mt.oMinv = e; }
+    LCQ_SYNC();
+}
+
+LCQ_DEV void raw_dense_ops(const Dims& d, const Inst& in, RawOps& ro, unsigned keep_mask)
+{
+    const int n = d.n;
+    if (!(keep_mask & (1u << LCQP_Q))) ro.Q = dense_op(in.Q, n, n, n, 0);
+    if (!(keep_mask & (1u << LCQP_L))) { ro.L = dense_op(in.L, d.nComp, n, n, 0); ro.Lt = dense_op(in.L, n, d.nComp, n, 1); }
+    if (!(keep_mask & (1u << LCQP_R))) { ro.R = dense_op(in.R, d.nComp, n, n, 0); ro.Rt = dense_op(in.R, n, d.nComp, n, 1); }
+    if (!(keep_mask & (1u << LCQP_A))) ro.At = dense_op(in.A, n, d.nC, n, 1);
+}
+
+// one thread writes `ro` (block-shared)
+LCQ_DEVN void raw_build_ops(const Dims& d, const Inst& in, RawOps& ro, unsigned shared_mask, CsrPool& pool, Scalars* sc)
+{
+    const int n = d.n;
+    if (LCQ_TID == 0) raw_dense_ops(d, in, ro, 0u);
+    LCQ_SYNC();
+    if (shared_mask & (1u << LCQP_Q)) { const Op a = build_op(in.Q, n, n, n, 0, pool, sc); if (LCQ_TID == 0) ro.Q = a; }
+    if (shared_mask & (1u << LCQP_L)) {
+        const Op a = build_op(in.L, d.nComp, n, n, 0, pool, sc);
+        const Op b = build_op(in.L, n, d.nComp, n, 1, pool, sc);
+        if (LCQ_TID == 0) { ro.L = a; ro.Lt = b; }
+    }
+    if (shared_mask & (1u << LCQP_R)) {
+        const Op a = build_op(in.R, d.nComp, n, n, 0, pool, sc);
+        const Op b = build_op(in.R, n, d.nComp, n, 1, pool, sc);
+        if (LCQ_TID == 0) { ro.R = a; ro.Rt = b; }
+    }
+    if ((shared_mask & (1u << LCQP_A)) && d.nC > 0) { const Op a = build_op(in.A, n, d.nC, n, 1, pool, sc); if (LCQ_TID == 0) ro.At = a; }
+    LCQ_SYNC();
+}
+
+// ------------------------------------------------------------------------------------------------
+// QP solver state machine
+// ------------------------------------------------------------------------------------------------
+struct QP {
+    Dims d;
+    const Mats* mt;
+    Work w;
+    const lcqp_cuda_options* o;
+    int nw;           // rows in the inequality working set = order of Tinv (idx[0..nw))
+    int have_W;
+    int tinv_valid;   // Tinv matches idx/W
+    long long n_admm, n_pass, n_changes;
+};
 
 // One ADMM iteration (osqp auxil.c:161-225, condensed KKT solve).
 LCQ_DEVN void admm_iter(QP& s)
 {
     const int n = s.d.n, m = s.d.m;
     Work& w = s.w;
-    const double alpha = s.o->qp_alpha, sigma = s.o->qp_sigma;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) w.w[i] = w.rhov[i] * w.z[i] - w.y[i];
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.t1[j] = sigma * w.x[j] - w.q[j];
+    const Mats& mt = *s.mt;
+    const double alpha = s.o->qp_alpha, sigma = s.o->qp_sigma, rho = s.o->qp_rho;
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) w.w[i] = rho_of(w.ctype[i], rho) * w.z[i] - w.y[i];
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.u[j] = sigma * w.x[j] - w.q[j];
     LCQ_SYNC();
-    mv_cols(s.pr.A, m, n, n, w.w, w.t1, 1.0, w.t2);  // rhs = sigma x - q + A'w
+    op_mv(mt.oAt, w.w, w.u, 1.0, w.t);        // rhs = sigma x - q + A'w
     LCQ_SYNC();
-    mv_rows(s.pr.Minv, n, n, n, w.t2, w.xe);         // xt
+    op_mv(mt.oMinv, w.t, nullptr, 1.0, w.dx); // xt
     LCQ_SYNC();
-    mv_rows(s.pr.A, m, n, n, w.xe, w.zt);            // zt = A xt
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = alpha * w.xe[j] + (1.0 - alpha) * w.x[j];
+    op_mv(mt.oA, w.dx, nullptr, 1.0, w.zp);   // zt = A xt
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = alpha * w.dx[j] + (1.0 - alpha) * w.x[j];
     LCQ_SYNC();
     for (int i = LCQ_TID; i < m; i += LCQ_NT) {
-        const double v = alpha * w.zt[i] + (1.0 - alpha) * w.z[i];
-        double zn = v + w.y[i] / w.rhov[i];
-        zn = fmin(fmax(zn, w.l[i]), w.u[i]);
-        w.y[i] += w.rhov[i] * (v - zn);
+        const double r = rho_of(w.ctype[i], rho);
+        const double v = alpha * w.zp[i] + (1.0 - alpha) * w.z[i];
+        double zn = v + w.y[i] / r;
+        zn = fmin(fmax(zn, w.l[i]), w.ub[i]);
+        w.y[i] += r * (v - zn);
         w.z[i] = zn;
     }
     LCQ_SYNC();
@@ -442,206 +820,227 @@ LCQ_DEVN void guess_working_set(QP& s, signed char* W)
     Work& w = s.w;
     for (int i = LCQ_TID; i < s.d.m; i += LCQ_NT) {
         signed char v = 0;
-        if (w.ctype[i] == 1) v = 1;
-        else if (w.ctype[i] < 0) v = 0;
+        const signed char t = w.ctype[i];
+        if (t == 1) v = 1;
+        else if (t != 0) v = 0;
         else if (w.z[i] - w.l[i] < -w.y[i]) v = 1;
-        else if (w.u[i] - w.z[i] < w.y[i]) v = 2;
+        else if (w.ub[i] - w.z[i] < w.y[i]) v = 2;
         W[i] = v;
     }
     LCQ_SYNC();
 }
 
-// ---- explicit inverse of S = G[W,W] + delta I, maintained by bordering -------------------------
-// Append row j of the constraint matrix to the working set (position nw).  A row that is numerically a
-// combination of the rows already in the set -- Schur pivot kappa at the level of the regularisation,
-// kappa <= 10 delta (1 + u'u) -- is NOT appended (the working set is kept linearly independent, as the
-// active-set theory requires); returns 1 in that case, 0 otherwise.
-LCQ_DEVN int sinv_append(QP& s, int j)
+// ---- explicit inverse of T[W,W] + delta I (packed), maintained by bordering ------------------------
+// Append inequality row j to the working set (position nw).  A row that is numerically a combination of
+// the rows already active -- Schur pivot kappa at the level of the regularisation, kappa <= 10 delta
+// (1 + u'u) -- is NOT appended (the working set is kept linearly independent, as the active-set theory
+// requires); returns 1 in that case, 0 otherwise.  Scratch: dI, lI.
+LCQ_DEVN int tinv_append(QP& s, int j)
 {
     Work& w = s.w;
-    const int nw = s.nw, cap = s.d.cap, m = s.d.m;
-    double* Si = w.Sinv;
-    const double* Gj = s.pr.G + (size_t)j * m;
-    // sv = G[j, idx[a]]  ->  dl2 ;  u = Sinv sv -> dl
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.dl2[a] = Gj[w.idx[a]];
+    const int nw = s.nw, m = s.d.m;
+    double* Si = w.Tinv;
+    const double* Tj = s.mt->T + (size_t)j * m;
+    for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.dI[a] = Tj[w.idx[a]];
     LCQ_SYNC();
-    mv_rows(Si, nw, nw, cap, w.dl2, w.dl);
+    sym_mv(Si, nw, w.dI, w.lI);
     LCQ_SYNC();
-    double part = 0, part2 = 0;
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) { part += w.dl2[a] * w.dl[a]; part2 += w.dl[a] * w.dl[a]; }
-    const double su = block_sum(part, w.sc);
-    const double uu = block_sum(part2, w.sc);
-    const double kappa = Gj[j] + s.o->qp_delta - su;
-    if (!(kappa > 10.0 * s.o->qp_delta * (1.0 + uu))) return 1;
+    double p1 = 0, p2 = 0;
+    for (int a = LCQ_TID; a < nw; a += LCQ_NT) { p1 += w.dI[a] * w.lI[a]; p2 += w.lI[a] * w.lI[a]; }
+    block_sum2(p1, p2, w.sc);
+    const double kappa = Tj[j] + s.o->qp_delta - p1;
+    if (!(kappa > 10.0 * s.o->qp_delta * (1.0 + p2))) return 1;
     const double ik = 1.0 / kappa;
-    for (int e = LCQ_TID; e < nw * nw; e += LCQ_NT) {
-        const int a = e / nw, b = e - a * nw;
-        Si[(size_t)a * cap + b] += w.dl[a] * w.dl[b] * ik;
+    for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
+        const double ua = w.lI[a] * ik;
+        double* row = Si + (size_t)a * (a + 1) / 2;
+        for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] += ua * w.lI[b];
     }
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
-        Si[(size_t)a * cap + nw] = -w.dl[a] * ik;
-        Si[(size_t)nw * cap + a] = -w.dl[a] * ik;
+    {
+        double* row = Si + (size_t)nw * (nw + 1) / 2;
+        for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
+        if (LCQ_TID == 0) { row[nw] = ik; w.idx[nw] = j; }
     }
-    if (LCQ_TID == 0) { Si[(size_t)nw * cap + nw] = ik; w.idx[nw] = j; }
     s.nw = nw + 1;
     LCQ_SYNC();
     return 0;
 }
 
-// remove position a from the working set (last position is moved into a)
-LCQ_DEVN void sinv_remove(QP& s, int a)
+// remove position p from the working set (the last position is moved into p).  Scratch: dI, lI.
+LCQ_DEVN void tinv_remove(QP& s, int p)
 {
     Work& w = s.w;
-    const int nw = s.nw, cap = s.d.cap, last = nw - 1;
-    double* Si = w.Sinv;
-    const double c = Si[(size_t)a * cap + a];
-    for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.dl2[b] = Si[(size_t)b * cap + a];
+    const int nw = s.nw, last = nw - 1;
+    double* Si = w.Tinv;
+    for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.dI[b] = Si[pidx(b, p)];
     LCQ_SYNC();
-    const double ic = 1.0 / c;
-    for (int e = LCQ_TID; e < nw * nw; e += LCQ_NT) {
-        const int r = e / nw, b = e - r * nw;
-        Si[(size_t)r * cap + b] -= w.dl2[r] * w.dl2[b] * ic;
+    const double ic = 1.0 / w.dI[p];
+    for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
+        const double ca = w.dI[a] * ic;
+        double* row = Si + (size_t)a * (a + 1) / 2;
+        for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] -= ca * w.dI[b];
     }
     LCQ_SYNC();
-    if (a != last) {
-        // move row/col `last` into position a
-        for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.dl2[b] = Si[(size_t)last * cap + b];
+    if (p != last) {
+        for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.lI[b] = Si[pidx(last, b)];
         LCQ_SYNC();
-        for (int b = LCQ_TID; b < last; b += LCQ_NT) {
-            const double v = (b == a) ? w.dl2[last] : w.dl2[b];
-            Si[(size_t)a * cap + b] = v;
-            Si[(size_t)b * cap + a] = v;
-        }
-        if (LCQ_TID == 0) w.idx[a] = w.idx[last];
+        for (int b = LCQ_TID; b < last; b += LCQ_NT) Si[pidx(p, b)] = (b == p) ? w.lI[last] : w.lI[b];
+        if (LCQ_TID == 0) w.idx[p] = w.idx[last];
     }
     s.nw = last;
     LCQ_SYNC();
 }
 
-// Rebuild idx/Sinv from W by successive bordering; rows found linearly dependent on the rows before
-// them are taken out of W.  Returns 1 if W has more rows than Sinv can hold.
-LCQ_DEVN int sinv_build(QP& s, signed char* W)
+// Rebuild idx/Tinv from W by successive bordering; inequality rows found linearly dependent on the rows
+// before them (or beyond the capacity) are taken out of W.  Equality rows: W follows the static block.
+LCQ_DEVN void tinv_build(QP& s, signed char* W)
 {
     const int m = s.d.m;
     s.nw = 0;
-    s.sinv_valid = 0;
-    int cnt = 0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) cnt += (W[i] != 0);
-    const int total = (int)(block_sum((double)cnt, s.w.sc) + 0.5);
-    (void)total;
-    // equality rows first, then the rest in row order (W is in shared memory: uniform branches)
-    for (int pass = 0; pass < 2; pass++)
-        for (int i = 0; i < m; i++) {
-            if (!W[i] || ((s.w.ctype[i] == 1) != (pass == 0))) continue;
-            if (s.nw >= s.d.cap || sinv_append(s, i)) {
-                LCQ_SYNC();
-                if (LCQ_TID == 0) W[i] = 0;
-                LCQ_SYNC();
-            }
-        }
-    s.sinv_valid = 1;
-    return 0;
-}
-
-// EQP on the working set (idx[0..nw), sides in W): regularised KKT + refinement (see file header).
-// Result: w.xe (x), w.lam (compact multipliers, OSQP sign).  s.eqp_res = final residual.
-LCQ_DEVN void eqp_solve(QP& s, const signed char* W)
-{
-    const int n = s.d.n, nw = s.nw, cap = s.d.cap;
-    Work& w = s.w;
-    const Prep& pr = s.pr;
-    s.n_eqp++;
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) { w.xe[j] = 0.0; w.dx[j] = 0.0; }
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) { w.lam[a] = 0.0; w.dl[a] = 0.0; }
+    s.tinv_valid = 0;
+    for (int i = LCQ_TID; i < m; i += LCQ_NT)
+        if (s.w.ctype[i] >= 1) W[i] = (s.w.ctype[i] == 1) ? 1 : 0;
     LCQ_SYNC();
-    double best = INFINITY;
-    for (int pass = 0;; pass++) {
-        // r1 = -q - P x - Aw' lam ; r2 = b - Aw x
-        mv_rows(pr.P, n, n, n, w.xe, w.px);
-        mv_rows_idx(pr.A, w.idx, nw, n, n, w.xe, w.r2);
-        LCQ_SYNC();
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.t1[j] = -w.q[j] - w.px[j];
-        double rn = 0;
-        for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
-            const int i = w.idx[a];
-            const double b = (W[i] == 1) ? w.l[i] : w.u[i];
-            w.r2[a] = b - w.r2[a];
-            rn = fmax(rn, fabs(w.r2[a]));
+    for (int i = 0; i < m; i++) {  // W is in shared memory: uniform branches
+        if (!W[i] || s.w.ctype[i] != 0) continue;
+        if (s.nw >= s.d.cap || tinv_append(s, i)) {
+#ifdef LCQP_HOST_EMU
+            if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu tinv_build: row %d rejected (nw=%d cap=%d mE=%d)\n", i, s.nw, s.d.cap, s.mt->mE);
+#endif
+            LCQ_SYNC();
+            if (LCQ_TID == 0) W[i] = 0;
+            LCQ_SYNC();
         }
-        LCQ_SYNC();
-        mv_cols_idx(pr.A, w.idx, nw, n, n, w.lam, w.t1, -1.0, w.r1);
-        LCQ_SYNC();
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) rn = fmax(rn, fabs(w.r1[j]));
-        rn = block_max(rn, w.sc);
-        if (pass > 0 && !(rn < best)) {  // last correction did not help: undo it and stop
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xe[j] -= w.dx[j];
-            for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.lam[a] -= w.dl[a];
-            break;
-        }
-        best = rn;
-        if (rn < 1e-15 || pass == s.o->qp_refine_iter) break;
-        // dlam = Sinv (Aw Hinv r1 - r2) ; dx = Hinv (r1 - Aw' dlam)
-        mv_rows(pr.Hinv, n, n, n, w.r1, w.t1);
-        LCQ_SYNC();
-        mv_rows_idx(pr.A, w.idx, nw, n, n, w.t1, w.dl2);
-        LCQ_SYNC();
-        for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.dl2[a] -= w.r2[a];
-        LCQ_SYNC();
-        mv_rows(w.Sinv, nw, nw, cap, w.dl2, w.dl);
-        LCQ_SYNC();
-        mv_cols_idx(pr.A, w.idx, nw, n, n, w.dl, w.r1, -1.0, w.t2);
-        LCQ_SYNC();
-        mv_rows(pr.Hinv, n, n, n, w.t2, w.dx);
-        LCQ_SYNC();
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xe[j] += w.dx[j];
-        for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.lam[a] += w.dl[a];
-        LCQ_SYNC();
     }
-    LCQ_SYNC();
-    s.eqp_res = best;
+    s.tinv_valid = 1;
 }
 
-// KKT conditions of the full QP at (xe, lam).  0 = satisfied; 2 stationarity, 3 active row off its
-// bound, 4 inactive row violated, 5/6 wrong multiplier sign (*worst = position in idx to drop).
-LCQ_DEVN int kkt_check(QP& s, const signed char* W, int* worst)
+// Solve the regularised KKT system of the working set,
+//     [P + dI, Aw'; Aw, -dI] [dx; dlam] = [r1; r2],
+// r2 / dlam full-length (m) vectors of which only the rows in W count / are written (others: dlam = 0).
+// Block elimination: Hinv, then the static equality block (SEinv), then the inequality rows (Tinv).
+// In: w.r1, w.r2.  Out: w.dx, w.dlam.  Scratch: u, t, cE, vE, dI, lI, yf.
+LCQ_DEVN void kkt_solve(QP& s)
 {
     const int n = s.d.n, m = s.d.m, nw = s.nw;
     Work& w = s.w;
-    const Prep& pr = s.pr;
+    const Mats& mt = *s.mt;
+    const int mE = mt.mE;
+    // K^-1 [r1; r2_E]:  u = Hinv r1, vE = SEinv (A_E u - r2_E), t = u - (Hinv A_E') vE
+    op_mv(mt.oHinv, w.r1, nullptr, 1.0, w.u);
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }
+    if (mE > 0) {
+        op_mv_rows(mt.oAH, mt.eidx, mE, w.r1, w.r2, w.cE);
+        LCQ_SYNC();
+        mv_dense(mt.SEinv, mE, mE, s.d.ldE, w.cE, w.vE);
+        LCQ_SYNC();
+        for (int a = LCQ_TID; a < mE; a += LCQ_NT) w.yf[mt.eidx[a]] = w.vE[a];
+        LCQ_SYNC();
+        op_mv(mt.oAHt, w.yf, w.u, -1.0, w.t);
+    } else {
+        LCQ_SYNC();
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.t[j] = w.u[j];
+    }
+    if (nw == 0) {
+        LCQ_SYNC();
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.dx[j] = w.t[j];
+        for (int a = LCQ_TID; a < mE; a += LCQ_NT) w.dlam[mt.eidx[a]] = w.vE[a];
+        LCQ_SYNC();
+        return;
+    }
+    LCQ_SYNC();
+    // lI = Tinv (A_I t - r2_I)
+    op_mv_rows(mt.oA, w.idx, nw, w.t, w.r2, w.dI);
+    LCQ_SYNC();
+    sym_mv(w.Tinv, nw, w.dI, w.lI);
+    LCQ_SYNC();
+    // second K^-1 on [r1 - A_I' lI; r2_E]
+    for (int a = LCQ_TID; a < mE; a += LCQ_NT) w.yf[mt.eidx[a]] = 0.0;
+    for (int a = LCQ_TID; a < nw; a += LCQ_NT) { w.yf[w.idx[a]] = w.lI[a]; w.dlam[w.idx[a]] = w.lI[a]; }
+    LCQ_SYNC();
+    op_mv(mt.oAt, w.yf, w.r1, -1.0, w.t);   // t = r1 - A_I' lI
+    LCQ_SYNC();
+    op_mv(mt.oHinv, w.t, nullptr, 1.0, w.u);
+    if (mE > 0) {
+        op_mv_rows(mt.oAH, mt.eidx, mE, w.t, w.r2, w.cE);
+        for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.yf[w.idx[a]] = 0.0;
+        LCQ_SYNC();
+        mv_dense(mt.SEinv, mE, mE, s.d.ldE, w.cE, w.vE);
+        LCQ_SYNC();
+        for (int a = LCQ_TID; a < mE; a += LCQ_NT) { w.yf[mt.eidx[a]] = w.vE[a]; w.dlam[mt.eidx[a]] = w.vE[a]; }
+        LCQ_SYNC();
+        op_mv(mt.oAHt, w.yf, w.u, -1.0, w.dx);
+    } else {
+        LCQ_SYNC();
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.dx[j] = w.u[j];
+    }
+    LCQ_SYNC();
+}
+
+// Residual of the UNREGULARISED KKT system of working set W at (x, lam):
+//   r1 = -q - P x - A' lam,  r2[i] = b_i - (A x)_i for rows in W (0 elsewhere);  also leaves px = P x, zx = A x.
+// Returns the infinity norm of (r1, r2).
+LCQ_DEVN double kkt_residual(QP& s, const signed char* W, const double* x, const double* lam)
+{
+    const int n = s.d.n, m = s.d.m;
+    Work& w = s.w;
+    const Mats& mt = *s.mt;
+    op_mv(mt.oP, x, nullptr, 1.0, w.px);
+    op_mv(mt.oA, x, nullptr, 1.0, w.zx);
+    LCQ_SYNC();
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.u[j] = -w.q[j] - w.px[j];
+    double rn = 0;
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+        double r = 0.0;
+        if (W[i]) r = ((W[i] == 1) ? w.l[i] : w.ub[i]) - w.zx[i];
+        w.r2[i] = r;
+        rn = fmax(rn, fabs(r));
+    }
+    LCQ_SYNC();
+    op_mv(mt.oAt, lam, w.u, -1.0, w.r1);
+    LCQ_SYNC();
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) rn = fmax(rn, fabs(w.r1[j]));
+    return block_max(rn, w.sc);
+}
+
+// KKT conditions of the full QP at (x, lam) with px, zx, r1 as left by kkt_residual.  0 = satisfied;
+// 2 stationarity, 3 active row off its bound, 4 inactive row violated, 5/6 wrong multiplier sign
+// (*worst = position in idx to drop).
+LCQ_DEVN int kkt_check(QP& s, const signed char* W, const double* lam, int* worst)
+{
+    const int n = s.d.n, m = s.d.m, nw = s.nw;
+    Work& w = s.w;
     const double ftol = s.o->qp_feas_tol, dtol = s.o->qp_dual_tol;
-    mv_rows(pr.P, n, n, n, w.xe, w.px);
-    mv_rows(pr.A, m, n, n, w.xe, w.zt);
-    LCQ_SYNC();
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.t1[j] = -w.q[j] - w.px[j];
-    double ln = 0;
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) ln = fmax(ln, fabs(w.lam[a]));
-    LCQ_SYNC();
-    mv_cols_idx(pr.A, w.idx, nw, n, n, w.lam, w.t1, -1.0, w.r1);
-    ln = block_max(ln, w.sc);
-    double rs = 0;
+    double ln = 0, rs = 0;
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) ln = fmax(ln, fabs(lam[i]));
     for (int j = LCQ_TID; j < n; j += LCQ_NT) rs = fmax(rs, fabs(w.r1[j]));
+    ln = block_max(ln, w.sc);
     rs = block_max(rs, w.sc);
     if (!(rs <= kResTol * (1.0 + ln))) return 2;
-    int bad3 = 0, bad4 = 0;
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
-        const int i = w.idx[a];
-        const double b = (W[i] == 1) ? w.l[i] : w.u[i];
-        if (!(fabs(b - w.zt[i]) <= kResTol * (1.0 + fabs(b)))) bad3 = 1;
-    }
+    int bad = 0;
     for (int i = LCQ_TID; i < m; i += LCQ_NT) {
-        const double tol = ftol * (1.0 + fabs(w.zt[i]));
-        if (w.zt[i] < w.l[i] - tol || w.zt[i] > w.u[i] + tol) bad4 = 1;
+        const double zi = w.zx[i];
+        if (W[i]) {
+            const double b = (W[i] == 1) ? w.l[i] : w.ub[i];
+            if (!(fabs(b - zi) <= kResTol * (1.0 + fabs(b)))) bad |= 2;
+        }
+        const double tol = ftol * (1.0 + fabs(zi));
+        if (zi < w.l[i] - tol || zi > w.ub[i] + tol) bad |= 1;
+#ifdef LCQP_HOST_EMU
+        if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1 && (zi < w.l[i] - tol || zi > w.ub[i] + tol))
+            fprintf(stderr, "      emu kkt_check: row %d W=%d pin=%d violated z=%.17g l=%.17g u=%.17g\n", i, (int)W[i], (int)w.pin[i], zi, w.l[i], w.ub[i]);
+#endif
     }
-    const double bad = block_max((double)(bad3 * 2 + bad4), w.sc);
-    if (bad >= 2.0) return 3;
-    if (bad >= 1.0) return 4;
+    bad = block_or(bad, w.sc);
+    if (bad & 2) return 3;
+    if (bad & 1) return 4;
     const double thr = dtol * (1.0 + ln);
     double bv = -1.0;
     int bi = -1;
     for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
         const int i = w.idx[a];
-        if (w.ctype[i] == 1 || w.pin[i]) continue;
-        const double v = (W[i] == 1) ? w.lam[a] : -w.lam[a];  // OSQP sign: lower-active needs lam <= 0
+        if (w.pin[i] & 1) continue;
+        const double v = (W[i] == 1) ? lam[i] : -lam[i];  // OSQP sign: lower-active needs lam <= 0
         if (v > thr && (bi < 0 || v > bv)) { bv = v; bi = a; }
     }
     double vout;
@@ -651,190 +1050,264 @@ LCQ_DEVN int kkt_check(QP& s, const signed char* W, int* worst)
     return (W[w.idx[pos]] == 1) ? 5 : 6;
 }
 
+// (xa, lam) is the exact optimum on working set W: make it the accepted solution of this QP.
 LCQ_DEVN void accept_solution(QP& s, const signed char* W)
 {
-    const int n = s.d.n, m = s.d.m, nw = s.nw;
+    const int n = s.d.n, m = s.d.m;
     Work& w = s.w;
-    const Prep& pr = s.pr;
-    if (W != w.W)
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) w.W[i] = W[i];
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) w.y[i] = 0.0;
-    LCQ_SYNC();
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.y[w.idx[a]] = w.lam[a];
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) {
-        w.xs[j] = pr.D[j] * w.xe[j];  // un-scale (osqp auxil.c:524-562), c = 1
-        w.x[j] = w.xe[j];
+    const Mats& mt = *s.mt;
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+        w.W[i] = W[i];
+        const double yi = W[i] ? w.lam[i] : 0.0;
+        w.y[i] = yi;
+        w.ys[i] = -(mt.E[i] * yi);   // un-scale (osqp auxil.c:524-562, c = 1), qpOASES sign
+        w.z[i] = w.zx[i];
     }
-    LCQ_SYNC();
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) w.ys[i] = -(pr.E[i] * w.y[i]);  // qpOASES sign
-    mv_rows(pr.A, m, n, n, w.x, w.z);
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = w.xa[j];
     s.have_W = 1;
     LCQ_SYNC();
 }
 
-// H-metric projection of xin onto the rows of the working set + feasibility test of every row.
-LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin, double* xout)
-{
-    const int n = s.d.n, m = s.d.m, nw = s.nw, cap = s.d.cap;
-    Work& w = s.w;
-    const Prep& pr = s.pr;
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) xout[j] = xin[j];
-    LCQ_SYNC();
-    for (int pass = 0; pass < 4; pass++) {
-        mv_rows_idx(pr.A, w.idx, nw, n, n, xout, w.dl2);
-        LCQ_SYNC();
-        double rn = 0;
-        for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
-            const int i = w.idx[a];
-            w.dl2[a] = ((W[i] == 1) ? w.l[i] : w.u[i]) - w.dl2[a];
-            rn = fmax(rn, fabs(w.dl2[a]));
-        }
-        rn = block_max(rn, w.sc);
-        if (rn < 1e-15) break;
-        mv_rows(w.Sinv, nw, nw, cap, w.dl2, w.dl);
-        LCQ_SYNC();
-        mv_cols_idx(pr.A, w.idx, nw, n, n, w.dl, nullptr, 1.0, w.t2);
-        LCQ_SYNC();
-        mv_rows(pr.Hinv, n, n, n, w.t2, w.dx);
-        LCQ_SYNC();
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) xout[j] += w.dx[j];
-        LCQ_SYNC();
-    }
-    mv_rows(pr.A, m, n, n, xout, w.zt);
-    LCQ_SYNC();
-    const double ftol = s.o->qp_feas_tol;
-    int bad = 0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
-        const double tol = ftol * (1.0 + fabs(w.zt[i]));
-        if (w.zt[i] < w.l[i] - tol || w.zt[i] > w.u[i] + tol) bad = 1;
-        if (W[i]) {
-            const double b = (W[i] == 1) ? w.l[i] : w.u[i];
-            if (fabs(w.zt[i] - b) > tol) bad = 1;
-        }
-    }
-    return block_max((double)bad, w.sc) < 0.5;
-}
-
-// Primal active-set iteration from the feasible point x whose active rows contain the working set
-// (idx/Sinv valid for W).  Returns 0 with the solution accepted, 1 if it gave up.
-LCQ_DEVN int active_set(QP& s, double* x, signed char* W)
+// Active-set iteration from the feasible point xa whose active rows contain the working set W (Tinv valid
+// for W), multiplier estimate lam (zero outside W).
+//   ratio_test = false: plain iterative refinement of the EQP on W (used to probe an ADMM guess), stops at
+//                       the converged point without looking at the inactive rows; returns the KKT verdict.
+//   ratio_test = true : the full primal active-set method; returns 0 with the solution accepted, 1 if it gave up.
+LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
 {
     const int n = s.d.n, m = s.d.m;
     Work& w = s.w;
-    const Prep& pr = s.pr;
+    const Mats& mt = *s.mt;
     const int cap_it = 20 * (n + m) + 100;
     int last_dropped = -1;
+    double best = INFINITY;
+    int passes = 0;      // corrections since the last working-set change
+    bool dirty = ratio_test;   // (xa, lam) is not the from-zero solution on W
+    bool clean = false;        // the from-zero recomputation is running: no ratio tests
     for (int it = 0; it < cap_it; it++) {
-        eqp_solve(s, W);
-        // direction to the EQP minimiser, ratio test (Nocedal & Wright alg. 16.3)
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.dx[j] = w.xe[j] - x[j];
-        LCQ_SYNC();
-        mv_rows(pr.A, m, n, n, x, w.w);       // A x
-        mv_rows(pr.A, m, n, n, w.dx, w.zt2);  // A p
-        LCQ_SYNC();
-        double apn = 0;
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) apn = fmax(apn, fabs(w.zt2[i]));
-        apn = block_max(apn, w.sc);
-        const double seps = 1e-13 * (1.0 + apn);
-        // per-thread best: smallest alpha, tie -> largest |s|, then smallest row
-        double ba = 2.0, bs = 0.0;
-        int bi = -1;
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) {
-            if (W[i] || w.ctype[i] < 0) continue;
-            const double sv = w.zt2[i];
-            double a = 2.0;
-            if (sv < -seps && w.l[i] > -INFINITY) a = fmax(w.w[i] - w.l[i], 0.0) / (-sv);
-            else if (sv > seps && w.u[i] < INFINITY) a = fmax(w.u[i] - w.w[i], 0.0) / sv;
-            else continue;
-            if (a < 1.0 && (bi < 0 || a < ba || (a == ba && fabs(sv) > bs))) { ba = a; bs = fabs(sv); bi = i; }
+        const double rn = kkt_residual(s, W, w.xa, w.lam);
+        bool converged = false;
+        if (passes > 0 && !(rn < best)) {
+            // the last correction did not help: undo it and take that point as the EQP solution
+            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] -= w.dx[j];
+            for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] -= w.dlam[i];
+            LCQ_SYNC();
+            kkt_residual(s, W, w.xa, w.lam);
+            converged = true;
+        } else {
+            best = rn;
+            if (rn < 1e-15 || passes >= s.o->qp_refine_iter) converged = true;
         }
-        // two-stage reduction: first the minimal alpha, then among the rows attaining it the largest |s|
-        const double amin = -block_max(bi >= 0 ? -ba : -2.0, w.sc);
+        if (converged) {
+            int worst = -1;
+            const int reason = kkt_check(s, W, w.lam, &worst);
+            if (!ratio_test) { if (worst_out) *worst_out = worst; return reason; }
+            if (reason == 0) {
+                accept_solution(s, W);
+                if (!dirty) return 0;
+                // The point was reached along a path of partial steps.  Recompute it from zero on the final
+                // working set so that the accepted solution is a function of (W, q) only (the path leaves
+                // round-off that a symmetric problem would amplify, and the oracle computes it this way).
+                // Where the EQP on W has no unique solution the recomputation may land elsewhere; then the
+                // point accepted above stands.
+                for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
+                for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
+                LCQ_SYNC();
+                dirty = false;
+                best = INFINITY;
+                passes = 0;
+                clean = true;
+                continue;
+            }
+            if (clean) return 0;   // the recomputation did not verify: keep the solution accepted before it
+            if ((reason == 5 || reason == 6) && worst >= 0) {
+                const int row = w.idx[worst];
+                LCQ_SYNC();
+                if (LCQ_TID == 0) { W[row] = 0; w.lam[row] = 0.0; }
+                for (int i = LCQ_TID; i < m; i += LCQ_NT) w.pin[i] &= 1;
+                tinv_remove(s, worst);
+#ifdef LCQP_HOST_EMU
+                if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d drop row %d (reason %d) rn=%.3e\n", it, s.nw, row, reason, rn);
+#endif
+                last_dropped = row;
+                s.n_changes++;
+                best = INFINITY;
+                passes = 0;
+                dirty = true;
+                clean = false;
+                continue;
+            }
+#ifdef LCQP_HOST_EMU
+            if (getenv("LCQP_EMU_DEBUG")) fprintf(stderr, "    emu as it=%d nw=%d gives up: reason %d rn=%.3e best=%.3e passes=%d\n", it, s.nw, reason, rn, best, passes);
+#endif
+            return 1;  // EQP not solvable to tolerance on this set
+        }
+        s.n_pass++;
+        kkt_solve(s);   // r1, r2 -> dx, dlam
+        double amin = 1.0;
         int block = -1;
-        if (amin < 1.0) {
-            double vout;
-            block = block_argmax((bi >= 0 && ba == amin) ? bs : -1.0, (bi >= 0 && ba == amin) ? bi : -1, &vout, w.sc);
+        double apn = 0;
+        if (ratio_test && !clean) {
+            // ratio test against the inactive rows (Nocedal & Wright alg. 16.3)
+            op_mv(mt.oA, w.dx, nullptr, 1.0, w.zp);
+            LCQ_SYNC();
+            for (int i = LCQ_TID; i < m; i += LCQ_NT) apn = fmax(apn, fabs(w.zp[i]));
+            apn = block_max(apn, w.sc);
+            const double seps = 1e-13 * (1.0 + apn);
+            for (;;) {
+                double ba = 2.0, bs = 0.0;
+                int bi = -1;
+                for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+                    if (W[i] || w.ctype[i] != 0 || (w.pin[i] & 2)) continue;
+                    const double sv = w.zp[i];
+                    double a;
+                    if (sv < -seps && w.l[i] > -INFINITY) a = fmax(w.zx[i] - w.l[i], 0.0) / (-sv);
+                    else if (sv > seps && w.ub[i] < INFINITY) a = fmax(w.ub[i] - w.zx[i], 0.0) / sv;
+                    else continue;
+                    if (a < 1.0 && (bi < 0 || a < ba || (a == ba && fabs(sv) > bs))) { ba = a; bs = fabs(sv); bi = i; }
+                }
+                // two-stage reduction: the minimal alpha, then among the rows attaining it the largest |s|
+                const double am = -block_max(bi >= 0 ? -ba : -2.0, w.sc);
+                block = -1;
+                if (am < 1.0) {
+                    double vout;
+                    block = block_argmax((bi >= 0 && ba == am) ? bs : -1.0, (bi >= 0 && ba == am) ? bi : -1, &vout, w.sc);
+                    if (block >= 0) amin = am;
+                }
+                if (block < 0) break;
+                if (s.nw >= s.d.cap) return 1;
+                if (tinv_append(s, block) == 0) break;
+                // The blocking row is a combination of the active rows (e.g. a box bound duplicating an active
+                // selection row): along the working set it cannot move; the apparent motion is the leak of the
+                // regularisation.  It is left out of the ratio tests until a row leaves the working set.
+                if (LCQ_TID == 0) w.pin[block] |= 2;
+#ifdef LCQP_HOST_EMU
+                if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d row %d is dependent (alpha=%.3e, sv=%.3e)\n", it, s.nw, block, amin, w.zp[block]);
+#endif
+                LCQ_SYNC();
+                amin = 1.0;
+            }
         }
         if (block >= 0) {
-            const signed char side = (w.zt2[block] < 0) ? 1 : 2;
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) x[j] += amin * w.dx[j];
-            LCQ_SYNC();
-            if (s.nw >= s.d.cap) return 1;
-            if (sinv_append(s, block)) return 1;  // a blocking row cannot be dependent on W (A_W p = 0)
+            const signed char side = (w.zp[block] < 0) ? 1 : 2;
+            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += amin * w.dx[j];
+            for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] += amin * w.dlam[i];
             // a row that comes straight back after a zero-length step was dropped on multiplier noise:
             // it is weakly active; exempt it from the sign test for the rest of this QP (anti-cycling)
-            if (LCQ_TID == 0) { W[block] = side; if (block == last_dropped && amin * (1.0 + apn) <= 1e-12) w.pin[block] = 1; }
+            if (LCQ_TID == 0) { W[block] = side; if (block == last_dropped && amin * (1.0 + apn) <= 1e-12) w.pin[block] |= 1; }
             last_dropped = -1;
             LCQ_SYNC();
             s.n_changes++;
 #ifdef LCQP_HOST_EMU
-            if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d add row %d side %d alpha=%.3e res=%.1e\n", it, s.nw, block, (int)side, amin, s.eqp_res);
+            if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d add row %d side %d alpha=%.3e rn=%.3e\n", it, s.nw, block, (int)side, amin, rn);
 #endif
+            best = INFINITY;
+            passes = 0;
             continue;
         }
-        // full step: x is the EQP minimiser; check its multipliers
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) x[j] = w.xe[j];
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += w.dx[j];
+        for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] += w.dlam[i];
         LCQ_SYNC();
-        int worst = -1;
-        const int reason = kkt_check(s, W, &worst);
-#ifdef LCQP_HOST_EMU
-        if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d full step reason=%d worst=%d res=%.1e\n", it, s.nw, reason, worst, s.eqp_res);
-#endif
-        if (reason == 0) { accept_solution(s, W); return 0; }
-        if ((reason == 5 || reason == 6) && worst >= 0) {
-            const int row = w.idx[worst];
-            LCQ_SYNC();
-            if (LCQ_TID == 0) W[row] = 0;
-            sinv_remove(s, worst);
-            last_dropped = row;
-            s.n_changes++;
-            continue;
-        }
-#ifdef LCQP_HOST_EMU
-        if (getenv("LCQP_EMU_DEBUG")) fprintf(stderr, "    emu as it=%d nw=%d gives up: reason %d res=%.1e\n", it, s.nw, reason, s.eqp_res);
-#endif
-        return 1;  // EQP not solvable to tolerance on this set
+        passes++;
     }
     return 1;
 }
 
-// SubsolverBase::solve contract (/root/reference/include/SubsolverBase.hpp:37-56).  g unscaled (shared
-// or global memory), x0 / y0 (m entries, qpOASES sign) may be null.  Returns 0 or a non-zero flag;
+// H-metric projection of xin onto the rows of the working set + feasibility test of every row -> xa.
+LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin)
+{
+    const int n = s.d.n, m = s.d.m;
+    Work& w = s.w;
+    const Mats& mt = *s.mt;
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = xin[j];
+    LCQ_SYNC();
+    for (int pass = 0; pass < 4; pass++) {
+        op_mv(mt.oA, w.xa, nullptr, 1.0, w.zx);
+        LCQ_SYNC();
+        double rn = 0;
+        for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+            double r = 0.0;
+            if (W[i]) r = ((W[i] == 1) ? w.l[i] : w.ub[i]) - w.zx[i];
+            w.r2[i] = r;
+            rn = fmax(rn, fabs(r));
+        }
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.r1[j] = 0.0;
+        rn = block_max(rn, w.sc);
+#ifdef LCQP_HOST_EMU
+        if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu project pass %d rn=%.3e nw=%d\n", pass, rn, s.nw);
+#endif
+        if (rn < 1e-15) break;
+        kkt_solve(s);
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += w.dx[j];
+        LCQ_SYNC();
+    }
+    op_mv(mt.oA, w.xa, nullptr, 1.0, w.zx);
+    LCQ_SYNC();
+    const double ftol = s.o->qp_feas_tol;
+    int bad = 0;
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+        const double tol = ftol * (1.0 + fabs(w.zx[i]));
+        if (w.zx[i] < w.l[i] - tol || w.zx[i] > w.ub[i] + tol) bad = 1;
+        if (W[i]) {
+            const double b = (W[i] == 1) ? w.l[i] : w.ub[i];
+            if (fabs(w.zx[i] - b) > tol) bad = 1;
+        }
+#ifdef LCQP_HOST_EMU
+        if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 2 && (w.zx[i] < w.l[i] - tol || w.zx[i] > w.ub[i] + tol || (W[i] && fabs(w.zx[i] - ((W[i] == 1) ? w.l[i] : w.ub[i])) > tol)))
+            fprintf(stderr, "      emu project: row %d W=%d ctype=%d z=%.17g l=%.17g u=%.17g\n", i, (int)W[i], (int)w.ctype[i], w.zx[i], w.l[i], w.ub[i]);
+#endif
+    }
+    return block_or(bad, w.sc) == 0;
+}
+
+// SubsolverBase::solve contract (/root/reference/include/SubsolverBase.hpp:37-56).  g unscaled,
+// x0 / y0 (m entries, qpOASES sign) may be null.  Returns 0 or a non-zero flag;
 // *iterations = ADMM iterations + working-set changes.
 LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, const double* y0A, const double* y0box, int* iterations, bool infeasible)
 {
     const int n = s.d.n, m = s.d.m, mA = s.d.mA;
     Work& w = s.w;
-    const Prep& pr = s.pr;
+    const Mats& mt = *s.mt;
     const lcqp_cuda_options& o = *s.o;
     *iterations = 0;
     if (infeasible) return 37;
     const long long ch0 = s.n_changes;
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.q[j] = pr.D[j] * g[j];  // osqp.c:752-779, c = 1
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.q[j] = mt.D[j] * g[j];  // osqp.c:752-779, c = 1
     for (int i = LCQ_TID; i < m; i += LCQ_NT) w.pin[i] = 0;
     LCQ_SYNC();
     if (initial) {
         // osqp_warm_start_x/_y (osqp.c:700-745)
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = x0 ? x0[j] / pr.D[j] : 0.0;
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = x0 ? x0[j] / mt.D[j] : 0.0;
         for (int i = LCQ_TID; i < m; i += LCQ_NT) {
             double yv = 0.0;
             if (i < mA) { if (y0A) yv = y0A[i]; }
             else if (y0box) yv = y0box[i - mA];
-            w.y[i] = -yv / pr.E[i];
+            w.y[i] = -yv / mt.E[i];
         }
         LCQ_SYNC();
-        mv_rows(pr.A, m, n, n, w.x, w.z);
+        op_mv(mt.oA, w.x, nullptr, 1.0, w.z);
         s.have_W = 0;
-        s.sinv_valid = 0;
+        s.tinv_valid = 0;
         LCQ_SYNC();
-    } else if (s.have_W && s.sinv_valid) {
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = w.x[j];
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) w.Wtry[i] = w.W[i];
+    } else if (s.have_W && s.tinv_valid) {
+        // hot start: the previous working set is tried first (EQP from zero: the usual case late in the
+        // homotopy, where the active set no longer changes) ...
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
+        for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.Wtry[i] = w.W[i]; w.lam[i] = 0.0; }
         LCQ_SYNC();
-        if (active_set(s, w.xa, w.Wtry) == 0) { *iterations = (int)(s.n_changes - ch0); return 0; }
+        const int reason = active_set(s, w.Wtry, false, nullptr);
+        if (reason == 0) { accept_solution(s, w.Wtry); return 0; }
+        if (reason != 5 && reason != 6) {
+            // ... else the active-set iteration continues from the previous optimum (feasible: the bounds did
+            // not change) with its multipliers; a feasible EQP point with a wrong-signed multiplier is kept
+            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = w.x[j];
+            for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = w.y[i];
+            LCQ_SYNC();
+        }
+        if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = (int)(s.n_changes - ch0); return 0; }
         // fall through to ADMM from the previous solution
-        s.sinv_valid = 0;
-        mv_rows(pr.A, m, n, n, w.x, w.z);
+        s.tinv_valid = 0;
+        op_mv(mt.oA, w.x, nullptr, 1.0, w.z);
         LCQ_SYNC();
     }
     int have_fail = 0;
@@ -843,31 +1316,33 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
         for (int k = 0; k < o.qp_check_interval && it < o.qp_max_iter; k++, it++) admm_iter(s);
         s.n_admm += o.qp_check_interval;
         guess_working_set(s, w.Wtry);
-        int same = 0;
         if (have_fail) {
             int diff = 0;
             for (int i = LCQ_TID; i < m; i += LCQ_NT) diff |= (w.Wtry[i] != w.Wfail[i]);
-            same = block_max((double)diff, w.sc) < 0.5;
+            if (!block_or(diff, w.sc)) continue;
         }
-        if (same) continue;
         for (int i = LCQ_TID; i < m; i += LCQ_NT) w.Wfail[i] = w.Wtry[i];
         have_fail = 1;
         LCQ_SYNC();
-        if (sinv_build(s, w.Wtry)) continue;  // guess larger than the Schur complement capacity
-        eqp_solve(s, w.Wtry);
-        const int reason = kkt_check(s, w.Wtry, nullptr);
+        tinv_build(s, w.Wtry);
+        // EQP on the guessed set, from zero
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
+        for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
+        LCQ_SYNC();
+        const int reason = active_set(s, w.Wtry, false, nullptr);
 #ifdef LCQP_HOST_EMU
-        if (getenv("LCQP_EMU_DEBUG")) fprintf(stderr, "  emu admm it=%d nw=%d probe reason=%d res=%.1e\n", it, s.nw, reason, s.eqp_res);
+        if (getenv("LCQP_EMU_DEBUG")) fprintf(stderr, "  emu admm it=%d nw=%d probe reason=%d\n", it, s.nw, reason);
 #endif
         if (reason == 0) { accept_solution(s, w.Wtry); *iterations = it + (int)(s.n_changes - ch0); return 0; }
         if (reason == 5 || reason == 6) {
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = w.xe[j];
+            // primal feasible EQP point with a wrong-signed multiplier: a valid active-set start
+            if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = it + (int)(s.n_changes - ch0); return 0; }
+            s.tinv_valid = 0;
+        } else if (project_feasible(s, w.Wtry, w.x)) {
+            for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
             LCQ_SYNC();
-            if (active_set(s, w.xa, w.Wtry) == 0) { *iterations = it + (int)(s.n_changes - ch0); return 0; }
-            s.sinv_valid = 0;
-        } else if (project_feasible(s, w.Wtry, w.x, w.xa)) {
-            if (active_set(s, w.xa, w.Wtry) == 0) { *iterations = it + (int)(s.n_changes - ch0); return 0; }
-            s.sinv_valid = 0;
+            if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = it + (int)(s.n_changes - ch0); return 0; }
+            s.tinv_valid = 0;
         }
     }
     *iterations = it + (int)(s.n_changes - ch0);
@@ -893,31 +1368,26 @@ struct LoopOut {
     double rhoOpt;
 };
 
-// t = Q v ; Lx = L v ; Rx = R v ; out = t + rho * (L' Rx + R' Lx) + add   (i.e. Qk v + add)
-LCQ_DEVN void qk_apply(const Dims& d, const Inst& in, double rho, const double* v, const double* add, double* out, Work& w)
+// out = Q v + rho * (L' (R v) + R' (L v)) + add   (i.e. Qk v + add); leaves Lx = L v, Rx = R v
+LCQ_DEVN void qk_apply(const RawOps& ro, double rho, const double* v, const double* add, double* out, Work& w)
 {
-    const int n = d.n, nComp = d.nComp;
-    mv_rows(in.Q, n, n, n, v, w.tn);
-    mv_rows(in.L, nComp, n, n, v, w.Lx);
-    mv_rows(in.R, nComp, n, n, v, w.Rx);
+    op_mv(ro.Q, v, add, 1.0, w.tn);
+    op_mv(ro.L, v, nullptr, 1.0, w.Lx);
+    op_mv(ro.R, v, nullptr, 1.0, w.Rx);
     LCQ_SYNC();
-    for (int c = LCQ_TID; c < n; c += LCQ_NT) {
-        double sL = 0, sR = 0;
-        for (int r = 0; r < nComp; r++) {
-            sL += in.L[(size_t)r * n + c] * w.Rx[r];
-            sR += in.R[(size_t)r * n + c] * w.Lx[r];
-        }
-        out[c] = w.tn[c] + rho * (sL + sR) + (add ? add[c] : 0.0);
-    }
+    op_mv(ro.Lt, w.Rx, w.tn, rho, out);
+    LCQ_SYNC();
+    op_mv(ro.Rt, w.Lx, out, rho, out);
     LCQ_SYNC();
 }
 
-LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
+LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long long instance,
                        bool infeasible, double* xout, double* yout, LoopOut& out)
 {
     const Dims& d = s.d;
     const int n = d.n, nC = d.nC, nComp = d.nComp, mA = d.mA;
     Work& w = s.w;
+    const Mats& mt = *s.mt;
     const lcqp_cuda_options& o = *s.o;
     const bool osqp_flavour = (o.qpSolver == 2);
     const int boxOff = osqp_flavour ? 0 : n;
@@ -933,23 +1403,20 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
         w.xk[j] = in.x0 ? in.x0[j] : 0.0;   // LCQProblem.ipp:138-142
         w.gt[j] = in.g[j];                  // g_tilde = g (LCQProblem.cpp:966-967)
         w.pk[j] = 0.0;
+        w.gphi[j] = 0.0;
     }
+    LCQ_SYNC();
     if (have_gphi) {  // LCQProblem.cpp:970-996
         double part = 0;
         for (int i = LCQ_TID; i < nComp; i += LCQ_NT) part += (in.lbL ? in.lbL[i] : 0.0) * (in.lbR ? in.lbR[i] : 0.0);
         phi_const = block_sum(part, w.sc);
-        for (int c = LCQ_TID; c < n; c += LCQ_NT) {
-            double sv = 0;
-            if (in.lbL) for (int r = 0; r < nComp; r++) sv += in.R[(size_t)r * n + c] * in.lbL[r];
-            if (in.lbR) for (int r = 0; r < nComp; r++) sv += in.L[(size_t)r * n + c] * in.lbR[r];
-            w.gphi[c] = -sv;
-        }
+        if (in.lbL) { op_mv(ro.Rt, in.lbL, w.gphi, -1.0, w.gphi); LCQ_SYNC(); }
+        if (in.lbR) { op_mv(ro.Lt, in.lbR, w.gphi, -1.0, w.gphi); LCQ_SYNC(); }
     }
-    LCQ_SYNC();
 
     auto phi = [&]() -> double {  // getPhi :1172-1185 ; x'Cx/2 = (Lx)'(Rx)
-        mv_rows(in.L, nComp, n, n, w.xk, w.Lx);
-        mv_rows(in.R, nComp, n, n, w.xk, w.Rx);
+        op_mv(ro.L, w.xk, nullptr, 1.0, w.Lx);
+        op_mv(ro.R, w.xk, nullptr, 1.0, w.Rx);
         LCQ_SYNC();
         double part = 0;
         for (int i = LCQ_TID; i < nComp; i += LCQ_NT) part += w.Lx[i] * w.Rx[i];
@@ -966,17 +1433,12 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
         }
     };
     auto linearize = [&]() {  // updateLinearization :1105-1112 : gk = rho C xk + g_tilde
-        mv_rows(in.L, nComp, n, n, w.xk, w.Lx);
-        mv_rows(in.R, nComp, n, n, w.xk, w.Rx);
+        op_mv(ro.L, w.xk, nullptr, 1.0, w.Lx);
+        op_mv(ro.R, w.xk, nullptr, 1.0, w.Rx);
         LCQ_SYNC();
-        for (int c = LCQ_TID; c < n; c += LCQ_NT) {
-            double sL = 0, sR = 0;
-            for (int r = 0; r < nComp; r++) {
-                sL += in.L[(size_t)r * n + c] * w.Rx[r];
-                sR += in.R[(size_t)r * n + c] * w.Lx[r];
-            }
-            w.gk[c] = rho * (sL + sR) + w.gt[c];
-        }
+        op_mv(ro.Lt, w.Rx, w.gt, rho, w.gk);
+        LCQ_SYNC();
+        op_mv(ro.Rt, w.Lx, w.gk, rho, w.gk);
         LCQ_SYNC();
     };
     auto solve_qp = [&](bool initial) -> bool {  // solveQPSubproblem :1115-1148
@@ -987,8 +1449,17 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
         subIter += qpIter;
         exitFlag = osqp_flavour ? (fl == 0 ? 1 : fl) : fl;
         if (fl != 0) { ret = (osqp_flavour && infeasible) ? RET_OSQP_GUESS : RET_SUBPROBLEM; return false; }
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.pk[j] = w.xs[j] - w.xk[j];
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.pk[j] = mt.D[j] * w.x[j] - w.xk[j];  // xnew = D xbar (auxil.c:524-562)
         LCQ_SYNC();
+#ifdef LCQP_HOST_EMU
+        if (getenv("LCQP_EMU_DEBUG")) {
+            fprintf(stderr, "emu qp i=%d rho=%g it=%d x=[", totalIter, rho, qpIter);
+            for (int j = 0; j < (n < 4 ? n : 4); j++) fprintf(stderr, "%.17g ", mt.D[j] * w.x[j]);
+            fprintf(stderr, "] ys=[");
+            for (int j = 0; j < (s.d.m < 4 ? s.d.m : 4); j++) fprintf(stderr, "%.17g ", w.ys[j]);
+            fprintf(stderr, "] passes=%lld changes=%lld\n", s.n_pass, s.n_changes);
+        }
+#endif
         return true;
     };
 
@@ -1008,17 +1479,16 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
         for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xk[j] = w.xk[j] + alphak * w.pk[j];
         LCQ_SYNC();
         // updateStationarity :1246-1272 : stat = Qk xk + g_tilde - A_full' yk_A - yk_box
-        qk_apply(d, in, rho, w.xk, w.gt, w.stat, w);
-        for (int c = LCQ_TID; c < n; c += LCQ_NT) {
-            double sv = 0;
-            for (int r = 0; r < nC; r++) sv += in.A[(size_t)r * n + c] * w.ys[r];
-            for (int r = 0; r < nComp; r++) sv += in.L[(size_t)r * n + c] * w.ys[nC + r];
-            for (int r = 0; r < nComp; r++) sv += in.R[(size_t)r * n + c] * w.ys[nC + nComp + r];
-            double st = w.stat[c] - sv;
-            if (d.has_box) st -= w.ys[mA + c];
-            w.stat[c] = st;
-        }
+        qk_apply(ro, rho, w.xk, w.gt, w.stat, w);
+        if (nC > 0) { op_mv(ro.At, w.ys, w.stat, -1.0, w.stat); LCQ_SYNC(); }
+        op_mv(ro.Lt, w.ys + nC, w.stat, -1.0, w.stat);
         LCQ_SYNC();
+        op_mv(ro.Rt, w.ys + nC + nComp, w.stat, -1.0, w.stat);
+        LCQ_SYNC();
+        if (d.has_box) {
+            for (int c = LCQ_TID; c < n; c += LCQ_NT) w.stat[c] -= w.ys[mA + c];
+            LCQ_SYNC();
+        }
         totalIter++;  // :493-496
 
         // leyfferCheckPositive :1275-1313
@@ -1039,7 +1509,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
             }
             if (fire) { update_penalty(); outerIter++; }
         }
-        linearize();  // :508
+        // (the reference linearises here, :508, and again at :545 before the QP; only the second one is used)
 
         double sm = 0;
         for (int j = LCQ_TID; j < n; j += LCQ_NT) sm = fmax(sm, fabs(w.stat[j]));
@@ -1059,8 +1529,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
                 }
                 // the reference returns W at the FIRST weak index whose test fails c-stationarity; any
                 // such index gives W, so an OR over the weak set is the same decision
-                int any = 0;
-                for (int b = 0; b < 3; b++) if (block_max((double)((fl >> b) & 1), w.sc) > 0.5) any |= (1 << b);
+                const int any = block_or(fl, w.sc);
                 status = (any & 4) ? 1 : (!(any & 1) ? 4 : (!(any & 2) ? 3 : 2));
                 success = true;
                 break;
@@ -1082,14 +1551,14 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
         }
         // getOptimalStepLength :1217-1237
         {
-            qk_apply(d, in, rho, w.pk, nullptr, w.stat, w);  // Qk pk
-            double part = 0;
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) part += w.stat[j] * w.pk[j];
-            const double qk = block_sum(part, w.sc);
-            qk_apply(d, in, rho, w.xk, w.gt, w.stat, w);     // Qk xk + g_tilde
-            part = 0;
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) part += w.stat[j] * w.pk[j];
-            const double lk = block_sum(part, w.sc);
+            qk_apply(ro, rho, w.pk, nullptr, w.stat, w);  // Qk pk
+            double p1 = 0;
+            for (int j = LCQ_TID; j < n; j += LCQ_NT) p1 += w.stat[j] * w.pk[j];
+            const double qk = block_sum(p1, w.sc);
+            qk_apply(ro, rho, w.xk, w.gt, w.stat, w);     // Qk xk + g_tilde
+            p1 = 0;
+            for (int j = LCQ_TID; j < n; j += LCQ_NT) p1 += w.stat[j] * w.pk[j];
+            const double lk = block_sum(p1, w.sc);
             alphak = 1.0;
             if (qk > 0 && lk < 0) alphak = fmin(-lk / qk, 1.0);
         }
@@ -1097,8 +1566,9 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
 
     // outputs: x = xk ; y = [box duals ; yk_A] (transformDuals :1381-1409 applied on success)
     for (int j = LCQ_TID; j < n; j += LCQ_NT) xout[j] = w.xk[j];
+    const bool have_y = !infeasible && s.have_W;
     if (!osqp_flavour)
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) yout[j] = (d.has_box && !infeasible) ? w.ys[mA + j] : 0.0;
+        for (int j = LCQ_TID; j < n; j += LCQ_NT) yout[j] = (d.has_box && have_y) ? w.ys[mA + j] : 0.0;
     if (success) {
         // Lx, Rx from the last phi() call hold L xk, R xk
         for (int i = LCQ_TID; i < mA; i += LCQ_NT) {
@@ -1108,7 +1578,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
             yout[boxOff + i] = v;
         }
     } else {
-        for (int i = LCQ_TID; i < mA; i += LCQ_NT) yout[boxOff + i] = infeasible ? 0.0 : w.ys[i];
+        for (int i = LCQ_TID; i < mA; i += LCQ_NT) yout[boxOff + i] = have_y ? w.ys[i] : 0.0;
     }
     LCQ_SYNC();
     out.ret = ret;
@@ -1120,54 +1590,139 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, unsigned long long instance,
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory carving
+// memory plan of one CTA
 // ------------------------------------------------------------------------------------------------
+// Doubles that are always in shared memory (QP iterates), doubles of the outer loop (shared memory when
+// they fit, else the CTA's global scratch), packed Tinv (likewise).
 struct SmemPlan {
-    size_t bytes;       // total dynamic shared memory
-    int sinv_in_smem;
+    size_t bytes;        // dynamic shared memory of the CTA
+    int outer_in_smem;
+    int tinv_in_smem;
+    size_t gl_doubles;   // doubles of global scratch per CTA for what did not fit
 };
 
-inline
-#ifndef LCQP_HOST_EMU
-__host__ __device__
-#endif
-size_t work_bytes(const Dims& d, bool sinv_in_smem)
+inline LCQ_HD size_t qp_doubles(const Dims& d) { return 8ull * d.n + 11ull * d.m + 2ull * d.cap + 2ull * d.capE + d.m /*ys*/; }
+inline LCQ_HD size_t outer_doubles(const Dims& d) { return 7ull * d.n + 2ull * d.nComp; }
+inline LCQ_HD size_t tinv_doubles(const Dims& d) { return (size_t)d.cap * (d.cap + 1) / 2; }
+inline LCQ_HD size_t misc_bytes(const Dims& d)
 {
-    size_t nd = 0;
-    nd += 9ull * d.n;       // q x xe xa px r1 t1 t2 dx
-    nd += 12ull * d.m;      // z y l u rhov lam r2 dl dl2 zt zt2 w
-    nd += 1ull * d.n + d.m; // xs ys
-    nd += 7ull * d.n;       // xk pk gk gt gphi stat tn
-    nd += 2ull * d.nComp;   // Lx Rx
-    if (sinv_in_smem) nd += (size_t)d.cap * d.cap;
-    size_t b = nd * sizeof(double);
-    b += (size_t)d.m * sizeof(int);          // idx
-    b += 5ull * ((d.m + 15) / 16) * 16;      // W Wtry Wfail ctype pin
-    b += sizeof(Scalars) + 64;
-    return b;
+    return (size_t)d.cap * sizeof(int) + 5ull * ((d.m + 15) / 16) * 16 + sizeof(Scalars) + 64;
 }
 
-LCQ_DEV void carve(Work& w, const Dims& d, unsigned char* base, double* sinv_global)
+inline LCQ_HD SmemPlan make_plan(const Dims& d, size_t budget)
 {
-    double* p = reinterpret_cast<double*>(base);
-    auto takeN = [&](int k) { double* r = p; p += k; return r; };
+    SmemPlan p;
+    size_t b = qp_doubles(d) * sizeof(double) + misc_bytes(d);
+    p.gl_doubles = 0;
+    p.tinv_in_smem = (b + tinv_doubles(d) * sizeof(double) <= budget);
+    if (p.tinv_in_smem) b += tinv_doubles(d) * sizeof(double); else p.gl_doubles += tinv_doubles(d);
+    p.outer_in_smem = (b + outer_doubles(d) * sizeof(double) <= budget);
+    if (p.outer_in_smem) b += outer_doubles(d) * sizeof(double); else p.gl_doubles += outer_doubles(d);
+    p.bytes = b;
+    return p;
+}
+
+LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* base, double* gl)
+{
+    double* q = reinterpret_cast<double*>(base);
+    auto take = [&](size_t k) { double* r = q; q += k; return r; };
+    auto takeg = [&](size_t k) { double* r = gl; gl += k; return r; };
     const int n = d.n, m = d.m;
-    w.q = takeN(n); w.x = takeN(n); w.xe = takeN(n); w.xa = takeN(n); w.px = takeN(n); w.r1 = takeN(n);
-    w.t1 = takeN(n); w.t2 = takeN(n); w.dx = takeN(n);
-    w.z = takeN(m); w.y = takeN(m); w.l = takeN(m); w.u = takeN(m); w.rhov = takeN(m); w.lam = takeN(m);
-    w.r2 = takeN(m); w.dl = takeN(m); w.dl2 = takeN(m); w.zt = takeN(m); w.zt2 = takeN(m); w.w = takeN(m);
-    w.xs = takeN(n); w.ys = takeN(m);
-    w.xk = takeN(n); w.pk = takeN(n); w.gk = takeN(n); w.gt = takeN(n); w.gphi = takeN(n); w.stat = takeN(n); w.tn = takeN(n);
-    w.Lx = takeN(d.nComp); w.Rx = takeN(d.nComp);
-    if (sinv_global) w.Sinv = sinv_global;
-    else w.Sinv = takeN(d.cap * d.cap);
-    w.idx = reinterpret_cast<int*>(p);
-    signed char* c = reinterpret_cast<signed char*>(w.idx + m);
+    w.q = take(n); w.x = take(n); w.xa = take(n); w.px = take(n); w.r1 = take(n); w.u = take(n); w.t = take(n); w.dx = take(n);
+    w.z = take(m); w.y = take(m); w.l = take(m); w.ub = take(m); w.lam = take(m); w.dlam = take(m); w.r2 = take(m);
+    w.zx = take(m); w.zp = take(m); w.w = take(m); w.yf = take(m);
+    w.dI = take(d.cap); w.lI = take(d.cap);
+    w.cE = take(d.capE); w.vE = take(d.capE);
+    w.ys = take(m);
+    w.Tinv = p.tinv_in_smem ? take(tinv_doubles(d)) : takeg(tinv_doubles(d));
+    auto tk = [&](size_t k) { return p.outer_in_smem ? take(k) : takeg(k); };
+    w.xk = tk(n); w.pk = tk(n); w.gk = tk(n); w.gt = tk(n); w.gphi = tk(n); w.stat = tk(n); w.tn = tk(n);
+    w.Lx = tk(d.nComp); w.Rx = tk(d.nComp);
+    w.idx = reinterpret_cast<int*>(q);
+    signed char* c = reinterpret_cast<signed char*>(w.idx + d.cap);
     const int mpad = ((m + 15) / 16) * 16;
     w.W = c; w.Wtry = c + mpad; w.Wfail = c + 2 * mpad; w.ctype = c + 3 * mpad; w.pin = c + 4 * mpad;
     uintptr_t sp = reinterpret_cast<uintptr_t>(c + 5 * mpad);
     sp = (sp + 15) & ~(uintptr_t)15;
     w.sc = reinterpret_cast<Scalars*>(sp);
+}
+
+// Layout of a Mats block in a flat array of doubles (+ ints at the end).
+inline LCQ_HD size_t mats_doubles(const Dims& d)
+{
+    const size_t n = d.n, m = d.m;
+    return 3 * n * n + 2 * m * n + n + m + m * m + (size_t)d.ldE * d.ldE + (m + 1) / 2 /*eidx*/ + (m + 7) / 8 /*ctype*/ + 2;
+}
+
+LCQ_DEV void carve_mats(Mats& mt, double* base, const Dims& d)
+{
+    const int mEcap = d.ldE;
+    const size_t n = d.n, m = d.m;
+    mt.P = base; base += n * n;
+    mt.A = base; base += m * n;
+    mt.D = base; base += n;
+    mt.E = base; base += m;
+    mt.Hinv = base; base += n * n;
+    mt.AH = base; base += m * n;
+    mt.T = base; base += m * m;
+    mt.Minv = base; base += n * n;
+    mt.SEinv = base; base += (size_t)mEcap * mEcap;
+    mt.eidx = reinterpret_cast<int*>(base); base += (m + 1) / 2;
+    mt.ctype = reinterpret_cast<signed char*>(base);
+    mt.mE = 0; mt.status = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One instance, start to finish (used by the persistent kernel and by the host emulation).
+// `mats_shared`: mt was prepared by the batch-level prepare step; otherwise this CTA prepares it here.
+// ------------------------------------------------------------------------------------------------
+LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, const RawOps& ro, unsigned long long instance,
+                           double* xo, double* yo, LoopOut& out)
+{
+    const Dims& d = s.d;
+    Work& w = s.w;
+    const lcqp_cuda_options& o = *s.o;
+    const int nD = d.n + d.mA;
+    s.mt = &mt;
+    s.nw = 0; s.have_W = 0; s.tinv_valid = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
+    out.ret = 0; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
+    bool skip = false;
+    // initializeSolver checks (LCQProblem.cpp:930-957): the OSQP-style layout has no box constraints
+    if (o.qpSolver == 2 && (in.lb || in.ub)) { out.ret = RET_INVALID_OSQP_BOX; skip = true; }
+    if (!skip) {
+        int prep_rc = 0;
+        if (!mats_shared) {
+            prepare_scale(d, in, mt, w.u, w.zx);
+            if (LCQ_TID == 0) mats_dense_ops(d, mt);
+            LCQ_SYNC();
+        }
+        const int bflags = set_bounds(d, in, mt.E, w.l, w.ub, w.ctype, w.sc);
+        if (bflags & 2) { out.ret = RET_INVALID_LOWER_COMP; skip = true; }  // loadLCQP fails (:747,:767)
+        const bool infeasible = (bflags & 1) != 0;
+        if (!skip && !infeasible) {
+            if (!mats_shared) {
+                prep_rc = prepare_factor(d, mt, w.ctype, o, w.u, w.t, w.zx, w.zp, w.w, w.sc);
+            } else {
+                int diff = (mt.status != 0);
+                for (int i = LCQ_TID; i < d.m; i += LCQ_NT) diff |= ((w.ctype[i] == 1) != (mt.ctype[i] >= 1)) || ((w.ctype[i] < 0) != (mt.ctype[i] < 0));
+                prep_rc = block_or(diff, w.sc);
+            }
+            if (!prep_rc) {
+                // rows found dependent at prepare time keep their type 2
+                for (int i = LCQ_TID; i < d.m; i += LCQ_NT) w.ctype[i] = mt.ctype[i];
+                LCQ_SYNC();
+            }
+        }
+        if (!skip) {
+            if (prep_rc) { out.ret = RET_SUBPROBLEM; out.exitFlag = 38; skip = true; }
+            else lcqp_loop(s, in, ro, instance, infeasible, xo, yo, out);
+        }
+    }
+    if (skip) {
+        for (int j = LCQ_TID; j < d.n; j += LCQ_NT) xo[j] = in.x0 ? in.x0[j] : 0.0;
+        for (int j = LCQ_TID; j < nD; j += LCQ_NT) yo[j] = 0.0;
+    }
+    LCQ_SYNC();
 }
 
 }  // namespace lcqp

@@ -1,0 +1,34 @@
+"""Host emulation of the product's device code -- TEST INFRASTRUCTURE ONLY (see emu_driver.cpp)."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+from oracle import pyref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+EMU_SO = os.path.join(HERE, "liblcqp_emu.so")
+SOURCES = [os.path.join(HERE, "emu_driver.cpp"), os.path.join(ROOT, "lcqpow_b200", "csrc", "lcqp_device.cuh"),
+           os.path.join(ROOT, "include", "lcqp_cuda.h")]
+
+
+def build(force: bool = False) -> str:
+    if not force and os.path.exists(EMU_SO) and all(os.path.getmtime(s) <= os.path.getmtime(EMU_SO) for s in SOURCES):
+        return EMU_SO
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DLCQP_HOST_EMU", "-ffp-contract=off",
+                    "-Wno-unused-function", "-o", EMU_SO, SOURCES[0]], check=True)
+    return EMU_SO
+
+
+class EmuLib(pyref._Lib):
+    """Same calling convention as oracle.pyref.OracleLib (lcqp_cuda_options is layout-identical to
+    lcqp_oracle_options; lcqp_cuda_stats to lcqp_oracle_result)."""
+    so_path = EMU_SO
+    prefix = "lcqp_emu"
+    kind = "emu"
+    options_cls = pyref.OracleOptions
+
+    def __init__(self):
+        build()
+        super().__init__()
