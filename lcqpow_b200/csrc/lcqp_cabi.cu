@@ -27,6 +27,8 @@ struct KernelArgs {
     unsigned shared_mask;        // loadLCQP arguments shared by the batch
     int mats_shared;             // Q, L, R, A all shared: one preparation for the batch
     SmemPlan plan;
+    unsigned long long cache_offset;     // byte offset of the operator cache in dynamic shared memory
+    unsigned long long cache_bytes;      // its size (0: operators stay in L2)
     Mats* shared_mats;           // prepared operands of the batch (device struct, written by prepare_shared_kernel)
     RawOps* shared_raw;          // CSR / dense operators on the unscaled shared matrices
     double* shared_mats_store;   // backing store of shared_mats
@@ -86,7 +88,11 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_shared_kernel(const __gr
         }
         if (rc == 0) mats_build_ops_post(d, mt, pool, &sc);
         __syncthreads();
-        if (threadIdx.x == 0) { mt.status = rc; *a.shared_mats = mt; }
+        if (threadIdx.x == 0) {
+            mt.status = rc;
+            if (rc == 0) cache_requirements(mt, ro, &mt.cache_bytes_hot, &mt.cache_bytes_raw);
+            *a.shared_mats = mt;
+        }
     }
 }
 
@@ -107,6 +113,7 @@ __global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_co
         ro = *a.shared_raw;
     }
     __syncthreads();
+    if (a.mats_shared && a.cache_bytes > 0 && mt.status == 0) cache_shared_operators(a.d, mt, ro, smem + a.cache_offset, (size_t)a.cache_bytes);
     const int nD = a.d.n + a.d.mA;
     const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (1u << LCQP_A);
     const bool raw_all_shared = (a.shared_mask & mat_bits) == mat_bits || (a.d.nC == 0 && (a.shared_mask & mat_bits) == (mat_bits & ~(1u << LCQP_A)));
@@ -511,15 +518,27 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     h->last_mE = mE;
     CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
 
-    // shared-memory plan: aim at two resident CTAs per SM, fall back to one
+    // shared-memory plan.  When the batch shares its matrices and the operators of the inner passes fit beside
+    // the instance's own state, one CTA per SM keeps them in shared memory (no L2 round trip per operator
+    // application); otherwise aim at two resident CTAs per SM with the operators in L2, fall back to one.
     SmemPlan plan = make_plan(d, kSmemSM / 2 - 1024);
-    if (!(plan.tinv_in_smem && plan.outer_in_smem)) {
+    a.cache_bytes = 0;
+    {
         const SmemPlan p1 = make_plan(d, kSmemMax);
-        if (p1.tinv_in_smem && !plan.tinv_in_smem) plan = p1;
+        const size_t base = (p1.bytes + 15) / 16 * 16;
+        const size_t hot = a.mats_shared && h->host_mats->status == 0 ? (size_t)h->host_mats->cache_bytes_hot : 0;
+        const size_t raw = a.mats_shared && h->host_mats->status == 0 ? (size_t)h->host_mats->cache_bytes_raw : 0;
+        if (hot > 0 && p1.tinv_in_smem && p1.outer_in_smem && base + hot <= kSmemMax) {
+            plan = p1;
+            a.cache_offset = base;
+            a.cache_bytes = hot + (base + hot + raw <= kSmemMax ? raw : 0);
+        } else if (!(plan.tinv_in_smem && plan.outer_in_smem)) {
+            if (p1.tinv_in_smem && !plan.tinv_in_smem) plan = p1;
+        }
     }
     if (plan.bytes > kSmemMax) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
     a.plan = plan;
-    const size_t smem = plan.bytes;
+    const size_t smem = a.cache_bytes ? (size_t)(a.cache_offset + a.cache_bytes) : plan.bytes;
     CK(cudaFuncSetAttribute(lcqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_solve_kernel, kThreads, smem), LCQP_CUDA_LAUNCH_FAILED);

@@ -85,14 +85,15 @@ enum { RET_OK = 0, RET_INVALID_OSQP_BOX = 110, RET_INVALID_LOWER_COMP = 120, RET
 
 // ------------------------------------------------------------------------------------------------
 // A linear operator y = M v, M logically rows x cols.
-//   rp != null : CSR (rp[rows+1], ci, va); rows with more than kLongRow entries are also listed in lrows
+//   rp != null : CSR (rp[rows+1], 16-bit column indices ci, values va); rows with more than kLongRow entries
+//                are also listed in lrows
 //   else trans == 0 : dense row-major, M[r][c] = dense[r*ld + c]
 //   else            : the transpose of a dense row-major matrix, M[r][c] = dense[c*ld + r]
 // ------------------------------------------------------------------------------------------------
 struct Op {
     const double* dense;
     const int* rp;
-    const int* ci;
+    const unsigned short* ci;
     const double* va;
     const int* lrows;
     int rows, cols, ld, trans, nlong;
@@ -119,8 +120,11 @@ struct Mats {
     double* SEinv;  // ldE*ldE (leading dimension d.ldE), order mE
     int* eidx;      // equality rows that are always in the working set (mE of them)
     signed char* ctype;  // m: -1 free row, 0 inequality, 1 equality, 2 equality found dependent (never active)
+    const double* SEinvP;  // packed (lower triangle) copy of SEinv in shared memory, or null
     int mE;
     int status;     // 0 ok, 1 factorisation failed
+    int cache_bytes_hot;   // shared memory that the per-pass operators (and packed SEinv) would take
+    int cache_bytes_raw;   // ... and the operators of the outer loop
     Op oP, oA, oAt, oHinv, oAH, oAHt, oMinv;
 };
 
@@ -311,12 +315,26 @@ LCQ_DEV void op_mv(const Op& op, const double* v, const double* init, double sca
                 if (LCQ_LANE == 0) out[r] = (init ? init[r] : 0.0) + scale * s;
             }
     } else if (!op.trans) {
-        for (int r = LCQ_WARP; r < op.rows; r += LCQ_NWARP) {
-            const double* row = op.dense + (size_t)r * op.ld;
-            double s = 0;
-            for (int c = LCQ_LANE; c < op.cols; c += LCQ_LANES) s += row[c] * v[c];
-            s = warp_sum(s);
-            if (LCQ_LANE == 0) out[r] = (init ? init[r] : 0.0) + scale * s;
+        const int rows = op.rows, cols = op.cols, ld = op.ld;
+        for (int r0 = LCQ_WARP; r0 < rows; r0 += 4 * LCQ_NWARP) {
+            const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
+            const double* a0 = op.dense + (size_t)r0 * ld;
+            const double* a1 = op.dense + (size_t)(r1 < rows ? r1 : r0) * ld;
+            const double* a2 = op.dense + (size_t)(r2 < rows ? r2 : r0) * ld;
+            const double* a3 = op.dense + (size_t)(r3 < rows ? r3 : r0) * ld;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) {
+                const double vc = v[c];
+                const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
+                s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
+            }
+            s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+            if (LCQ_LANE == 0) {
+                out[r0] = (init ? init[r0] : 0.0) + scale * s0;
+                if (r1 < rows) out[r1] = (init ? init[r1] : 0.0) + scale * s1;
+                if (r2 < rows) out[r2] = (init ? init[r2] : 0.0) + scale * s2;
+                if (r3 < rows) out[r3] = (init ? init[r3] : 0.0) + scale * s3;
+            }
         }
     } else {
         for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
@@ -349,15 +367,29 @@ LCQ_DEV void op_mv_rows(const Op& op, const int* idx, int na, const double* v, c
     }
 }
 
-// plain dense mat-vec with a leading dimension (one warp per row)
+// plain dense mat-vec with a leading dimension: one warp per row, four rows of a warp in flight (the matrix
+// usually sits in L2: the loads of the four rows overlap)
 LCQ_DEV void mv_dense(const double* __restrict__ M, int rows, int cols, int ld, const double* v, double* out)
 {
-    for (int r = LCQ_WARP; r < rows; r += LCQ_NWARP) {
-        const double* row = M + (size_t)r * ld;
-        double s = 0;
-        for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) s += row[c] * v[c];
-        s = warp_sum(s);
-        if (LCQ_LANE == 0) out[r] = s;
+    for (int r0 = LCQ_WARP; r0 < rows; r0 += 4 * LCQ_NWARP) {
+        const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
+        const double* a0 = M + (size_t)r0 * ld;
+        const double* a1 = M + (size_t)(r1 < rows ? r1 : r0) * ld;
+        const double* a2 = M + (size_t)(r2 < rows ? r2 : r0) * ld;
+        const double* a3 = M + (size_t)(r3 < rows ? r3 : r0) * ld;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) {
+            const double vc = v[c];
+            const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
+            s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (LCQ_LANE == 0) {
+            out[r0] = s0;
+            if (r1 < rows) out[r1] = s1;
+            if (r2 < rows) out[r2] = s2;
+            if (r3 < rows) out[r3] = s3;
+        }
     }
 }
 
@@ -439,12 +471,13 @@ LCQ_DEVN Op build_op(const double* src, int rows, int cols, int ld, int trans, C
         rp[0] = 0;
         for (int r = 0; r < rows; r++) { const int c = rp[r + 1]; nl += (c > kLongRow); tot += c; rp[r + 1] = tot; }
         const int io = pool.used[0], dof = pool.used[1];
-        const bool sparse = (long long)tot * 4 <= (long long)rows * cols && io + tot + nl <= pool.icap && dof + tot <= pool.dcap;
+        const int ci_ints = (tot + 1) / 2;   // 16-bit column indices
+        const bool sparse = cols < 65536 && (long long)tot * 4 <= (long long)rows * cols && io + ci_ints + nl <= pool.icap && dof + tot <= pool.dcap;
         if (sparse) {
-            pool.used[0] = io + tot + nl;
+            pool.used[0] = io + ci_ints + nl;
             pool.used[1] = dof + tot;
             sc->ired[1] = io; sc->ired[2] = dof; sc->ired[3] = nl;
-            int* lr = pool.ibuf + io + tot;
+            int* lr = pool.ibuf + io + ci_ints;
             int k = 0;
             for (int r = 0; r < rows; r++) if (rp[r + 1] - rp[r] > kLongRow) lr[k++] = r;
         } else {
@@ -455,17 +488,17 @@ LCQ_DEVN Op build_op(const double* src, int rows, int cols, int ld, int trans, C
     LCQ_SYNC();
     const int io = sc->ired[1], dof = sc->ired[2], nl = sc->ired[3];
     if (io < 0) { LCQ_SYNC(); return op; }
-    int* ci = pool.ibuf + io;
+    unsigned short* ci = reinterpret_cast<unsigned short*>(pool.ibuf + io);
     double* va = pool.dbuf + dof;
     for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
         int k = rp[r];
         for (int j = 0; j < cols; j++) {
             const double v = trans ? src[(size_t)j * ld + r] : src[(size_t)r * ld + j];
-            if (v != 0.0) { ci[k] = j; va[k] = v; k++; }
+            if (v != 0.0) { ci[k] = (unsigned short)j; va[k] = v; k++; }
         }
     }
     LCQ_SYNC();
-    op.rp = rp; op.ci = ci; op.va = va; op.lrows = ci + rp[rows]; op.nlong = nl;
+    op.rp = rp; op.ci = ci; op.va = va; op.lrows = pool.ibuf + io + (rp[rows] + 1) / 2; op.nlong = nl;
     return op;
 }
 
@@ -773,6 +806,83 @@ LCQ_DEVN void raw_build_ops(const Dims& d, const Inst& in, RawOps& ro, unsigned 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Shared-memory cache of the batch-shared operators.  A persistent CTA copies the CSR arrays of the
+// operators it applies in every pass (and the packed inverse of the static equality block) from L2 into its
+// own shared memory once, at kernel start; every later application is then free of L2 round trips.
+// ------------------------------------------------------------------------------------------------
+inline LCQ_HD size_t op_cache_bytes(int rows, int nnz, int nlong)
+{
+    size_t b = ((size_t)nnz * sizeof(double) + 15) / 16 * 16;
+    b += (((size_t)rows + 1 + nlong) * sizeof(int) + 15) / 16 * 16;
+    b += ((size_t)nnz * sizeof(unsigned short) + 15) / 16 * 16;
+    return b;
+}
+
+LCQ_DEV size_t op_cache_bytes(const Op& op) { return op.rp ? op_cache_bytes(op.rows, op.rp[op.rows], op.nlong) : 0; }
+
+// Copy a CSR operator into [*cur, end) if it fits (block-cooperative; every thread gets the same result).
+LCQ_DEVN void cache_op(Op& op, unsigned char*& cur, unsigned char* end)
+{
+    if (!op.rp) return;
+    const int rows = op.rows, nnz = op.rp[rows], nl = op.nlong;
+    const size_t need = op_cache_bytes(rows, nnz, nl);
+    if (cur + need > end) return;
+    double* va = reinterpret_cast<double*>(cur);
+    int* rp = reinterpret_cast<int*>(cur + ((size_t)nnz * sizeof(double) + 15) / 16 * 16);
+    int* lr = rp + rows + 1;
+    unsigned short* ci = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(rp) + (((size_t)rows + 1 + nl) * sizeof(int) + 15) / 16 * 16);
+    for (int k = LCQ_TID; k < nnz; k += LCQ_NT) { va[k] = op.va[k]; ci[k] = op.ci[k]; }
+    for (int r = LCQ_TID; r <= rows; r += LCQ_NT) rp[r] = op.rp[r];
+    for (int a = LCQ_TID; a < nl; a += LCQ_NT) lr[a] = op.lrows[a];
+    op.va = va; op.rp = rp; op.ci = ci; op.lrows = lr;
+    cur += need;
+}
+
+// `mt` / `ro` are this CTA's block-shared copies; one thread writes them.
+LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsigned char* base, size_t bytes)
+{
+    unsigned char* cur = base;
+    unsigned char* end = base + bytes;
+    const int mE = mt.mE;
+    LCQ_SYNC();
+    const double* sep = nullptr;
+    if (mE > 0) {
+        const size_t need = ((size_t)mE * (mE + 1) / 2 * sizeof(double) + 15) / 16 * 16;
+        if (cur + need <= end) {
+            double* P = reinterpret_cast<double*>(cur);
+            for (int e = LCQ_TID; e < mE * mE; e += LCQ_NT) {
+                const int a = e / mE, b = e - a * mE;
+                if (b <= a) P[(size_t)a * (a + 1) / 2 + b] = mt.SEinv[(size_t)a * d.ldE + b];
+            }
+            sep = P;
+            cur += need;
+        }
+    }
+    Op oA = mt.oA, oAt = mt.oAt, oAH = mt.oAH, oAHt = mt.oAHt, oHinv = mt.oHinv, oP = mt.oP;
+    cache_op(oA, cur, end); cache_op(oAt, cur, end); cache_op(oAH, cur, end); cache_op(oAHt, cur, end);
+    cache_op(oHinv, cur, end); cache_op(oP, cur, end);
+    Op rL = ro.L, rR = ro.R, rLt = ro.Lt, rRt = ro.Rt, rQ = ro.Q, rAt = ro.At;
+    cache_op(rL, cur, end); cache_op(rR, cur, end); cache_op(rLt, cur, end); cache_op(rRt, cur, end);
+    cache_op(rQ, cur, end); cache_op(rAt, cur, end);
+    LCQ_SYNC();
+    if (LCQ_TID == 0) {
+        mt.SEinvP = sep;
+        mt.oA = oA; mt.oAt = oAt; mt.oAH = oAH; mt.oAHt = oAHt; mt.oHinv = oHinv; mt.oP = oP;
+        ro.L = rL; ro.R = rR; ro.Lt = rLt; ro.Rt = rRt; ro.Q = rQ; ro.At = rAt;
+    }
+    LCQ_SYNC();
+}
+
+// bytes the cache would take (thread 0 of the prepare step calls this)
+LCQ_DEV void cache_requirements(const Mats& mt, const RawOps& ro, int* hot, int* raw)
+{
+    size_t h = ((size_t)mt.mE * (mt.mE + 1) / 2 * sizeof(double) + 15) / 16 * 16;
+    h += op_cache_bytes(mt.oA) + op_cache_bytes(mt.oAt) + op_cache_bytes(mt.oAH) + op_cache_bytes(mt.oAHt) + op_cache_bytes(mt.oHinv) + op_cache_bytes(mt.oP);
+    size_t r = op_cache_bytes(ro.L) + op_cache_bytes(ro.R) + op_cache_bytes(ro.Lt) + op_cache_bytes(ro.Rt) + op_cache_bytes(ro.Q) + op_cache_bytes(ro.At);
+    *hot = (int)h; *raw = (int)r;
+}
+
+// ------------------------------------------------------------------------------------------------
 // QP solver state machine
 // ------------------------------------------------------------------------------------------------
 struct QP {
@@ -932,7 +1042,7 @@ LCQ_DEVN void kkt_solve(QP& s)
     if (mE > 0) {
         op_mv_rows(mt.oAH, mt.eidx, mE, w.r1, w.r2, w.cE);
         LCQ_SYNC();
-        mv_dense(mt.SEinv, mE, mE, s.d.ldE, w.cE, w.vE);
+        if (mt.SEinvP) sym_mv(mt.SEinvP, mE, w.cE, w.vE); else mv_dense(mt.SEinv, mE, mE, s.d.ldE, w.cE, w.vE);
         LCQ_SYNC();
         for (int a = LCQ_TID; a < mE; a += LCQ_NT) w.yf[mt.eidx[a]] = w.vE[a];
         LCQ_SYNC();
@@ -965,7 +1075,7 @@ LCQ_DEVN void kkt_solve(QP& s)
         op_mv_rows(mt.oAH, mt.eidx, mE, w.t, w.r2, w.cE);
         for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.yf[w.idx[a]] = 0.0;
         LCQ_SYNC();
-        mv_dense(mt.SEinv, mE, mE, s.d.ldE, w.cE, w.vE);
+        if (mt.SEinvP) sym_mv(mt.SEinvP, mE, w.cE, w.vE); else mv_dense(mt.SEinv, mE, mE, s.d.ldE, w.cE, w.vE);
         LCQ_SYNC();
         for (int a = LCQ_TID; a < mE; a += LCQ_NT) { w.yf[mt.eidx[a]] = w.vE[a]; w.dlam[mt.eidx[a]] = w.vE[a]; }
         LCQ_SYNC();
@@ -1669,7 +1779,8 @@ LCQ_DEV void carve_mats(Mats& mt, double* base, const Dims& d)
     mt.SEinv = base; base += (size_t)mEcap * mEcap;
     mt.eidx = reinterpret_cast<int*>(base); base += (m + 1) / 2;
     mt.ctype = reinterpret_cast<signed char*>(base);
-    mt.mE = 0; mt.status = 0;
+    mt.SEinvP = nullptr;
+    mt.mE = 0; mt.status = 0; mt.cache_bytes_hot = 0; mt.cache_bytes_raw = 0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -74,18 +74,28 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
             if (rc == 0) shrink_dims(d, shared_mt.mE);
         }
     }
-    // the persistent solver CTA (lcqp_solve_kernel)
+    // the persistent solver CTA (lcqp_solve_kernel), with the shared-memory operator cache when it fits
     const SmemPlan plan = make_plan(d, 227 * 1024);
-    std::vector<unsigned char> smem(plan.bytes + 64);
+    size_t cache_bytes = 0;
+    const size_t cache_offset = (plan.bytes + 15) / 16 * 16;
+    if (mats_shared && shared_mt.status == 0) {
+        cache_requirements(shared_mt, shared_ro, &shared_mt.cache_bytes_hot, &shared_mt.cache_bytes_raw);
+        if (plan.tinv_in_smem && plan.outer_in_smem && cache_offset + shared_mt.cache_bytes_hot <= 227 * 1024)
+            cache_bytes = shared_mt.cache_bytes_hot + (cache_offset + shared_mt.cache_bytes_hot + shared_mt.cache_bytes_raw <= 227 * 1024 ? shared_mt.cache_bytes_raw : 0);
+        if (getenv("LCQP_EMU_NO_CACHE")) cache_bytes = 0;
+    }
+    std::vector<double> smem_d((cache_offset + cache_bytes + 64) / 8 + 2);
+    unsigned char* smem = reinterpret_cast<unsigned char*>(smem_d.data());
     std::vector<double> gl(plan.gl_doubles + 1);
     std::vector<double> ws(mats_shared ? 1 : mats_doubles(d));
     QP s;
     s.d = d;
     s.o = o;
-    carve(s.w, d, plan, smem.data(), gl.data());
+    carve(s.w, d, plan, smem, gl.data());
     Mats mt;
     if (mats_shared) mt = shared_mt; else carve_mats(mt, ws.data(), d);
     RawOps ro = shared_ro;
+    if (cache_bytes) cache_shared_operators(d, mt, ro, smem + cache_offset, cache_bytes);
     const int nD = nV + nC + 2 * nComp;
     int nfail = 0;
     for (int b = 0; b < batch; b++) {
