@@ -29,6 +29,7 @@ struct KernelArgs {
     SmemPlan plan;
     unsigned long long cache_offset;     // byte offset of the operator cache in dynamic shared memory
     unsigned long long cache_bytes;      // its size (0: operators stay in L2)
+    int cache_what;                      // bit0 packed SEinv, bit1 inner-pass operators, bit2 outer-loop operators
     Mats* shared_mats;           // prepared operands of the batch (device struct, written by prepare_shared_kernel)
     RawOps* shared_raw;          // CSR / dense operators on the unscaled shared matrices
     double* shared_mats_store;   // backing store of shared_mats
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_shared_kernel(const __gr
         __syncthreads();
         if (threadIdx.x == 0) {
             mt.status = rc;
-            if (rc == 0) cache_requirements(mt, ro, &mt.cache_bytes_hot, &mt.cache_bytes_raw);
+            if (rc == 0) cache_requirements(mt, ro);
             *a.shared_mats = mt;
         }
     }
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_co
         ro = *a.shared_raw;
     }
     __syncthreads();
-    if (a.mats_shared && a.cache_bytes > 0 && mt.status == 0) cache_shared_operators(a.d, mt, ro, smem + a.cache_offset, (size_t)a.cache_bytes);
+    if (a.mats_shared && a.cache_bytes > 0 && mt.status == 0) cache_shared_operators(a.d, mt, ro, smem + a.cache_offset, (size_t)a.cache_bytes, a.cache_what);
     const int nD = a.d.n + a.d.mA;
     const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (1u << LCQP_A);
     const bool raw_all_shared = (a.shared_mask & mat_bits) == mat_bits || (a.d.nC == 0 && (a.shared_mask & mat_bits) == (mat_bits & ~(1u << LCQP_A)));
@@ -175,7 +176,7 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
     s.d = a.d;
     s.o = &a.o;
     carve(s.w, a.d, a.plan, smem, a.gl);
-    s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
+    s.ph = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
     if (!a.initial) {
         for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
             reinterpret_cast<double*>(smem)[k] = reinterpret_cast<const double*>(a.saved_smem)[k];
@@ -196,6 +197,7 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
         if (!infeasible) {
             if (prepare_factor(a.d, mt, s.w.ctype, a.o, s.w.u, s.w.t, s.w.zx, s.w.zp, s.w.w, s.w.sc)) flag = 38;
             else {
+                if (threadIdx.x == 0) mats_dense_ops_post(a.d, mt);
                 for (int i = LCQ_TID; i < a.d.m; i += LCQ_NT) s.w.ctype[i] = mt.ctype[i];
                 __syncthreads();
             }
@@ -518,21 +520,43 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     h->last_mE = mE;
     CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
 
-    // shared-memory plan.  When the batch shares its matrices and the operators of the inner passes fit beside
-    // the instance's own state, one CTA per SM keeps them in shared memory (no L2 round trip per operator
-    // application); otherwise aim at two resident CTAs per SM with the operators in L2, fall back to one.
-    SmemPlan plan = make_plan(d, kSmemSM / 2 - 1024);
-    a.cache_bytes = 0;
-    {
-        const SmemPlan p1 = make_plan(d, kSmemMax);
-        const size_t base = (p1.bytes + 15) / 16 * 16;
-        const size_t hot = a.mats_shared && h->host_mats->status == 0 ? (size_t)h->host_mats->cache_bytes_hot : 0;
-        const size_t raw = a.mats_shared && h->host_mats->status == 0 ? (size_t)h->host_mats->cache_bytes_raw : 0;
-        if (hot > 0 && p1.tinv_in_smem && p1.outer_in_smem && base + hot <= kSmemMax) {
-            plan = p1;
-            a.cache_offset = base;
-            a.cache_bytes = hot + (base + hot + raw <= kSmemMax ? raw : 0);
-        } else if (!(plan.tinv_in_smem && plan.outer_in_smem)) {
+    // Shared-memory plan.  Candidates, best first:
+    //   B: the working-set inverse in L2 (full storage), the inner-pass operators cached in shared memory,
+    //      as many CTAs per SM as fit (several independent instances per SM hide each other's latencies);
+    //   A: everything of the instance in shared memory + all operators + packed SEinv, one CTA per SM;
+    //   C: no operator cache (matrices not shared by the batch, or nothing fits): instance state in shared
+    //      memory, two CTAs per SM when possible.
+    // LCQP_CUDA_PLAN=A|B|C overrides the choice (tuning aid).
+    const bool can_cache = a.mats_shared && h->host_mats->status == 0;
+    const size_t c_se = can_cache ? (size_t)h->host_mats->cache_bytes_se : 0;
+    const size_t c_hot = can_cache ? (size_t)h->host_mats->cache_bytes_hot : 0;
+    const size_t c_raw = can_cache ? (size_t)h->host_mats->cache_bytes_raw : 0;
+    const char* force = getenv("LCQP_CUDA_PLAN");
+    SmemPlan plan;
+    a.cache_bytes = 0; a.cache_what = 0; a.cache_offset = 0;
+    bool chosen = false;
+    auto fits_per_sm = [&](size_t bytes) { return (int)((kSmemSM) / (bytes + 1024 + 2048)); };  // + reserved + static
+    if (can_cache && c_hot > 0 && (!force || force[0] == 'B')) {
+        SmemPlan pb = make_plan(d, 0, true);   // Tinv and the outer-loop vectors in global memory
+        const size_t base = (pb.bytes + 15) / 16 * 16;
+        if (base + c_hot <= kSmemMax && (force || fits_per_sm(base + c_hot) >= 2)) {
+            plan = pb; a.cache_offset = base; a.cache_bytes = c_hot; a.cache_what = 2; chosen = true;
+        }
+    }
+    if (!chosen && can_cache && c_hot > 0 && (!force || force[0] == 'A')) {
+        SmemPlan pa = make_plan(d, kSmemMax);
+        const size_t base = (pa.bytes + 15) / 16 * 16;
+        if (pa.tinv_in_smem && base + c_hot <= kSmemMax) {
+            plan = pa; a.cache_offset = base; a.cache_bytes = c_hot; a.cache_what = 2;
+            if (base + a.cache_bytes + c_se <= kSmemMax) { a.cache_bytes += c_se; a.cache_what |= 1; }
+            if (base + a.cache_bytes + c_raw <= kSmemMax) { a.cache_bytes += c_raw; a.cache_what |= 4; }
+            chosen = true;
+        }
+    }
+    if (!chosen) {
+        plan = make_plan(d, kSmemSM / 2 - 1024);
+        if (!(plan.tinv_in_smem && plan.outer_in_smem)) {
+            const SmemPlan p1 = make_plan(d, kSmemMax);
             if (p1.tinv_in_smem && !plan.tinv_in_smem) plan = p1;
         }
     }

@@ -118,14 +118,16 @@ struct Mats {
     double* T;      // m*m   A Hinv A', then the equality rows eliminated (see prepare_factor)
     double* Minv;   // n*n   (P + sigma I + A' R A)^-1
     double* SEinv;  // ldE*ldE (leading dimension d.ldE), order mE
+    double* AHE;    // ldE*n  the rows of A Hinv that belong to the static equality block (compact)
     int* eidx;      // equality rows that are always in the working set (mE of them)
     signed char* ctype;  // m: -1 free row, 0 inequality, 1 equality, 2 equality found dependent (never active)
     const double* SEinvP;  // packed (lower triangle) copy of SEinv in shared memory, or null
     int mE;
     int status;     // 0 ok, 1 factorisation failed
-    int cache_bytes_hot;   // shared memory that the per-pass operators (and packed SEinv) would take
+    int cache_bytes_se;    // shared memory that the packed SEinv would take,
+    int cache_bytes_hot;   // ... the operators applied in every pass,
     int cache_bytes_raw;   // ... and the operators of the outer loop
-    Op oP, oA, oAt, oHinv, oAH, oAHt, oMinv;
+    Op oP, oA, oAt, oHinv, oAHE, oAHtE, oMinv;   // oAHE: mE x n, oAHtE: n x mE
 };
 
 // Operators on the UNSCALED matrices, used by the outer loop.
@@ -180,6 +182,8 @@ inline LCQ_HD void shrink_dims(Dims& d, int mE)
 struct Scalars {
     double red[64];
     int ired[32];
+    double fred[2][3][8];   // double-buffered partials of the single-barrier reductions (solver CTAs: <= 8 warps)
+    int fired[2][8];
     int bidx;
     int flag;
     int pad[2];
@@ -194,7 +198,8 @@ struct Work {
     double *cE, *vE;                                                // mE
     signed char *W, *Wtry, *Wfail, *ctype, *pin;                    // m
     int* idx;                                                       // cap: rows of the inequality working set
-    double* Tinv;                                                   // packed lower triangle, cap*(cap+1)/2
+    double* Tinv;                                                   // shared memory: packed lower triangle, cap*(cap+1)/2;
+    int tld;                                                        // global memory: full storage, leading dimension tld (0 = packed)
     double* ys;                                                     // m  accepted multipliers, unscaled, qpOASES sign
     // outer loop (unscaled)
     double *xk, *pk, *gk, *gt, *gphi, *stat, *tn;                   // n
@@ -292,19 +297,84 @@ LCQ_DEV int block_argmax(double v, int i, double* vout, Scalars* sc)
     return bi;
 }
 
+// ---- single-barrier reductions for the inner passes ---------------------------------------------------
+// The partials go to one of two buffers, alternating from call to call (`ph` is a per-thread copy of the
+// same counter): the barrier of call k+1 separates the reads of call k from the writes of call k+2.
+// Only for CTAs of at most 8 warps.
+LCQ_DEV double fast_max(double v, Scalars* sc, int& ph)
+{
+    v = warp_max(v);
+    double* buf = sc->fred[ph][0];
+    ph ^= 1;
+    if (LCQ_LANE == 0) buf[LCQ_WARP] = v;
+    LCQ_SYNC();
+    double r = buf[0];
+    for (int k = 1; k < LCQ_NWARP; k++) r = fmax(r, buf[k]);
+    return r;
+}
+
+LCQ_DEV void fast_sum2(double& a, double& b, Scalars* sc, int& ph)
+{
+    a = warp_sum(a);
+    b = warp_sum(b);
+    double* b0 = sc->fred[ph][0];
+    double* b1 = sc->fred[ph][1];
+    ph ^= 1;
+    if (LCQ_LANE == 0) { b0[LCQ_WARP] = a; b1[LCQ_WARP] = b; }
+    LCQ_SYNC();
+    double x = 0, y = 0;
+    for (int k = 0; k < LCQ_NWARP; k++) { x += b0[k]; y += b1[k]; }
+    a = x; b = y;
+}
+
+// lexicographic selection over (alpha ascending, weight descending, index ascending); i < 0: no candidate.
+LCQ_DEV bool lex_better(double a, double wgt, int i, double a2, double w2, int i2)
+{
+    if (i2 < 0) return false;
+    if (i < 0) return true;
+    if (a2 != a) return a2 < a;
+    if (w2 != wgt) return w2 > wgt;
+    return i2 < i;
+}
+
+LCQ_DEV int fast_argmin_lex(double a, double wgt, int i, double* aout, Scalars* sc, int& ph)
+{
+#ifndef LCQP_HOST_EMU
+    for (int o = 16; o > 0; o >>= 1) {
+        const double a2 = __shfl_xor_sync(0xffffffffu, a, o);
+        const double w2 = __shfl_xor_sync(0xffffffffu, wgt, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+        if (lex_better(a, wgt, i, a2, w2, i2)) { a = a2; wgt = w2; i = i2; }
+    }
+#endif
+    double* ba = sc->fred[ph][0];
+    double* bw = sc->fred[ph][1];
+    int* bi = sc->fired[ph];
+    ph ^= 1;
+    if (LCQ_LANE == 0) { ba[LCQ_WARP] = a; bw[LCQ_WARP] = wgt; bi[LCQ_WARP] = i; }
+    LCQ_SYNC();
+    double ra = ba[0], rw = bw[0];
+    int ri = bi[0];
+    for (int k = 1; k < LCQ_NWARP; k++)
+        if (lex_better(ra, rw, ri, ba[k], bw[k], bi[k])) { ra = ba[k]; rw = bw[k]; ri = bi[k]; }
+    *aout = ra;
+    return ri;
+}
+
 // ------------------------------------------------------------------------------------------------
 // operator application
 // ------------------------------------------------------------------------------------------------
-// out[r] = (init ? init[r] : 0) + scale * sum_c M[r][c] v[c]      (no barrier inside)
-LCQ_DEV void op_mv(const Op& op, const double* v, const double* init, double scale, double* out)
+// out[r] = (init ? init[iidx ? iidx[r] : r] : 0) + scale * sum_c M[r][c] v[c]      (no barrier inside)
+LCQ_DEVN void op_mv(const Op& op, const double* v, const double* init, double scale, double* out, const int* iidx = nullptr)
 {
+#define LCQ_INIT(r) (init ? init[iidx ? iidx[r] : (r)] : 0.0)
     if (op.rp) {
         for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
             const int k0 = op.rp[r], k1 = op.rp[r + 1];
             if (k1 - k0 > kLongRow && LCQ_LANES > 1) continue;
             double s = 0;
             for (int k = k0; k < k1; k++) s += op.va[k] * v[op.ci[k]];
-            out[r] = (init ? init[r] : 0.0) + scale * s;
+            out[r] = LCQ_INIT(r) + scale * s;
         }
         if (LCQ_LANES > 1)
             for (int a = LCQ_WARP; a < op.nlong; a += LCQ_NWARP) {
@@ -312,7 +382,7 @@ LCQ_DEV void op_mv(const Op& op, const double* v, const double* init, double sca
                 double s = 0;
                 for (int k = op.rp[r] + LCQ_LANE; k < op.rp[r + 1]; k += LCQ_LANES) s += op.va[k] * v[op.ci[k]];
                 s = warp_sum(s);
-                if (LCQ_LANE == 0) out[r] = (init ? init[r] : 0.0) + scale * s;
+                if (LCQ_LANE == 0) out[r] = LCQ_INIT(r) + scale * s;
             }
     } else if (!op.trans) {
         const int rows = op.rows, cols = op.cols, ld = op.ld;
@@ -330,23 +400,24 @@ LCQ_DEV void op_mv(const Op& op, const double* v, const double* init, double sca
             }
             s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
             if (LCQ_LANE == 0) {
-                out[r0] = (init ? init[r0] : 0.0) + scale * s0;
-                if (r1 < rows) out[r1] = (init ? init[r1] : 0.0) + scale * s1;
-                if (r2 < rows) out[r2] = (init ? init[r2] : 0.0) + scale * s2;
-                if (r3 < rows) out[r3] = (init ? init[r3] : 0.0) + scale * s3;
+                out[r0] = LCQ_INIT(r0) + scale * s0;
+                if (r1 < rows) out[r1] = LCQ_INIT(r1) + scale * s1;
+                if (r2 < rows) out[r2] = LCQ_INIT(r2) + scale * s2;
+                if (r3 < rows) out[r3] = LCQ_INIT(r3) + scale * s3;
             }
         }
     } else {
         for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
             double s = 0;
             for (int c = 0; c < op.cols; c++) s += op.dense[(size_t)c * op.ld + r] * v[c];
-            out[r] = (init ? init[r] : 0.0) + scale * s;
+            out[r] = LCQ_INIT(r) + scale * s;
         }
     }
+#undef LCQ_INIT
 }
 
 // out[a] = sum_c M[idx[a]][c] v[c] - (sub ? sub[idx[a]] : 0)   for a < na   (rows selected by idx; op not transposed)
-LCQ_DEV void op_mv_rows(const Op& op, const int* idx, int na, const double* v, const double* sub, double* out)
+LCQ_DEVN void op_mv_rows(const Op& op, const int* idx, int na, const double* v, const double* sub, double* out)
 {
     if (op.rp) {
         for (int a = LCQ_TID; a < na; a += LCQ_NT) {
@@ -396,15 +467,76 @@ LCQ_DEV void mv_dense(const double* __restrict__ M, int rows, int cols, int ld, 
 // ---- packed symmetric matrix (lower triangle, row-major): S(a,b), b <= a, at a(a+1)/2 + b ----------------
 LCQ_DEV size_t pidx(int a, int b) { return a >= b ? (size_t)a * (a + 1) / 2 + b : (size_t)b * (b + 1) / 2 + a; }
 
-// out[a] = sum_b S(a,b) v[b]
+// f(a, sum_b S(a,b) v[b]) for every row a < nw.  Two threads per row, each over half of the columns: below the
+// diagonal the row is contiguous, above it the column is walked with an incrementally updated offset.
+template <class F>
+LCQ_DEV void sym_mv_f(const double* S, int nw, const double* v, F f)
+{
+#ifdef LCQP_HOST_EMU
+    for (int a = 0; a < nw; a++) {
+        double s = 0;
+        for (int b = 0; b < nw; b++) s += S[pidx(a, b)] * v[b];
+        f(a, s);
+    }
+#else
+    const int half = (nw + 1) >> 1;
+    for (int base = 0; base < 2 * nw; base += LCQ_NT) {
+        const int t = base + LCQ_TID;
+        const int a = t >> 1, h = t & 1;
+        double s = 0;
+        if (a < nw) {
+            const int b0 = h ? half : 0, b1 = h ? nw : half;
+            const double* row = S + (size_t)a * (a + 1) / 2;
+            const int be = b1 < a + 1 ? b1 : a + 1;
+            for (int b = b0; b < be; b++) s += row[b] * v[b];
+            int b = b0 > a + 1 ? b0 : a + 1;
+            const double* q = S + (size_t)b * (b + 1) / 2 + a;
+            for (; b < b1; b++) { s += *q * v[b]; q += b + 1; }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        if (a < nw && h == 0) f(a, s);
+    }
+#endif
+}
+
 LCQ_DEV void sym_mv(const double* S, int nw, const double* v, double* out)
 {
-    for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
-        double s = 0;
-        for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) s += S[pidx(a, b)] * v[b];
-        s = warp_sum(s);
-        if (LCQ_LANE == 0) out[a] = s;
+    sym_mv_f(S, nw, v, [&](int a, double s) { out[a] = s; });
+}
+
+// The same for a symmetric matrix in FULL storage with leading dimension ld (it lives in global memory / L2):
+// one warp per row with coalesced row reads, four rows of a warp in flight; f runs on lane 0.
+template <class F>
+LCQ_DEV void full_mv_f(const double* __restrict__ M, int nw, int ld, const double* v, F f)
+{
+    for (int r0 = LCQ_WARP; r0 < nw; r0 += 4 * LCQ_NWARP) {
+        const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
+        const double* a0 = M + (size_t)r0 * ld;
+        const double* a1 = M + (size_t)(r1 < nw ? r1 : r0) * ld;
+        const double* a2 = M + (size_t)(r2 < nw ? r2 : r0) * ld;
+        const double* a3 = M + (size_t)(r3 < nw ? r3 : r0) * ld;
+        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        for (int c = LCQ_LANE; c < nw; c += LCQ_LANES) {
+            const double vc = v[c];
+            const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
+            s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+        if (LCQ_LANE == 0) {
+            f(r0, s0);
+            if (r1 < nw) f(r1, s1);
+            if (r2 < nw) f(r2, s2);
+            if (r3 < nw) f(r3, s3);
+        }
     }
+}
+
+// f(a, (Tinv v)[a]) for the working-set inverse in either storage
+template <class F>
+LCQ_DEV void tinv_mv_f(const Work& w, int nw, const double* v, F f)
+{
+    if (w.tld) full_mv_f(w.Tinv, nw, w.tld, v, f);
+    else sym_mv_f(w.Tinv, nw, v, f);
 }
 
 LCQ_DEV double limit_scaling(double v)
@@ -732,6 +864,10 @@ LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, c
             LCQ_SYNC();
         }
     }
+    for (int e = LCQ_TID; e < mE * n; e += LCQ_NT) {
+        const int a = e / n, j = e - a * n;
+        mt.AHE[e] = mt.AH[(size_t)mt.eidx[a] * n + j];
+    }
     if (LCQ_TID == 0) { mt.mE = mE; mt.status = 0; }
     LCQ_SYNC();
     (void)uu;
@@ -746,9 +882,14 @@ LCQ_DEV void mats_dense_ops(const Dims& d, Mats& mt)
     mt.oA = dense_op(mt.A, m, n, n, 0);
     mt.oAt = dense_op(mt.A, n, m, n, 1);
     mt.oHinv = dense_op(mt.Hinv, n, n, n, 0);
-    mt.oAH = dense_op(mt.AH, m, n, n, 0);
-    mt.oAHt = dense_op(mt.AH, n, m, n, 1);
     mt.oMinv = dense_op(mt.Minv, n, n, n, 0);
+}
+
+// the operators of the static equality block need its order (known after prepare_factor)
+LCQ_DEV void mats_dense_ops_post(const Dims& d, Mats& mt)
+{
+    mt.oAHE = dense_op(mt.AHE, mt.mE, d.n, d.n, 0);
+    mt.oAHtE = dense_op(mt.AHE, d.n, mt.mE, d.n, 1);
 }
 
 // ... or CSR copies where the matrix is sparse (shared preparation, done once per batch): the scaled
@@ -768,10 +909,11 @@ LCQ_DEVN void mats_build_ops_post(const Dims& d, Mats& mt, CsrPool& pool, Scalar
 {
     const int n = d.n, m = d.m;
     const Op a = build_op(mt.Hinv, n, n, n, 0, pool, sc);
-    const Op b = build_op(mt.AH, m, n, n, 0, pool, sc);
-    const Op c = build_op(mt.AH, n, m, n, 1, pool, sc);
+    const Op b = build_op(mt.AHE, mt.mE, n, n, 0, pool, sc);
+    const Op c = build_op(mt.AHE, n, mt.mE, n, 1, pool, sc);
     const Op e = build_op(mt.Minv, n, n, n, 0, pool, sc);
-    if (LCQ_TID == 0) { mt.oHinv = a; mt.oAH = b; mt.oAHt = c; mt.oMinv = e; }
+    (void)m;
+    if (LCQ_TID == 0) { mt.oHinv = a; mt.oAHE = b; mt.oAHtE = c; mt.oMinv = e; }
     LCQ_SYNC();
 }
 
@@ -838,15 +980,16 @@ LCQ_DEVN void cache_op(Op& op, unsigned char*& cur, unsigned char* end)
     cur += need;
 }
 
-// `mt` / `ro` are this CTA's block-shared copies; one thread writes them.
-LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsigned char* base, size_t bytes)
+// `mt` / `ro` are this CTA's block-shared copies; one thread writes them.  what: bit0 packed SEinv,
+// bit1 the operators of the inner passes, bit2 the operators of the outer loop.
+LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsigned char* base, size_t bytes, int what)
 {
     unsigned char* cur = base;
     unsigned char* end = base + bytes;
     const int mE = mt.mE;
     LCQ_SYNC();
     const double* sep = nullptr;
-    if (mE > 0) {
+    if (mE > 0 && (what & 1)) {
         const size_t need = ((size_t)mE * (mE + 1) / 2 * sizeof(double) + 15) / 16 * 16;
         if (cur + need <= end) {
             double* P = reinterpret_cast<double*>(cur);
@@ -858,28 +1001,33 @@ LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsign
             cur += need;
         }
     }
-    Op oA = mt.oA, oAt = mt.oAt, oAH = mt.oAH, oAHt = mt.oAHt, oHinv = mt.oHinv, oP = mt.oP;
-    cache_op(oA, cur, end); cache_op(oAt, cur, end); cache_op(oAH, cur, end); cache_op(oAHt, cur, end);
-    cache_op(oHinv, cur, end); cache_op(oP, cur, end);
+    Op oA = mt.oA, oAt = mt.oAt, oAHE = mt.oAHE, oAHtE = mt.oAHtE, oHinv = mt.oHinv, oP = mt.oP;
+    if (what & 2) {
+        cache_op(oA, cur, end); cache_op(oAt, cur, end); cache_op(oAHE, cur, end); cache_op(oAHtE, cur, end);
+        cache_op(oHinv, cur, end); cache_op(oP, cur, end);
+    }
     Op rL = ro.L, rR = ro.R, rLt = ro.Lt, rRt = ro.Rt, rQ = ro.Q, rAt = ro.At;
-    cache_op(rL, cur, end); cache_op(rR, cur, end); cache_op(rLt, cur, end); cache_op(rRt, cur, end);
-    cache_op(rQ, cur, end); cache_op(rAt, cur, end);
+    if (what & 4) {
+        cache_op(rL, cur, end); cache_op(rR, cur, end); cache_op(rLt, cur, end); cache_op(rRt, cur, end);
+        cache_op(rQ, cur, end); cache_op(rAt, cur, end);
+    }
     LCQ_SYNC();
     if (LCQ_TID == 0) {
         mt.SEinvP = sep;
-        mt.oA = oA; mt.oAt = oAt; mt.oAH = oAH; mt.oAHt = oAHt; mt.oHinv = oHinv; mt.oP = oP;
+        mt.oA = oA; mt.oAt = oAt; mt.oAHE = oAHE; mt.oAHtE = oAHtE; mt.oHinv = oHinv; mt.oP = oP;
         ro.L = rL; ro.R = rR; ro.Lt = rLt; ro.Rt = rRt; ro.Q = rQ; ro.At = rAt;
     }
     LCQ_SYNC();
 }
 
 // bytes the cache would take (thread 0 of the prepare step calls this)
-LCQ_DEV void cache_requirements(const Mats& mt, const RawOps& ro, int* hot, int* raw)
+LCQ_DEV void cache_requirements(Mats& mt, const RawOps& ro)
 {
-    size_t h = ((size_t)mt.mE * (mt.mE + 1) / 2 * sizeof(double) + 15) / 16 * 16;
-    h += op_cache_bytes(mt.oA) + op_cache_bytes(mt.oAt) + op_cache_bytes(mt.oAH) + op_cache_bytes(mt.oAHt) + op_cache_bytes(mt.oHinv) + op_cache_bytes(mt.oP);
-    size_t r = op_cache_bytes(ro.L) + op_cache_bytes(ro.R) + op_cache_bytes(ro.Lt) + op_cache_bytes(ro.Rt) + op_cache_bytes(ro.Q) + op_cache_bytes(ro.At);
-    *hot = (int)h; *raw = (int)r;
+    mt.cache_bytes_se = (int)(((size_t)mt.mE * (mt.mE + 1) / 2 * sizeof(double) + 15) / 16 * 16);
+    mt.cache_bytes_hot = (int)(op_cache_bytes(mt.oA) + op_cache_bytes(mt.oAt) + op_cache_bytes(mt.oAHE) + op_cache_bytes(mt.oAHtE) +
+                               op_cache_bytes(mt.oHinv) + op_cache_bytes(mt.oP));
+    mt.cache_bytes_raw = (int)(op_cache_bytes(ro.L) + op_cache_bytes(ro.R) + op_cache_bytes(ro.Lt) + op_cache_bytes(ro.Rt) +
+                               op_cache_bytes(ro.Q) + op_cache_bytes(ro.At));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -893,6 +1041,7 @@ struct QP {
     int nw;           // rows in the inequality working set = order of Tinv (idx[0..nw))
     int have_W;
     int tinv_valid;   // Tinv matches idx/W
+    int ph;           // phase of the single-barrier reductions
     long long n_admm, n_pass, n_changes;
 };
 
@@ -953,20 +1102,29 @@ LCQ_DEVN int tinv_append(QP& s, int j)
     const double* Tj = s.mt->T + (size_t)j * m;
     for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.dI[a] = Tj[w.idx[a]];
     LCQ_SYNC();
-    sym_mv(Si, nw, w.dI, w.lI);
-    LCQ_SYNC();
     double p1 = 0, p2 = 0;
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) { p1 += w.dI[a] * w.lI[a]; p2 += w.lI[a] * w.lI[a]; }
-    block_sum2(p1, p2, w.sc);
+    tinv_mv_f(w, nw, w.dI, [&](int a, double v) { w.lI[a] = v; p1 += w.dI[a] * v; p2 += v * v; });
+    fast_sum2(p1, p2, w.sc, s.ph);
     const double kappa = Tj[j] + s.o->qp_delta - p1;
     if (!(kappa > 10.0 * s.o->qp_delta * (1.0 + p2))) return 1;
     const double ik = 1.0 / kappa;
-    for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
-        const double ua = w.lI[a] * ik;
-        double* row = Si + (size_t)a * (a + 1) / 2;
-        for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] += ua * w.lI[b];
-    }
-    {
+    if (w.tld) {
+        const int ld = w.tld;
+        for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
+            const double ua = w.lI[a] * ik;
+            double* row = Si + (size_t)a * ld;
+            for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) row[b] += ua * w.lI[b];
+            if (LCQ_LANE == 0) row[nw] = -ua;
+        }
+        double* row = Si + (size_t)nw * ld;
+        for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
+        if (LCQ_TID == 0) { row[nw] = ik; w.idx[nw] = j; }
+    } else {
+        for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
+            const double ua = w.lI[a] * ik;
+            double* row = Si + (size_t)a * (a + 1) / 2;
+            for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] += ua * w.lI[b];
+        }
         double* row = Si + (size_t)nw * (nw + 1) / 2;
         for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
         if (LCQ_TID == 0) { row[nw] = ik; w.idx[nw] = j; }
@@ -982,19 +1140,30 @@ LCQ_DEVN void tinv_remove(QP& s, int p)
     Work& w = s.w;
     const int nw = s.nw, last = nw - 1;
     double* Si = w.Tinv;
-    for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.dI[b] = Si[pidx(b, p)];
+    const int ld = w.tld;
+    for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.dI[b] = ld ? Si[(size_t)b * ld + p] : Si[pidx(b, p)];
     LCQ_SYNC();
     const double ic = 1.0 / w.dI[p];
     for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
         const double ca = w.dI[a] * ic;
-        double* row = Si + (size_t)a * (a + 1) / 2;
-        for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] -= ca * w.dI[b];
+        if (ld) {
+            double* row = Si + (size_t)a * ld;
+            for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) row[b] -= ca * w.dI[b];
+        } else {
+            double* row = Si + (size_t)a * (a + 1) / 2;
+            for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] -= ca * w.dI[b];
+        }
     }
     LCQ_SYNC();
     if (p != last) {
-        for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.lI[b] = Si[pidx(last, b)];
+        // move row/column `last` into position p
+        for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.lI[b] = ld ? Si[(size_t)last * ld + b] : Si[pidx(last, b)];
         LCQ_SYNC();
-        for (int b = LCQ_TID; b < last; b += LCQ_NT) Si[pidx(p, b)] = (b == p) ? w.lI[last] : w.lI[b];
+        for (int b = LCQ_TID; b < last; b += LCQ_NT) {
+            const double v = (b == p) ? w.lI[last] : w.lI[b];
+            if (ld) { Si[(size_t)p * ld + b] = v; Si[(size_t)b * ld + p] = v; }
+            else Si[pidx(p, b)] = v;
+        }
         if (LCQ_TID == 0) w.idx[p] = w.idx[last];
     }
     s.nw = last;
@@ -1027,78 +1196,69 @@ LCQ_DEVN void tinv_build(QP& s, signed char* W)
 
 // Solve the regularised KKT system of the working set,
 //     [P + dI, Aw'; Aw, -dI] [dx; dlam] = [r1; r2],
-// r2 / dlam full-length (m) vectors of which only the rows in W count / are written (others: dlam = 0).
+// r2 / dlam full-length (m) vectors of which only the rows in W count / are written.
 // Block elimination: Hinv, then the static equality block (SEinv), then the inequality rows (Tinv).
-// In: w.r1, w.r2.  Out: w.dx, w.dlam.  Scratch: u, t, cE, vE, dI, lI, yf.
+// In: w.r1, w.r2.  Out: w.dx, w.dlam.  Scratch: u, t, cE, vE, dI, yf.
+// Invariants kept by the callers: yf is zero on entry (and on exit); dlam is zero outside the working set.
 LCQ_DEVN void kkt_solve(QP& s)
 {
-    const int n = s.d.n, m = s.d.m, nw = s.nw;
+    const int n = s.d.n, nw = s.nw;
     Work& w = s.w;
     const Mats& mt = *s.mt;
     const int mE = mt.mE;
+    const int ldE = s.d.ldE;
+    // the equality-block solve: f(a, (SEinv cE)[a])
+    auto se_solve = [&](auto f) {
+        if (mt.SEinvP) sym_mv_f(mt.SEinvP, mE, w.cE, f);
+        else full_mv_f(mt.SEinv, mE, ldE, w.cE, f);
+    };
     // K^-1 [r1; r2_E]:  u = Hinv r1, vE = SEinv (A_E u - r2_E), t = u - (Hinv A_E') vE
-    op_mv(mt.oHinv, w.r1, nullptr, 1.0, w.u);
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }
+    op_mv(mt.oHinv, w.r1, nullptr, 1.0, (mE > 0 || nw > 0) ? w.u : w.dx);
     if (mE > 0) {
-        op_mv_rows(mt.oAH, mt.eidx, mE, w.r1, w.r2, w.cE);
+        op_mv(mt.oAHE, w.r1, w.r2, -1.0, w.cE, mt.eidx);   // cE = r2_E - AHE r1  (sign folded below)
         LCQ_SYNC();
-        if (mt.SEinvP) sym_mv(mt.SEinvP, mE, w.cE, w.vE); else mv_dense(mt.SEinv, mE, mE, s.d.ldE, w.cE, w.vE);
+        if (nw == 0) se_solve([&](int a, double v) { w.vE[a] = -v; w.dlam[mt.eidx[a]] = -v; });
+        else se_solve([&](int a, double v) { w.vE[a] = -v; });
         LCQ_SYNC();
-        for (int a = LCQ_TID; a < mE; a += LCQ_NT) w.yf[mt.eidx[a]] = w.vE[a];
-        LCQ_SYNC();
-        op_mv(mt.oAHt, w.yf, w.u, -1.0, w.t);
-    } else {
+        op_mv(mt.oAHtE, w.vE, w.u, -1.0, nw == 0 ? w.dx : w.t);
+    } else if (nw > 0) {
         LCQ_SYNC();
         for (int j = LCQ_TID; j < n; j += LCQ_NT) w.t[j] = w.u[j];
     }
-    if (nw == 0) {
-        LCQ_SYNC();
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.dx[j] = w.t[j];
-        for (int a = LCQ_TID; a < mE; a += LCQ_NT) w.dlam[mt.eidx[a]] = w.vE[a];
-        LCQ_SYNC();
-        return;
-    }
     LCQ_SYNC();
+    if (nw == 0) return;
     // lI = Tinv (A_I t - r2_I)
     op_mv_rows(mt.oA, w.idx, nw, w.t, w.r2, w.dI);
     LCQ_SYNC();
-    sym_mv(w.Tinv, nw, w.dI, w.lI);
+    tinv_mv_f(w, nw, w.dI, [&](int a, double v) { const int i = w.idx[a]; w.yf[i] = v; w.dlam[i] = v; });
     LCQ_SYNC();
     // second K^-1 on [r1 - A_I' lI; r2_E]
-    for (int a = LCQ_TID; a < mE; a += LCQ_NT) w.yf[mt.eidx[a]] = 0.0;
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) { w.yf[w.idx[a]] = w.lI[a]; w.dlam[w.idx[a]] = w.lI[a]; }
+    op_mv(mt.oAt, w.yf, w.r1, -1.0, w.t);
     LCQ_SYNC();
-    op_mv(mt.oAt, w.yf, w.r1, -1.0, w.t);   // t = r1 - A_I' lI
-    LCQ_SYNC();
-    op_mv(mt.oHinv, w.t, nullptr, 1.0, w.u);
+    op_mv(mt.oHinv, w.t, nullptr, 1.0, mE > 0 ? w.u : w.dx);
+    for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.yf[w.idx[a]] = 0.0;
     if (mE > 0) {
-        op_mv_rows(mt.oAH, mt.eidx, mE, w.t, w.r2, w.cE);
-        for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.yf[w.idx[a]] = 0.0;
+        op_mv(mt.oAHE, w.t, w.r2, -1.0, w.cE, mt.eidx);
         LCQ_SYNC();
-        if (mt.SEinvP) sym_mv(mt.SEinvP, mE, w.cE, w.vE); else mv_dense(mt.SEinv, mE, mE, s.d.ldE, w.cE, w.vE);
+        se_solve([&](int a, double v) { w.vE[a] = -v; w.dlam[mt.eidx[a]] = -v; });
         LCQ_SYNC();
-        for (int a = LCQ_TID; a < mE; a += LCQ_NT) { w.yf[mt.eidx[a]] = w.vE[a]; w.dlam[mt.eidx[a]] = w.vE[a]; }
-        LCQ_SYNC();
-        op_mv(mt.oAHt, w.yf, w.u, -1.0, w.dx);
-    } else {
-        LCQ_SYNC();
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.dx[j] = w.u[j];
+        op_mv(mt.oAHtE, w.vE, w.u, -1.0, w.dx);
     }
     LCQ_SYNC();
 }
 
 // Residual of the UNREGULARISED KKT system of working set W at (x, lam):
-//   r1 = -q - P x - A' lam,  r2[i] = b_i - (A x)_i for rows in W (0 elsewhere);  also leaves px = P x, zx = A x.
+//   r1 = -q - P x - A' lam,  r2[i] = b_i - (A x)_i for rows in W (0 elsewhere);  also leaves zx = A x.
 // Returns the infinity norm of (r1, r2).
 LCQ_DEVN double kkt_residual(QP& s, const signed char* W, const double* x, const double* lam)
 {
     const int n = s.d.n, m = s.d.m;
     Work& w = s.w;
     const Mats& mt = *s.mt;
-    op_mv(mt.oP, x, nullptr, 1.0, w.px);
+    op_mv(mt.oP, x, w.q, 1.0, w.px);            // q + P x
+    op_mv(mt.oAt, lam, nullptr, 1.0, w.u);      // A' lam
     op_mv(mt.oA, x, nullptr, 1.0, w.zx);
     LCQ_SYNC();
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.u[j] = -w.q[j] - w.px[j];
     double rn = 0;
     for (int i = LCQ_TID; i < m; i += LCQ_NT) {
         double r = 0.0;
@@ -1106,14 +1266,15 @@ LCQ_DEVN double kkt_residual(QP& s, const signed char* W, const double* x, const
         w.r2[i] = r;
         rn = fmax(rn, fabs(r));
     }
-    LCQ_SYNC();
-    op_mv(mt.oAt, lam, w.u, -1.0, w.r1);
-    LCQ_SYNC();
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) rn = fmax(rn, fabs(w.r1[j]));
-    return block_max(rn, w.sc);
+    for (int j = LCQ_TID; j < n; j += LCQ_NT) {
+        const double r = -w.px[j] - w.u[j];
+        w.r1[j] = r;
+        rn = fmax(rn, fabs(r));
+    }
+    return fast_max(rn, w.sc, s.ph);
 }
 
-// KKT conditions of the full QP at (x, lam) with px, zx, r1 as left by kkt_residual.  0 = satisfied;
+// KKT conditions of the full QP at (x, lam) with zx, r1 as left by kkt_residual.  0 = satisfied;
 // 2 stationarity, 3 active row off its bound, 4 inactive row violated, 5/6 wrong multiplier sign
 // (*worst = position in idx to drop).
 LCQ_DEVN int kkt_check(QP& s, const signed char* W, const double* lam, int* worst)
@@ -1192,6 +1353,8 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
     int last_dropped = -1;
     double best = INFINITY;
     int passes = 0;      // corrections since the last working-set change
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }   // invariants of kkt_solve
+    LCQ_SYNC();
     bool dirty = ratio_test;   // (xa, lam) is not the from-zero solution on W
     bool clean = false;        // the from-zero recomputation is running: no ratio tests
     for (int it = 0; it < cap_it; it++) {
@@ -1233,7 +1396,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             if ((reason == 5 || reason == 6) && worst >= 0) {
                 const int row = w.idx[worst];
                 LCQ_SYNC();
-                if (LCQ_TID == 0) { W[row] = 0; w.lam[row] = 0.0; }
+                if (LCQ_TID == 0) { W[row] = 0; w.lam[row] = 0.0; w.dlam[row] = 0.0; }
                 for (int i = LCQ_TID; i < m; i += LCQ_NT) w.pin[i] &= 1;
                 tinv_remove(s, worst);
 #ifdef LCQP_HOST_EMU
@@ -1262,9 +1425,10 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             op_mv(mt.oA, w.dx, nullptr, 1.0, w.zp);
             LCQ_SYNC();
             for (int i = LCQ_TID; i < m; i += LCQ_NT) apn = fmax(apn, fabs(w.zp[i]));
-            apn = block_max(apn, w.sc);
+            apn = fast_max(apn, w.sc, s.ph);
             const double seps = 1e-13 * (1.0 + apn);
             for (;;) {
+                // the smallest step length; among the rows attaining it the largest |s|, then the smallest row
                 double ba = 2.0, bs = 0.0;
                 int bi = -1;
                 for (int i = LCQ_TID; i < m; i += LCQ_NT) {
@@ -1274,16 +1438,11 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                     if (sv < -seps && w.l[i] > -INFINITY) a = fmax(w.zx[i] - w.l[i], 0.0) / (-sv);
                     else if (sv > seps && w.ub[i] < INFINITY) a = fmax(w.ub[i] - w.zx[i], 0.0) / sv;
                     else continue;
-                    if (a < 1.0 && (bi < 0 || a < ba || (a == ba && fabs(sv) > bs))) { ba = a; bs = fabs(sv); bi = i; }
+                    if (a < 1.0 && lex_better(ba, bs, bi, a, fabs(sv), i)) { ba = a; bs = fabs(sv); bi = i; }
                 }
-                // two-stage reduction: the minimal alpha, then among the rows attaining it the largest |s|
-                const double am = -block_max(bi >= 0 ? -ba : -2.0, w.sc);
-                block = -1;
-                if (am < 1.0) {
-                    double vout;
-                    block = block_argmax((bi >= 0 && ba == am) ? bs : -1.0, (bi >= 0 && ba == am) ? bi : -1, &vout, w.sc);
-                    if (block >= 0) amin = am;
-                }
+                double am;
+                block = fast_argmin_lex(ba, bs, bi, &am, w.sc, s.ph);
+                amin = block >= 0 ? am : 1.0;
                 if (block < 0) break;
                 if (s.nw >= s.d.cap) return 1;
                 if (tinv_append(s, block) == 0) break;
@@ -1330,6 +1489,7 @@ LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin)
     Work& w = s.w;
     const Mats& mt = *s.mt;
     for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = xin[j];
+    for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }   // invariants of kkt_solve
     LCQ_SYNC();
     for (int pass = 0; pass < 4; pass++) {
         op_mv(mt.oA, w.xa, nullptr, 1.0, w.zx);
@@ -1711,7 +1871,7 @@ struct SmemPlan {
     size_t gl_doubles;   // doubles of global scratch per CTA for what did not fit
 };
 
-inline LCQ_HD size_t qp_doubles(const Dims& d) { return 8ull * d.n + 11ull * d.m + 2ull * d.cap + 2ull * d.capE + d.m /*ys*/; }
+inline LCQ_HD size_t qp_doubles(const Dims& d) { return 7ull * d.n + 10ull * d.m + 2ull * d.cap + 2ull * d.capE + d.m /*ys*/; }
 inline LCQ_HD size_t outer_doubles(const Dims& d) { return 7ull * d.n + 2ull * d.nComp; }
 inline LCQ_HD size_t tinv_doubles(const Dims& d) { return (size_t)d.cap * (d.cap + 1) / 2; }
 inline LCQ_HD size_t misc_bytes(const Dims& d)
@@ -1719,13 +1879,14 @@ inline LCQ_HD size_t misc_bytes(const Dims& d)
     return (size_t)d.cap * sizeof(int) + 5ull * ((d.m + 15) / 16) * 16 + sizeof(Scalars) + 64;
 }
 
-inline LCQ_HD SmemPlan make_plan(const Dims& d, size_t budget)
+// tinv_global: keep the working-set inverse in global memory (full storage) even if it would fit
+inline LCQ_HD SmemPlan make_plan(const Dims& d, size_t budget, bool tinv_global = false)
 {
     SmemPlan p;
     size_t b = qp_doubles(d) * sizeof(double) + misc_bytes(d);
     p.gl_doubles = 0;
-    p.tinv_in_smem = (b + tinv_doubles(d) * sizeof(double) <= budget);
-    if (p.tinv_in_smem) b += tinv_doubles(d) * sizeof(double); else p.gl_doubles += tinv_doubles(d);
+    p.tinv_in_smem = !tinv_global && (b + tinv_doubles(d) * sizeof(double) <= budget);
+    if (p.tinv_in_smem) b += tinv_doubles(d) * sizeof(double); else p.gl_doubles += (size_t)d.cap * d.cap;
     p.outer_in_smem = (b + outer_doubles(d) * sizeof(double) <= budget);
     if (p.outer_in_smem) b += outer_doubles(d) * sizeof(double); else p.gl_doubles += outer_doubles(d);
     p.bytes = b;
@@ -1738,13 +1899,16 @@ LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* bas
     auto take = [&](size_t k) { double* r = q; q += k; return r; };
     auto takeg = [&](size_t k) { double* r = gl; gl += k; return r; };
     const int n = d.n, m = d.m;
-    w.q = take(n); w.x = take(n); w.xa = take(n); w.px = take(n); w.r1 = take(n); w.u = take(n); w.t = take(n); w.dx = take(n);
+    w.q = take(n); w.x = take(n); w.xa = take(n); w.r1 = take(n); w.u = take(n); w.t = take(n); w.dx = take(n);
+    w.px = w.t;   // q + P x lives only inside kkt_residual, t only inside kkt_solve / admm_iter
     w.z = take(m); w.y = take(m); w.l = take(m); w.ub = take(m); w.lam = take(m); w.dlam = take(m); w.r2 = take(m);
-    w.zx = take(m); w.zp = take(m); w.w = take(m); w.yf = take(m);
+    w.zx = take(m); w.zp = take(m); w.yf = take(m);
+    w.w = w.yf;   // ADMM scratch; yf is scratch of the active-set passes (zeroed before they start)
     w.dI = take(d.cap); w.lI = take(d.cap);
     w.cE = take(d.capE); w.vE = take(d.capE);
     w.ys = take(m);
-    w.Tinv = p.tinv_in_smem ? take(tinv_doubles(d)) : takeg(tinv_doubles(d));
+    w.Tinv = p.tinv_in_smem ? take(tinv_doubles(d)) : takeg((size_t)d.cap * d.cap);
+    w.tld = p.tinv_in_smem ? 0 : d.cap;
     auto tk = [&](size_t k) { return p.outer_in_smem ? take(k) : takeg(k); };
     w.xk = tk(n); w.pk = tk(n); w.gk = tk(n); w.gt = tk(n); w.gphi = tk(n); w.stat = tk(n); w.tn = tk(n);
     w.Lx = tk(d.nComp); w.Rx = tk(d.nComp);
@@ -1761,7 +1925,7 @@ LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* bas
 inline LCQ_HD size_t mats_doubles(const Dims& d)
 {
     const size_t n = d.n, m = d.m;
-    return 3 * n * n + 2 * m * n + n + m + m * m + (size_t)d.ldE * d.ldE + (m + 1) / 2 /*eidx*/ + (m + 7) / 8 /*ctype*/ + 2;
+    return 3 * n * n + 2 * m * n + n + m + m * m + (size_t)d.ldE * d.ldE + (size_t)d.ldE * n + (m + 1) / 2 /*eidx*/ + (m + 7) / 8 /*ctype*/ + 2;
 }
 
 LCQ_DEV void carve_mats(Mats& mt, double* base, const Dims& d)
@@ -1777,10 +1941,11 @@ LCQ_DEV void carve_mats(Mats& mt, double* base, const Dims& d)
     mt.T = base; base += m * m;
     mt.Minv = base; base += n * n;
     mt.SEinv = base; base += (size_t)mEcap * mEcap;
+    mt.AHE = base; base += (size_t)mEcap * n;
     mt.eidx = reinterpret_cast<int*>(base); base += (m + 1) / 2;
     mt.ctype = reinterpret_cast<signed char*>(base);
     mt.SEinvP = nullptr;
-    mt.mE = 0; mt.status = 0; mt.cache_bytes_hot = 0; mt.cache_bytes_raw = 0;
+    mt.mE = 0; mt.status = 0; mt.cache_bytes_se = 0; mt.cache_bytes_hot = 0; mt.cache_bytes_raw = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1795,7 +1960,7 @@ LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, co
     const lcqp_cuda_options& o = *s.o;
     const int nD = d.n + d.mA;
     s.mt = &mt;
-    s.nw = 0; s.have_W = 0; s.tinv_valid = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
+    s.nw = 0; s.have_W = 0; s.tinv_valid = 0; s.ph = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
     out.ret = 0; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
     bool skip = false;
     // initializeSolver checks (LCQProblem.cpp:930-957): the OSQP-style layout has no box constraints
@@ -1813,6 +1978,8 @@ LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, co
         if (!skip && !infeasible) {
             if (!mats_shared) {
                 prep_rc = prepare_factor(d, mt, w.ctype, o, w.u, w.t, w.zx, w.zp, w.w, w.sc);
+                if (LCQ_TID == 0 && !prep_rc) mats_dense_ops_post(d, mt);
+                LCQ_SYNC();
             } else {
                 int diff = (mt.status != 0);
                 for (int i = LCQ_TID; i < d.m; i += LCQ_NT) diff |= ((w.ctype[i] == 1) != (mt.ctype[i] >= 1)) || ((w.ctype[i] < 0) != (mt.ctype[i] < 0));

@@ -69,20 +69,25 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
             mats_build_ops_pre(d, shared_mt, pool, &sc);
             set_bounds(d, in0, shared_mt.E, lo.data(), up.data(), ctype.data(), &sc);
             int rc = prepare_factor(d, shared_mt, ctype.data(), *o, v1.data(), v2.data(), e1.data(), e2.data(), e3.data(), &sc);
+            if (rc == 0) mats_dense_ops_post(d, shared_mt);
             if (rc == 0) mats_build_ops_post(d, shared_mt, pool, &sc);
             shared_mt.status = rc;
             if (rc == 0) shrink_dims(d, shared_mt.mE);
         }
     }
-    // the persistent solver CTA (lcqp_solve_kernel), with the shared-memory operator cache when it fits
-    const SmemPlan plan = make_plan(d, 227 * 1024);
+    // the persistent solver CTA (lcqp_solve_kernel); LCQP_EMU_PLAN selects the memory plan like the host code does:
+    //   A (default) everything in "shared memory" + operator cache, B working-set inverse in "global memory"
+    //   (full storage) + operator cache, C no operator cache
+    const char* pl = getenv("LCQP_EMU_PLAN");
+    const char plan_id = pl ? pl[0] : 'A';
+    const SmemPlan plan = plan_id == 'B' ? make_plan(d, 0, true) : make_plan(d, 227 * 1024);
     size_t cache_bytes = 0;
+    int cache_what = 0;
     const size_t cache_offset = (plan.bytes + 15) / 16 * 16;
-    if (mats_shared && shared_mt.status == 0) {
-        cache_requirements(shared_mt, shared_ro, &shared_mt.cache_bytes_hot, &shared_mt.cache_bytes_raw);
-        if (plan.tinv_in_smem && plan.outer_in_smem && cache_offset + shared_mt.cache_bytes_hot <= 227 * 1024)
-            cache_bytes = shared_mt.cache_bytes_hot + (cache_offset + shared_mt.cache_bytes_hot + shared_mt.cache_bytes_raw <= 227 * 1024 ? shared_mt.cache_bytes_raw : 0);
-        if (getenv("LCQP_EMU_NO_CACHE")) cache_bytes = 0;
+    if (mats_shared && shared_mt.status == 0 && plan_id != 'C') {
+        cache_requirements(shared_mt, shared_ro);
+        cache_bytes = shared_mt.cache_bytes_hot; cache_what = 2;
+        if (plan_id == 'A') { cache_bytes += shared_mt.cache_bytes_se + shared_mt.cache_bytes_raw; cache_what = 7; }
     }
     std::vector<double> smem_d((cache_offset + cache_bytes + 64) / 8 + 2);
     unsigned char* smem = reinterpret_cast<unsigned char*>(smem_d.data());
@@ -95,7 +100,7 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
     Mats mt;
     if (mats_shared) mt = shared_mt; else carve_mats(mt, ws.data(), d);
     RawOps ro = shared_ro;
-    if (cache_bytes) cache_shared_operators(d, mt, ro, smem + cache_offset, cache_bytes);
+    if (cache_bytes) cache_shared_operators(d, mt, ro, smem + cache_offset, cache_bytes, cache_what);
     const int nD = nV + nC + 2 * nComp;
     int nfail = 0;
     for (int b = 0; b < batch; b++) {
