@@ -103,12 +103,18 @@ __global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_co
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Mats mt;
     __shared__ RawOps ro;
+    __shared__ Work wk;
+    __shared__ Dims dm;
+    __shared__ lcqp_cuda_options opt;
     QP s;
-    s.d = a.d;
-    s.o = &a.o;
+    s.d = &dm;
+    s.o = &opt;
+    s.w = &wk;
     double* ws = a.workspace + a.ws_stride * blockIdx.x;
-    carve(s.w, a.d, a.plan, smem, ws + a.ws_mats_doubles);
     if (threadIdx.x == 0) {
+        dm = a.d;
+        opt = a.o;
+        carve(wk, a.d, a.plan, smem, ws + a.ws_mats_doubles);
         if (a.mats_shared) mt = *a.shared_mats;
         else carve_mats(mt, ws, a.d);
         ro = *a.shared_raw;
@@ -121,9 +127,9 @@ __global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_co
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s.w.sc->bidx = (int)atomicAdd(a.counter, 1u);
+        if (threadIdx.x == 0) wk.sc->bidx = (int)atomicAdd(a.counter, 1u);
         __syncthreads();
-        const int b = s.w.sc->bidx;
+        const int b = wk.sc->bidx;
         if (b >= a.batch) break;
         const Inst in = make_inst(a, b);
         if (!raw_all_shared) {
@@ -172,10 +178,15 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ Mats mt;
+    __shared__ Work wk;
+    __shared__ Dims dm;
+    __shared__ lcqp_cuda_options opt;
     QP s;
-    s.d = a.d;
-    s.o = &a.o;
-    carve(s.w, a.d, a.plan, smem, a.gl);
+    s.d = &dm;
+    s.o = &opt;
+    s.w = &wk;
+    if (threadIdx.x == 0) { dm = a.d; opt = a.o; carve(wk, a.d, a.plan, smem, a.gl); }
+    __syncthreads();
     s.ph = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
     if (!a.initial) {
         for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
@@ -191,14 +202,14 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
     int infeasible = a.initial ? 0 : a.state->infeasible;
     int flag = 0, iters = 0;
     if (a.initial) {
-        prepare_scale(a.d, a.in, mt, s.w.u, s.w.zx);
-        const int bflags = set_bounds(a.d, a.in, mt.E, s.w.l, s.w.ub, s.w.ctype, s.w.sc);
+        prepare_scale(a.d, a.in, mt, wk.u, wk.zx);
+        const int bflags = set_bounds(a.d, a.in, mt.E, wk.l, wk.ub, wk.ctype, wk.sc);
         infeasible = bflags & 1;
         if (!infeasible) {
-            if (prepare_factor(a.d, mt, s.w.ctype, a.o, s.w.u, s.w.t, s.w.zx, s.w.zp, s.w.w, s.w.sc)) flag = 38;
+            if (prepare_factor(a.d, mt, wk.ctype, a.o, wk.u, wk.t, wk.zx, wk.zp, wk.w, wk.sc)) flag = 38;
             else {
                 if (threadIdx.x == 0) mats_dense_ops_post(a.d, mt);
-                for (int i = LCQ_TID; i < a.d.m; i += LCQ_NT) s.w.ctype[i] = mt.ctype[i];
+                for (int i = LCQ_TID; i < a.d.m; i += LCQ_NT) wk.ctype[i] = mt.ctype[i];
                 __syncthreads();
             }
         }
@@ -210,10 +221,10 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
     }
     if (flag == 0) {
         for (int j = LCQ_TID; j < a.d.n; j += LCQ_NT) {
-            a.xout[j] = mt.D[j] * s.w.x[j];
-            a.yout[j] = a.d.has_box ? s.w.ys[a.d.mA + j] : 0.0;
+            a.xout[j] = mt.D[j] * wk.x[j];
+            a.yout[j] = a.d.has_box ? wk.ys[a.d.mA + j] : 0.0;
         }
-        for (int i = LCQ_TID; i < a.d.mA; i += LCQ_NT) a.yout[a.d.n + i] = s.w.ys[i];
+        for (int i = LCQ_TID; i < a.d.mA; i += LCQ_NT) a.yout[a.d.n + i] = wk.ys[i];
     }
     __syncthreads();
     for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
@@ -566,6 +577,7 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     CK(cudaFuncSetAttribute(lcqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_solve_kernel, kThreads, smem), LCQP_CUDA_LAUNCH_FAILED);
+    if (const char* t = getenv("LCQP_CUDA_CTAS_PER_SM")) { const int v = atoi(t); if (v >= 1 && v < per_sm) per_sm = v; }  // tuning aid
     if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
     int grid = per_sm * h->num_sms;
     if (grid > h->batch) grid = h->batch;
@@ -582,7 +594,9 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     }
     a.workspace = h->workspace;
 
-    lcqp_solve_kernel<<<grid, kThreads, smem, stream>>>(a);
+    int threads = kThreads;
+    if (const char* t = getenv("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v == 64 || v == 128 || v == 256) threads = v; }  // tuning aid
+    lcqp_solve_kernel<<<grid, threads, smem, stream>>>(a);
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);

@@ -51,6 +51,7 @@
 #define LCQ_NWARP 1
 #define LCQ_LANES 1
 #define LCQ_SYNC() ((void)0)
+#define LCQ_LOOP
 #else
 #define LCQ_DEV __device__ __forceinline__
 #define LCQ_DEVN __device__ __noinline__
@@ -62,6 +63,9 @@
 #define LCQ_NWARP ((int)(blockDim.x >> 5))
 #define LCQ_LANES 32
 #define LCQ_SYNC() __syncthreads()
+// The solver is bound by instruction fetch, not by issue slots: its hot path must stay inside the 32 KB
+// L1.5 instruction cache, so no loop is unrolled.
+#define LCQ_LOOP _Pragma("unroll 1")
 #endif
 
 #include "../../include/lcqp_cuda.h"
@@ -234,7 +238,7 @@ LCQ_DEV double block_sum(double v, Scalars* sc)
     if (LCQ_LANE == 0) sc->red[LCQ_WARP] = v;
     LCQ_SYNC();
     double s = 0;
-    for (int k = 0; k < LCQ_NWARP; k++) s += sc->red[k];
+    LCQ_LOOP for (int k = 0; k < LCQ_NWARP; k++) s += sc->red[k];
     return s;
 }
 
@@ -245,7 +249,7 @@ LCQ_DEV double block_max(double v, Scalars* sc)
     if (LCQ_LANE == 0) sc->red[LCQ_WARP] = v;
     LCQ_SYNC();
     double s = sc->red[0];
-    for (int k = 1; k < LCQ_NWARP; k++) s = fmax(s, sc->red[k]);
+    LCQ_LOOP for (int k = 1; k < LCQ_NWARP; k++) s = fmax(s, sc->red[k]);
     return s;
 }
 
@@ -258,7 +262,7 @@ LCQ_DEV void block_sum2(double& a, double& b, Scalars* sc)
     if (LCQ_LANE == 0) { sc->red[LCQ_WARP] = a; sc->red[32 + LCQ_WARP] = b; }
     LCQ_SYNC();
     double s = 0, t = 0;
-    for (int k = 0; k < LCQ_NWARP; k++) { s += sc->red[k]; t += sc->red[32 + k]; }
+    LCQ_LOOP for (int k = 0; k < LCQ_NWARP; k++) { s += sc->red[k]; t += sc->red[32 + k]; }
     a = s; b = t;
 }
 
@@ -288,7 +292,7 @@ LCQ_DEV int block_argmax(double v, int i, double* vout, Scalars* sc)
     LCQ_SYNC();
     double bv = sc->red[0];
     int bi = sc->ired[0];
-    for (int k = 1; k < LCQ_NWARP; k++) {
+    LCQ_LOOP for (int k = 1; k < LCQ_NWARP; k++) {
         double ov = sc->red[k];
         int oi = sc->ired[k];
         if (oi >= 0 && (bi < 0 || ov > bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
@@ -309,7 +313,7 @@ LCQ_DEV double fast_max(double v, Scalars* sc, int& ph)
     if (LCQ_LANE == 0) buf[LCQ_WARP] = v;
     LCQ_SYNC();
     double r = buf[0];
-    for (int k = 1; k < LCQ_NWARP; k++) r = fmax(r, buf[k]);
+    LCQ_LOOP for (int k = 1; k < LCQ_NWARP; k++) r = fmax(r, buf[k]);
     return r;
 }
 
@@ -323,7 +327,7 @@ LCQ_DEV void fast_sum2(double& a, double& b, Scalars* sc, int& ph)
     if (LCQ_LANE == 0) { b0[LCQ_WARP] = a; b1[LCQ_WARP] = b; }
     LCQ_SYNC();
     double x = 0, y = 0;
-    for (int k = 0; k < LCQ_NWARP; k++) { x += b0[k]; y += b1[k]; }
+    LCQ_LOOP for (int k = 0; k < LCQ_NWARP; k++) { x += b0[k]; y += b1[k]; }
     a = x; b = y;
 }
 
@@ -355,7 +359,7 @@ LCQ_DEV int fast_argmin_lex(double a, double wgt, int i, double* aout, Scalars* 
     LCQ_SYNC();
     double ra = ba[0], rw = bw[0];
     int ri = bi[0];
-    for (int k = 1; k < LCQ_NWARP; k++)
+    LCQ_LOOP for (int k = 1; k < LCQ_NWARP; k++)
         if (lex_better(ra, rw, ri, ba[k], bw[k], bi[k])) { ra = ba[k]; rw = bw[k]; ri = bi[k]; }
     *aout = ra;
     return ri;
@@ -369,31 +373,31 @@ LCQ_DEVN void op_mv(const Op& op, const double* v, const double* init, double sc
 {
 #define LCQ_INIT(r) (init ? init[iidx ? iidx[r] : (r)] : 0.0)
     if (op.rp) {
-        for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
+        LCQ_LOOP for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
             const int k0 = op.rp[r], k1 = op.rp[r + 1];
             if (k1 - k0 > kLongRow && LCQ_LANES > 1) continue;
             double s = 0;
-            for (int k = k0; k < k1; k++) s += op.va[k] * v[op.ci[k]];
+            LCQ_LOOP for (int k = k0; k < k1; k++) s += op.va[k] * v[op.ci[k]];
             out[r] = LCQ_INIT(r) + scale * s;
         }
         if (LCQ_LANES > 1)
-            for (int a = LCQ_WARP; a < op.nlong; a += LCQ_NWARP) {
+            LCQ_LOOP for (int a = LCQ_WARP; a < op.nlong; a += LCQ_NWARP) {
                 const int r = op.lrows[a];
                 double s = 0;
-                for (int k = op.rp[r] + LCQ_LANE; k < op.rp[r + 1]; k += LCQ_LANES) s += op.va[k] * v[op.ci[k]];
+                LCQ_LOOP for (int k = op.rp[r] + LCQ_LANE; k < op.rp[r + 1]; k += LCQ_LANES) s += op.va[k] * v[op.ci[k]];
                 s = warp_sum(s);
                 if (LCQ_LANE == 0) out[r] = LCQ_INIT(r) + scale * s;
             }
     } else if (!op.trans) {
         const int rows = op.rows, cols = op.cols, ld = op.ld;
-        for (int r0 = LCQ_WARP; r0 < rows; r0 += 4 * LCQ_NWARP) {
+        LCQ_LOOP for (int r0 = LCQ_WARP; r0 < rows; r0 += 4 * LCQ_NWARP) {
             const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
             const double* a0 = op.dense + (size_t)r0 * ld;
             const double* a1 = op.dense + (size_t)(r1 < rows ? r1 : r0) * ld;
             const double* a2 = op.dense + (size_t)(r2 < rows ? r2 : r0) * ld;
             const double* a3 = op.dense + (size_t)(r3 < rows ? r3 : r0) * ld;
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) {
+            LCQ_LOOP for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) {
                 const double vc = v[c];
                 const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
                 s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
@@ -407,9 +411,9 @@ LCQ_DEVN void op_mv(const Op& op, const double* v, const double* init, double sc
             }
         }
     } else {
-        for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
+        LCQ_LOOP for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
             double s = 0;
-            for (int c = 0; c < op.cols; c++) s += op.dense[(size_t)c * op.ld + r] * v[c];
+            LCQ_LOOP for (int c = 0; c < op.cols; c++) s += op.dense[(size_t)c * op.ld + r] * v[c];
             out[r] = LCQ_INIT(r) + scale * s;
         }
     }
@@ -420,18 +424,18 @@ LCQ_DEVN void op_mv(const Op& op, const double* v, const double* init, double sc
 LCQ_DEVN void op_mv_rows(const Op& op, const int* idx, int na, const double* v, const double* sub, double* out)
 {
     if (op.rp) {
-        for (int a = LCQ_TID; a < na; a += LCQ_NT) {
+        LCQ_LOOP for (int a = LCQ_TID; a < na; a += LCQ_NT) {
             const int r = idx[a];
             double s = 0;
-            for (int k = op.rp[r]; k < op.rp[r + 1]; k++) s += op.va[k] * v[op.ci[k]];
+            LCQ_LOOP for (int k = op.rp[r]; k < op.rp[r + 1]; k++) s += op.va[k] * v[op.ci[k]];
             out[a] = s - (sub ? sub[r] : 0.0);
         }
     } else {
-        for (int a = LCQ_WARP; a < na; a += LCQ_NWARP) {
+        LCQ_LOOP for (int a = LCQ_WARP; a < na; a += LCQ_NWARP) {
             const int r = idx[a];
             const double* row = op.dense + (size_t)r * op.ld;
             double s = 0;
-            for (int c = LCQ_LANE; c < op.cols; c += LCQ_LANES) s += row[c] * v[c];
+            LCQ_LOOP for (int c = LCQ_LANE; c < op.cols; c += LCQ_LANES) s += row[c] * v[c];
             s = warp_sum(s);
             if (LCQ_LANE == 0) out[a] = s - (sub ? sub[r] : 0.0);
         }
@@ -442,14 +446,14 @@ LCQ_DEVN void op_mv_rows(const Op& op, const int* idx, int na, const double* v, 
 // usually sits in L2: the loads of the four rows overlap)
 LCQ_DEV void mv_dense(const double* __restrict__ M, int rows, int cols, int ld, const double* v, double* out)
 {
-    for (int r0 = LCQ_WARP; r0 < rows; r0 += 4 * LCQ_NWARP) {
+    LCQ_LOOP for (int r0 = LCQ_WARP; r0 < rows; r0 += 4 * LCQ_NWARP) {
         const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
         const double* a0 = M + (size_t)r0 * ld;
         const double* a1 = M + (size_t)(r1 < rows ? r1 : r0) * ld;
         const double* a2 = M + (size_t)(r2 < rows ? r2 : r0) * ld;
         const double* a3 = M + (size_t)(r3 < rows ? r3 : r0) * ld;
         double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) {
+        LCQ_LOOP for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) {
             const double vc = v[c];
             const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
             s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
@@ -467,20 +471,59 @@ LCQ_DEV void mv_dense(const double* __restrict__ M, int rows, int cols, int ld, 
 // ---- packed symmetric matrix (lower triangle, row-major): S(a,b), b <= a, at a(a+1)/2 + b ----------------
 LCQ_DEV size_t pidx(int a, int b) { return a >= b ? (size_t)a * (a + 1) / 2 + b : (size_t)b * (b + 1) / 2 + a; }
 
-// f(a, sum_b S(a,b) v[b]) for every row a < nw.  Two threads per row, each over half of the columns: below the
-// diagonal the row is contiguous, above it the column is walked with an incrementally updated offset.
-template <class F>
-LCQ_DEV void sym_mv_f(const double* S, int nw, const double* v, F f)
+// y = sgn * S v for a symmetric matrix S of order nw, scattered to up to three places:
+//     out[a] = y_a;   o2[sidx[a]] = y_a;   o3[sidx[a]] = y_a          (null pointers are skipped)
+// ld == 0: S is a packed lower triangle in shared memory.  Two threads per row, each over half of the
+//          columns: below the diagonal the row is contiguous, above it the column is walked with an
+//          incrementally updated offset.
+// ld  > 0: S is in full storage with leading dimension ld in global memory (L2): one warp per row with
+//          coalesced row reads, four rows of a warp in flight.
+// One non-inlined copy serves every call site (the solver is instruction-fetch bound).
+LCQ_DEVN void sym_apply(const double* __restrict__ S, int ld, int nw, const double* v, double sgn,
+                        double* out, const int* sidx, double* o2, double* o3)
 {
+#define LCQ_EMIT(a, val)                                  \
+    do {                                                  \
+        const double y_ = sgn * (val);                    \
+        if (out) out[a] = y_;                             \
+        if (sidx) {                                       \
+            const int i_ = sidx[a];                       \
+            if (o2) o2[i_] = y_;                          \
+            if (o3) o3[i_] = y_;                          \
+        }                                                 \
+    } while (0)
+    if (ld) {
+        LCQ_LOOP for (int r0 = LCQ_WARP; r0 < nw; r0 += 4 * LCQ_NWARP) {
+            const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
+            const double* a0 = S + (size_t)r0 * ld;
+            const double* a1 = S + (size_t)(r1 < nw ? r1 : r0) * ld;
+            const double* a2 = S + (size_t)(r2 < nw ? r2 : r0) * ld;
+            const double* a3 = S + (size_t)(r3 < nw ? r3 : r0) * ld;
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            LCQ_LOOP for (int c = LCQ_LANE; c < nw; c += LCQ_LANES) {
+                const double vc = v[c];
+                const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
+                s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
+            }
+            s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+            if (LCQ_LANE == 0) {
+                LCQ_EMIT(r0, s0);
+                if (r1 < nw) LCQ_EMIT(r1, s1);
+                if (r2 < nw) LCQ_EMIT(r2, s2);
+                if (r3 < nw) LCQ_EMIT(r3, s3);
+            }
+        }
+        return;
+    }
 #ifdef LCQP_HOST_EMU
     for (int a = 0; a < nw; a++) {
         double s = 0;
         for (int b = 0; b < nw; b++) s += S[pidx(a, b)] * v[b];
-        f(a, s);
+        LCQ_EMIT(a, s);
     }
 #else
     const int half = (nw + 1) >> 1;
-    for (int base = 0; base < 2 * nw; base += LCQ_NT) {
+    LCQ_LOOP for (int base = 0; base < 2 * nw; base += LCQ_NT) {
         const int t = base + LCQ_TID;
         const int a = t >> 1, h = t & 1;
         double s = 0;
@@ -488,55 +531,21 @@ LCQ_DEV void sym_mv_f(const double* S, int nw, const double* v, F f)
             const int b0 = h ? half : 0, b1 = h ? nw : half;
             const double* row = S + (size_t)a * (a + 1) / 2;
             const int be = b1 < a + 1 ? b1 : a + 1;
-            for (int b = b0; b < be; b++) s += row[b] * v[b];
-            int b = b0 > a + 1 ? b0 : a + 1;
+            double s2 = 0;
+            int b = b0;
+            LCQ_LOOP for (; b + 1 < be; b += 2) { s += row[b] * v[b]; s2 += row[b + 1] * v[b + 1]; }
+            if (b < be) s += row[b] * v[b];
+            b = b0 > a + 1 ? b0 : a + 1;
             const double* q = S + (size_t)b * (b + 1) / 2 + a;
-            for (; b < b1; b++) { s += *q * v[b]; q += b + 1; }
+            LCQ_LOOP for (; b + 1 < b1; b += 2) { s += q[0] * v[b]; s2 += q[b + 1] * v[b + 1]; q += 2 * b + 3; }
+            if (b < b1) s += q[0] * v[b];
+            s += s2;
         }
         s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (a < nw && h == 0) f(a, s);
+        if (a < nw && h == 0) LCQ_EMIT(a, s);
     }
 #endif
-}
-
-LCQ_DEV void sym_mv(const double* S, int nw, const double* v, double* out)
-{
-    sym_mv_f(S, nw, v, [&](int a, double s) { out[a] = s; });
-}
-
-// The same for a symmetric matrix in FULL storage with leading dimension ld (it lives in global memory / L2):
-// one warp per row with coalesced row reads, four rows of a warp in flight; f runs on lane 0.
-template <class F>
-LCQ_DEV void full_mv_f(const double* __restrict__ M, int nw, int ld, const double* v, F f)
-{
-    for (int r0 = LCQ_WARP; r0 < nw; r0 += 4 * LCQ_NWARP) {
-        const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
-        const double* a0 = M + (size_t)r0 * ld;
-        const double* a1 = M + (size_t)(r1 < nw ? r1 : r0) * ld;
-        const double* a2 = M + (size_t)(r2 < nw ? r2 : r0) * ld;
-        const double* a3 = M + (size_t)(r3 < nw ? r3 : r0) * ld;
-        double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-        for (int c = LCQ_LANE; c < nw; c += LCQ_LANES) {
-            const double vc = v[c];
-            const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
-            s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
-        }
-        s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-        if (LCQ_LANE == 0) {
-            f(r0, s0);
-            if (r1 < nw) f(r1, s1);
-            if (r2 < nw) f(r2, s2);
-            if (r3 < nw) f(r3, s3);
-        }
-    }
-}
-
-// f(a, (Tinv v)[a]) for the working-set inverse in either storage
-template <class F>
-LCQ_DEV void tinv_mv_f(const Work& w, int nw, const double* v, F f)
-{
-    if (w.tld) full_mv_f(w.Tinv, nw, w.tld, v, f);
-    else sym_mv_f(w.Tinv, nw, v, f);
+#undef LCQ_EMIT
 }
 
 LCQ_DEV double limit_scaling(double v)
@@ -551,23 +560,23 @@ LCQ_DEV double limit_scaling(double v)
 // the pivot column is zero are left alone, so a block-diagonal matrix keeps its exact zeros.
 LCQ_DEVN int spd_invert_inplace(double* M, int n, double* colbuf, double* rowbuf)
 {
-    for (int k = 0; k < n; k++) {
+    LCQ_LOOP for (int k = 0; k < n; k++) {
         LCQ_SYNC();
         const double p = M[(size_t)k * n + k];
         if (!(p > 0.0)) return 1;  // uniform: every thread reads the same value
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) {
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) {
             colbuf[j] = M[(size_t)j * n + k];
             rowbuf[j] = (j == k ? 1.0 : M[(size_t)k * n + j]) / p;
         }
         LCQ_SYNC();
-        for (int i = LCQ_WARP; i < n; i += LCQ_NWARP) {
+        LCQ_LOOP for (int i = LCQ_WARP; i < n; i += LCQ_NWARP) {
             double* row = M + (size_t)i * n;
             if (i == k) {
-                for (int j = LCQ_LANE; j < n; j += LCQ_LANES) row[j] = rowbuf[j];
+                LCQ_LOOP for (int j = LCQ_LANE; j < n; j += LCQ_LANES) row[j] = rowbuf[j];
             } else {
                 const double ci = colbuf[i];
                 if (ci == 0.0) continue;
-                for (int j = LCQ_LANE; j < n; j += LCQ_LANES) row[j] = (j == k ? 0.0 : row[j]) - ci * rowbuf[j];
+                LCQ_LOOP for (int j = LCQ_LANE; j < n; j += LCQ_LANES) row[j] = (j == k ? 0.0 : row[j]) - ci * rowbuf[j];
             }
         }
     }
@@ -592,16 +601,16 @@ LCQ_DEVN Op build_op(const double* src, int rows, int cols, int ld, int trans, C
     const int rpoff = sc->ired[0];
     if (rpoff < 0) return op;
     int* rp = pool.ibuf + rpoff;
-    for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
+    LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
         int c = 0;
-        for (int j = 0; j < cols; j++) c += ((trans ? src[(size_t)j * ld + r] : src[(size_t)r * ld + j]) != 0.0);
+        LCQ_LOOP for (int j = 0; j < cols; j++) c += ((trans ? src[(size_t)j * ld + r] : src[(size_t)r * ld + j]) != 0.0);
         rp[r + 1] = c;
     }
     LCQ_SYNC();
     if (LCQ_TID == 0) {
         int tot = 0, nl = 0;
         rp[0] = 0;
-        for (int r = 0; r < rows; r++) { const int c = rp[r + 1]; nl += (c > kLongRow); tot += c; rp[r + 1] = tot; }
+        LCQ_LOOP for (int r = 0; r < rows; r++) { const int c = rp[r + 1]; nl += (c > kLongRow); tot += c; rp[r + 1] = tot; }
         const int io = pool.used[0], dof = pool.used[1];
         const int ci_ints = (tot + 1) / 2;   // 16-bit column indices
         const bool sparse = cols < 65536 && (long long)tot * 4 <= (long long)rows * cols && io + ci_ints + nl <= pool.icap && dof + tot <= pool.dcap;
@@ -611,7 +620,7 @@ LCQ_DEVN Op build_op(const double* src, int rows, int cols, int ld, int trans, C
             sc->ired[1] = io; sc->ired[2] = dof; sc->ired[3] = nl;
             int* lr = pool.ibuf + io + ci_ints;
             int k = 0;
-            for (int r = 0; r < rows; r++) if (rp[r + 1] - rp[r] > kLongRow) lr[k++] = r;
+            LCQ_LOOP for (int r = 0; r < rows; r++) if (rp[r + 1] - rp[r] > kLongRow) lr[k++] = r;
         } else {
             sc->ired[1] = -1;
             pool.used[0] = rpoff;  // give the row pointers back
@@ -622,9 +631,9 @@ LCQ_DEVN Op build_op(const double* src, int rows, int cols, int ld, int trans, C
     if (io < 0) { LCQ_SYNC(); return op; }
     unsigned short* ci = reinterpret_cast<unsigned short*>(pool.ibuf + io);
     double* va = pool.dbuf + dof;
-    for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
+    LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
         int k = rp[r];
-        for (int j = 0; j < cols; j++) {
+        LCQ_LOOP for (int j = 0; j < cols; j++) {
             const double v = trans ? src[(size_t)j * ld + r] : src[(size_t)r * ld + j];
             if (v != 0.0) { ci[k] = (unsigned short)j; va[k] = v; k++; }
         }
@@ -642,8 +651,8 @@ LCQ_DEVN void prepare_scale(const Dims& d, const Inst& in, Mats& mt, double* v1,
 {
     const int n = d.n, m = d.m, mA = d.mA, nC = d.nC, nComp = d.nComp;
     // P = Q, A = [A; L; R; I]
-    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) mt.P[e] = in.Q[e];
-    for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
+    LCQ_LOOP for (int e = LCQ_TID; e < n * n; e += LCQ_NT) mt.P[e] = in.Q[e];
+    LCQ_LOOP for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
         const int i = e / n, j = e - i * n;
         double v;
         if (i < nC) v = in.A[e];
@@ -652,35 +661,35 @@ LCQ_DEVN void prepare_scale(const Dims& d, const Inst& in, Mats& mt, double* v1,
         else v = (i - mA == j) ? 1.0 : 0.0;
         mt.A[e] = v;
     }
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) mt.D[j] = 1.0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) mt.E[i] = 1.0;
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) mt.D[j] = 1.0;
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) mt.E[i] = 1.0;
     double* Dt = v1;
     double* Et = e1;
-    for (int it = 0; it < kScalingIters; it++) {
+    LCQ_LOOP for (int it = 0; it < kScalingIters; it++) {
         LCQ_SYNC();
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) {
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) {
             double v = 0;
-            for (int i = 0; i < n; i++) v = fmax(v, fabs(mt.P[(size_t)i * n + j]));
-            for (int i = 0; i < m; i++) v = fmax(v, fabs(mt.A[(size_t)i * n + j]));
+            LCQ_LOOP for (int i = 0; i < n; i++) v = fmax(v, fabs(mt.P[(size_t)i * n + j]));
+            LCQ_LOOP for (int i = 0; i < m; i++) v = fmax(v, fabs(mt.A[(size_t)i * n + j]));
             Dt[j] = 1.0 / sqrt(limit_scaling(v));
         }
-        for (int i = LCQ_WARP; i < m; i += LCQ_NWARP) {
+        LCQ_LOOP for (int i = LCQ_WARP; i < m; i += LCQ_NWARP) {
             double v = 0;
-            for (int j = LCQ_LANE; j < n; j += LCQ_LANES) v = fmax(v, fabs(mt.A[(size_t)i * n + j]));
+            LCQ_LOOP for (int j = LCQ_LANE; j < n; j += LCQ_LANES) v = fmax(v, fabs(mt.A[(size_t)i * n + j]));
             v = warp_max(v);
             if (LCQ_LANE == 0) Et[i] = 1.0 / sqrt(limit_scaling(v));
         }
         LCQ_SYNC();
-        for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
+        LCQ_LOOP for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
             const int i = e / n, j = e - i * n;
             mt.P[e] *= Dt[i] * Dt[j];
         }
-        for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
+        LCQ_LOOP for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
             const int i = e / n, j = e - i * n;
             mt.A[e] *= Et[i] * Dt[j];
         }
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) mt.D[j] *= Dt[j];
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) mt.E[i] *= Et[i];
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) mt.D[j] *= Dt[j];
+        LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) mt.E[i] *= Et[i];
     }
     LCQ_SYNC();
 }
@@ -691,7 +700,7 @@ LCQ_DEVN void prepare_scale(const Dims& d, const Inst& in, Mats& mt, double* v1,
 LCQ_DEVN int set_bounds(const Dims& d, const Inst& in, const double* E, double* l, double* u, signed char* ctype, Scalars* sc)
 {
     int bad = 0;
-    for (int i = LCQ_TID; i < d.m; i += LCQ_NT) {
+    LCQ_LOOP for (int i = LCQ_TID; i < d.m; i += LCQ_NT) {
         double lo, up;
         if (i < d.nC) { lo = in.lbA ? in.lbA[i] : -INFINITY; up = in.ubA ? in.ubA[i] : INFINITY; }
         else if (i < d.nC + d.nComp) {
@@ -731,15 +740,15 @@ LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, c
     const int n = d.n, m = d.m;
     const double delta = o.qp_delta;
     // Hinv
-    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
+    LCQ_LOOP for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
         const int i = e / n, j = e - i * n;
         mt.Hinv[e] = mt.P[e] + (i == j ? delta : 0.0);
     }
     if (spd_invert_inplace(mt.Hinv, n, v1, v2)) return 1;
     // Minv
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) { e1[i] = rho_of(ctype[i], o.qp_rho); mt.ctype[i] = ctype[i]; }
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) { e1[i] = rho_of(ctype[i], o.qp_rho); mt.ctype[i] = ctype[i]; }
     LCQ_SYNC();
-    for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
+    LCQ_LOOP for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
         const int i = e / n, j = e - i * n;
         mt.Minv[e] = mt.P[e] + (i == j ? o.qp_sigma : 0.0);
     }
@@ -748,20 +757,20 @@ LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, c
         // A' R A accumulated row by row of A (rows are short); one thread per row pair product would race, so
         // rows are processed one after the other and the (a, b) pairs of a row in parallel
         const Op& oa = mt.oA;
-        for (int r = 0; r < m; r++) {
+        LCQ_LOOP for (int r = 0; r < m; r++) {
             const int k0 = oa.rp[r], len = oa.rp[r + 1] - k0;
-            for (int e = LCQ_TID; e < len * len; e += LCQ_NT) {
+            LCQ_LOOP for (int e = LCQ_TID; e < len * len; e += LCQ_NT) {
                 const int a = e / len, b = e - a * len;
                 mt.Minv[(size_t)oa.ci[k0 + a] * n + oa.ci[k0 + b]] += e1[r] * oa.va[k0 + a] * oa.va[k0 + b];
             }
             LCQ_SYNC();
         }
     } else {
-        for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
+        LCQ_LOOP for (int e = LCQ_TID; e < n * n; e += LCQ_NT) {
             const int i = e / n, j = e - i * n;
             if (j > i) continue;
             double s = 0;
-            for (int r = 0; r < m; r++) s += e1[r] * mt.A[(size_t)r * n + i] * mt.A[(size_t)r * n + j];
+            LCQ_LOOP for (int r = 0; r < m; r++) s += e1[r] * mt.A[(size_t)r * n + i] * mt.A[(size_t)r * n + j];
             mt.Minv[e] += s;
             if (j != i) mt.Minv[(size_t)j * n + i] += s;
         }
@@ -769,36 +778,36 @@ LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, c
     if (spd_invert_inplace(mt.Minv, n, v1, v2)) return 1;
     // AH = A Hinv, G = AH A' (into T); through the CSR rows of A when they exist (mt.oA is set by the caller)
     const Op& oA = mt.oA;
-    for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
+    LCQ_LOOP for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
         const int i = e / n, j = e - i * n;
         double s = 0;
         if (oA.rp) {
-            for (int k = oA.rp[i]; k < oA.rp[i + 1]; k++) s += oA.va[k] * mt.Hinv[(size_t)oA.ci[k] * n + j];
+            LCQ_LOOP for (int k = oA.rp[i]; k < oA.rp[i + 1]; k++) s += oA.va[k] * mt.Hinv[(size_t)oA.ci[k] * n + j];
         } else {
             const double* ar = mt.A + (size_t)i * n;
-            for (int k = 0; k < n; k++) s += ar[k] * mt.Hinv[(size_t)k * n + j];
+            LCQ_LOOP for (int k = 0; k < n; k++) s += ar[k] * mt.Hinv[(size_t)k * n + j];
         }
         mt.AH[e] = s;
     }
     LCQ_SYNC();
     if (oA.rp) {
-        for (int e = LCQ_TID; e < m * m; e += LCQ_NT) {
+        LCQ_LOOP for (int e = LCQ_TID; e < m * m; e += LCQ_NT) {
             const int i = e / m, r = e - i * m;
             if (r > i) continue;
             const double* ah = mt.AH + (size_t)i * n;
             double s = 0;
-            for (int k = oA.rp[r]; k < oA.rp[r + 1]; k++) s += ah[oA.ci[k]] * oA.va[k];
+            LCQ_LOOP for (int k = oA.rp[r]; k < oA.rp[r + 1]; k++) s += ah[oA.ci[k]] * oA.va[k];
             mt.T[(size_t)i * m + r] = s;
             mt.T[(size_t)r * m + i] = s;
         }
     } else {
-        for (int e = LCQ_WARP; e < m * m; e += LCQ_NWARP) {
+        LCQ_LOOP for (int e = LCQ_WARP; e < m * m; e += LCQ_NWARP) {
             const int i = e / m, r = e - i * m;
             if (r > i) continue;
             const double* ah = mt.AH + (size_t)i * n;
             const double* ar = mt.A + (size_t)r * n;
             double s = 0;
-            for (int k = LCQ_LANE; k < n; k += LCQ_LANES) s += ah[k] * ar[k];
+            LCQ_LOOP for (int k = LCQ_LANE; k < n; k += LCQ_LANES) s += ah[k] * ar[k];
             s = warp_sum(s);
             if (LCQ_LANE == 0) { mt.T[(size_t)i * m + r] = s; mt.T[(size_t)r * m + i] = s; }
         }
@@ -812,15 +821,15 @@ LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, c
     double* Si = mt.SEinv;
     double* sv = e1;   // G[j, E]
     double* uu = e2;   // SEinv sv
-    for (int j = 0; j < m; j++) {
+    LCQ_LOOP for (int j = 0; j < m; j++) {
         if (ctype[j] != 1) continue;
         const double* Gj = mt.T + (size_t)j * m;
-        for (int a = LCQ_TID; a < mE; a += LCQ_NT) sv[a] = Gj[mt.eidx[a]];
+        LCQ_LOOP for (int a = LCQ_TID; a < mE; a += LCQ_NT) sv[a] = Gj[mt.eidx[a]];
         LCQ_SYNC();
         mv_dense(Si, mE, mE, mEcap, sv, uu);
         LCQ_SYNC();
         double p1 = 0, p2 = 0;
-        for (int a = LCQ_TID; a < mE; a += LCQ_NT) { p1 += sv[a] * uu[a]; p2 += uu[a] * uu[a]; }
+        LCQ_LOOP for (int a = LCQ_TID; a < mE; a += LCQ_NT) { p1 += sv[a] * uu[a]; p2 += uu[a] * uu[a]; }
         block_sum2(p1, p2, sc);
         const double kappa = Gj[j] + delta - p1;
         if (mE >= mEcap || !(kappa > 10.0 * delta * (1.0 + p2))) {
@@ -829,11 +838,11 @@ LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, c
             continue;
         }
         const double ik = 1.0 / kappa;
-        for (int e = LCQ_TID; e < mE * mE; e += LCQ_NT) {
+        LCQ_LOOP for (int e = LCQ_TID; e < mE * mE; e += LCQ_NT) {
             const int a = e / mE, b = e - a * mE;
             Si[(size_t)a * mEcap + b] += uu[a] * uu[b] * ik;
         }
-        for (int a = LCQ_TID; a < mE; a += LCQ_NT) {
+        LCQ_LOOP for (int a = LCQ_TID; a < mE; a += LCQ_NT) {
             Si[(size_t)a * mEcap + mE] = -uu[a] * ik;
             Si[(size_t)mE * mEcap + a] = -uu[a] * ik;
         }
@@ -844,27 +853,27 @@ LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, c
     // T <- G - G[:,E] SEinv G[E,:]   (only entries with both rows outside E are used afterwards)
     if (mE > 0) {
         // X = G[:,E] SEinv, row by row, kept in e3; then T[i,:] -= X[i,:] G[E,:]
-        for (int i = 0; i < m; i++) {
+        LCQ_LOOP for (int i = 0; i < m; i++) {
             if (mt.ctype[i] == 1) continue;
             double* Ti = mt.T + (size_t)i * m;
-            for (int a = LCQ_TID; a < mE; a += LCQ_NT) sv[a] = Ti[mt.eidx[a]];
+            LCQ_LOOP for (int a = LCQ_TID; a < mE; a += LCQ_NT) sv[a] = Ti[mt.eidx[a]];
             LCQ_SYNC();
             int any = 0;
-            for (int a = LCQ_TID; a < mE; a += LCQ_NT) any |= (sv[a] != 0.0);
+            LCQ_LOOP for (int a = LCQ_TID; a < mE; a += LCQ_NT) any |= (sv[a] != 0.0);
             any = block_or(any, sc);
             if (!any) continue;  // row decoupled from the equality block
             mv_dense(Si, mE, mE, mEcap, sv, e3);
             LCQ_SYNC();
-            for (int r = LCQ_TID; r < m; r += LCQ_NT) {
+            LCQ_LOOP for (int r = LCQ_TID; r < m; r += LCQ_NT) {
                 if (mt.ctype[r] == 1) continue;
                 double s = 0;
-                for (int a = 0; a < mE; a++) s += e3[a] * mt.T[(size_t)mt.eidx[a] * m + r];
+                LCQ_LOOP for (int a = 0; a < mE; a++) s += e3[a] * mt.T[(size_t)mt.eidx[a] * m + r];
                 Ti[r] -= s;
             }
             LCQ_SYNC();
         }
     }
-    for (int e = LCQ_TID; e < mE * n; e += LCQ_NT) {
+    LCQ_LOOP for (int e = LCQ_TID; e < mE * n; e += LCQ_NT) {
         const int a = e / n, j = e - a * n;
         mt.AHE[e] = mt.AH[(size_t)mt.eidx[a] * n + j];
     }
@@ -973,9 +982,9 @@ LCQ_DEVN void cache_op(Op& op, unsigned char*& cur, unsigned char* end)
     int* rp = reinterpret_cast<int*>(cur + ((size_t)nnz * sizeof(double) + 15) / 16 * 16);
     int* lr = rp + rows + 1;
     unsigned short* ci = reinterpret_cast<unsigned short*>(reinterpret_cast<unsigned char*>(rp) + (((size_t)rows + 1 + nl) * sizeof(int) + 15) / 16 * 16);
-    for (int k = LCQ_TID; k < nnz; k += LCQ_NT) { va[k] = op.va[k]; ci[k] = op.ci[k]; }
-    for (int r = LCQ_TID; r <= rows; r += LCQ_NT) rp[r] = op.rp[r];
-    for (int a = LCQ_TID; a < nl; a += LCQ_NT) lr[a] = op.lrows[a];
+    LCQ_LOOP for (int k = LCQ_TID; k < nnz; k += LCQ_NT) { va[k] = op.va[k]; ci[k] = op.ci[k]; }
+    LCQ_LOOP for (int r = LCQ_TID; r <= rows; r += LCQ_NT) rp[r] = op.rp[r];
+    LCQ_LOOP for (int a = LCQ_TID; a < nl; a += LCQ_NT) lr[a] = op.lrows[a];
     op.va = va; op.rp = rp; op.ci = ci; op.lrows = lr;
     cur += need;
 }
@@ -993,7 +1002,7 @@ LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsign
         const size_t need = ((size_t)mE * (mE + 1) / 2 * sizeof(double) + 15) / 16 * 16;
         if (cur + need <= end) {
             double* P = reinterpret_cast<double*>(cur);
-            for (int e = LCQ_TID; e < mE * mE; e += LCQ_NT) {
+            LCQ_LOOP for (int e = LCQ_TID; e < mE * mE; e += LCQ_NT) {
                 const int a = e / mE, b = e - a * mE;
                 if (b <= a) P[(size_t)a * (a + 1) / 2 + b] = mt.SEinv[(size_t)a * d.ldE + b];
             }
@@ -1033,10 +1042,13 @@ LCQ_DEV void cache_requirements(Mats& mt, const RawOps& ro)
 // ------------------------------------------------------------------------------------------------
 // QP solver state machine
 // ------------------------------------------------------------------------------------------------
+// Per-thread view of the solver state.  Everything large or read-only (dimensions, the pointers of the
+// working set, the prepared operands) is block-shared and only POINTED to from here, so that the non-inlined
+// device functions find their operands in shared memory instead of a per-thread stack frame in L2.
 struct QP {
-    Dims d;
+    const Dims* d;
     const Mats* mt;
-    Work w;
+    const Work* w;
     const lcqp_cuda_options* o;
     int nw;           // rows in the inequality working set = order of Tinv (idx[0..nw))
     int have_W;
@@ -1048,21 +1060,21 @@ struct QP {
 // One ADMM iteration (osqp auxil.c:161-225, condensed KKT solve).
 LCQ_DEVN void admm_iter(QP& s)
 {
-    const int n = s.d.n, m = s.d.m;
-    Work& w = s.w;
+    const int n = s.d->n, m = s.d->m;
+    const Work& w = *s.w;
     const Mats& mt = *s.mt;
     const double alpha = s.o->qp_alpha, sigma = s.o->qp_sigma, rho = s.o->qp_rho;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) w.w[i] = rho_of(w.ctype[i], rho) * w.z[i] - w.y[i];
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.u[j] = sigma * w.x[j] - w.q[j];
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.w[i] = rho_of(w.ctype[i], rho) * w.z[i] - w.y[i];
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.u[j] = sigma * w.x[j] - w.q[j];
     LCQ_SYNC();
     op_mv(mt.oAt, w.w, w.u, 1.0, w.t);        // rhs = sigma x - q + A'w
     LCQ_SYNC();
     op_mv(mt.oMinv, w.t, nullptr, 1.0, w.dx); // xt
     LCQ_SYNC();
     op_mv(mt.oA, w.dx, nullptr, 1.0, w.zp);   // zt = A xt
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = alpha * w.dx[j] + (1.0 - alpha) * w.x[j];
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = alpha * w.dx[j] + (1.0 - alpha) * w.x[j];
     LCQ_SYNC();
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
         const double r = rho_of(w.ctype[i], rho);
         const double v = alpha * w.zp[i] + (1.0 - alpha) * w.z[i];
         double zn = v + w.y[i] / r;
@@ -1076,8 +1088,8 @@ LCQ_DEVN void admm_iter(QP& s)
 // Active-set guess from the ADMM iterate (osqp polish.c:33-49; equality rows always active).
 LCQ_DEVN void guess_working_set(QP& s, signed char* W)
 {
-    Work& w = s.w;
-    for (int i = LCQ_TID; i < s.d.m; i += LCQ_NT) {
+    const Work& w = *s.w;
+    LCQ_LOOP for (int i = LCQ_TID; i < s.d->m; i += LCQ_NT) {
         signed char v = 0;
         const signed char t = w.ctype[i];
         if (t == 1) v = 1;
@@ -1096,37 +1108,39 @@ LCQ_DEVN void guess_working_set(QP& s, signed char* W)
 // requires); returns 1 in that case, 0 otherwise.  Scratch: dI, lI.
 LCQ_DEVN int tinv_append(QP& s, int j)
 {
-    Work& w = s.w;
-    const int nw = s.nw, m = s.d.m;
+    const Work& w = *s.w;
+    const int nw = s.nw, m = s.d->m;
     double* Si = w.Tinv;
     const double* Tj = s.mt->T + (size_t)j * m;
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.dI[a] = Tj[w.idx[a]];
+    LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.dI[a] = Tj[w.idx[a]];
+    LCQ_SYNC();
+    sym_apply(Si, w.tld, nw, w.dI, 1.0, w.lI, nullptr, nullptr, nullptr);
     LCQ_SYNC();
     double p1 = 0, p2 = 0;
-    tinv_mv_f(w, nw, w.dI, [&](int a, double v) { w.lI[a] = v; p1 += w.dI[a] * v; p2 += v * v; });
+    LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) { const double v = w.lI[a]; p1 += w.dI[a] * v; p2 += v * v; }
     fast_sum2(p1, p2, w.sc, s.ph);
     const double kappa = Tj[j] + s.o->qp_delta - p1;
     if (!(kappa > 10.0 * s.o->qp_delta * (1.0 + p2))) return 1;
     const double ik = 1.0 / kappa;
     if (w.tld) {
         const int ld = w.tld;
-        for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
+        LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
             const double ua = w.lI[a] * ik;
             double* row = Si + (size_t)a * ld;
-            for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) row[b] += ua * w.lI[b];
+            LCQ_LOOP for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) row[b] += ua * w.lI[b];
             if (LCQ_LANE == 0) row[nw] = -ua;
         }
         double* row = Si + (size_t)nw * ld;
-        for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
+        LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
         if (LCQ_TID == 0) { row[nw] = ik; w.idx[nw] = j; }
     } else {
-        for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
+        LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
             const double ua = w.lI[a] * ik;
             double* row = Si + (size_t)a * (a + 1) / 2;
-            for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] += ua * w.lI[b];
+            LCQ_LOOP for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] += ua * w.lI[b];
         }
         double* row = Si + (size_t)nw * (nw + 1) / 2;
-        for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
+        LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
         if (LCQ_TID == 0) { row[nw] = ik; w.idx[nw] = j; }
     }
     s.nw = nw + 1;
@@ -1137,29 +1151,29 @@ LCQ_DEVN int tinv_append(QP& s, int j)
 // remove position p from the working set (the last position is moved into p).  Scratch: dI, lI.
 LCQ_DEVN void tinv_remove(QP& s, int p)
 {
-    Work& w = s.w;
+    const Work& w = *s.w;
     const int nw = s.nw, last = nw - 1;
     double* Si = w.Tinv;
     const int ld = w.tld;
-    for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.dI[b] = ld ? Si[(size_t)b * ld + p] : Si[pidx(b, p)];
+    LCQ_LOOP for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.dI[b] = ld ? Si[(size_t)b * ld + p] : Si[pidx(b, p)];
     LCQ_SYNC();
     const double ic = 1.0 / w.dI[p];
-    for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
+    LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
         const double ca = w.dI[a] * ic;
         if (ld) {
             double* row = Si + (size_t)a * ld;
-            for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) row[b] -= ca * w.dI[b];
+            LCQ_LOOP for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) row[b] -= ca * w.dI[b];
         } else {
             double* row = Si + (size_t)a * (a + 1) / 2;
-            for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] -= ca * w.dI[b];
+            LCQ_LOOP for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] -= ca * w.dI[b];
         }
     }
     LCQ_SYNC();
     if (p != last) {
         // move row/column `last` into position p
-        for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.lI[b] = ld ? Si[(size_t)last * ld + b] : Si[pidx(last, b)];
+        LCQ_LOOP for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.lI[b] = ld ? Si[(size_t)last * ld + b] : Si[pidx(last, b)];
         LCQ_SYNC();
-        for (int b = LCQ_TID; b < last; b += LCQ_NT) {
+        LCQ_LOOP for (int b = LCQ_TID; b < last; b += LCQ_NT) {
             const double v = (b == p) ? w.lI[last] : w.lI[b];
             if (ld) { Si[(size_t)p * ld + b] = v; Si[(size_t)b * ld + p] = v; }
             else Si[pidx(p, b)] = v;
@@ -1174,17 +1188,17 @@ LCQ_DEVN void tinv_remove(QP& s, int p)
 // before them (or beyond the capacity) are taken out of W.  Equality rows: W follows the static block.
 LCQ_DEVN void tinv_build(QP& s, signed char* W)
 {
-    const int m = s.d.m;
+    const int m = s.d->m;
     s.nw = 0;
     s.tinv_valid = 0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT)
-        if (s.w.ctype[i] >= 1) W[i] = (s.w.ctype[i] == 1) ? 1 : 0;
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT)
+        if (s.w->ctype[i] >= 1) W[i] = (s.w->ctype[i] == 1) ? 1 : 0;
     LCQ_SYNC();
-    for (int i = 0; i < m; i++) {  // W is in shared memory: uniform branches
-        if (!W[i] || s.w.ctype[i] != 0) continue;
-        if (s.nw >= s.d.cap || tinv_append(s, i)) {
+    LCQ_LOOP for (int i = 0; i < m; i++) {  // W is in shared memory: uniform branches
+        if (!W[i] || s.w->ctype[i] != 0) continue;
+        if (s.nw >= s.d->cap || tinv_append(s, i)) {
 #ifdef LCQP_HOST_EMU
-            if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu tinv_build: row %d rejected (nw=%d cap=%d mE=%d)\n", i, s.nw, s.d.cap, s.mt->mE);
+            if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu tinv_build: row %d rejected (nw=%d cap=%d mE=%d)\n", i, s.nw, s.d->cap, s.mt->mE);
 #endif
             LCQ_SYNC();
             if (LCQ_TID == 0) W[i] = 0;
@@ -1202,45 +1216,41 @@ LCQ_DEVN void tinv_build(QP& s, signed char* W)
 // Invariants kept by the callers: yf is zero on entry (and on exit); dlam is zero outside the working set.
 LCQ_DEVN void kkt_solve(QP& s)
 {
-    const int n = s.d.n, nw = s.nw;
-    Work& w = s.w;
+    const int n = s.d->n, nw = s.nw;
+    const Work& w = *s.w;
     const Mats& mt = *s.mt;
     const int mE = mt.mE;
-    const int ldE = s.d.ldE;
-    // the equality-block solve: f(a, (SEinv cE)[a])
-    auto se_solve = [&](auto f) {
-        if (mt.SEinvP) sym_mv_f(mt.SEinvP, mE, w.cE, f);
-        else full_mv_f(mt.SEinv, mE, ldE, w.cE, f);
-    };
+    const int ldE = s.d->ldE;
+    const double* SE = mt.SEinvP ? mt.SEinvP : mt.SEinv;
+    const int seld = mt.SEinvP ? 0 : ldE;
     // K^-1 [r1; r2_E]:  u = Hinv r1, vE = SEinv (A_E u - r2_E), t = u - (Hinv A_E') vE
     op_mv(mt.oHinv, w.r1, nullptr, 1.0, (mE > 0 || nw > 0) ? w.u : w.dx);
     if (mE > 0) {
-        op_mv(mt.oAHE, w.r1, w.r2, -1.0, w.cE, mt.eidx);   // cE = r2_E - AHE r1  (sign folded below)
+        op_mv(mt.oAHE, w.r1, w.r2, -1.0, w.cE, mt.eidx);   // cE = r2_E - AHE r1: the sign is undone below
         LCQ_SYNC();
-        if (nw == 0) se_solve([&](int a, double v) { w.vE[a] = -v; w.dlam[mt.eidx[a]] = -v; });
-        else se_solve([&](int a, double v) { w.vE[a] = -v; });
+        sym_apply(SE, seld, mE, w.cE, -1.0, w.vE, nw == 0 ? mt.eidx : nullptr, w.dlam, nullptr);
         LCQ_SYNC();
         op_mv(mt.oAHtE, w.vE, w.u, -1.0, nw == 0 ? w.dx : w.t);
     } else if (nw > 0) {
         LCQ_SYNC();
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.t[j] = w.u[j];
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.t[j] = w.u[j];
     }
     LCQ_SYNC();
     if (nw == 0) return;
     // lI = Tinv (A_I t - r2_I)
     op_mv_rows(mt.oA, w.idx, nw, w.t, w.r2, w.dI);
     LCQ_SYNC();
-    tinv_mv_f(w, nw, w.dI, [&](int a, double v) { const int i = w.idx[a]; w.yf[i] = v; w.dlam[i] = v; });
+    sym_apply(w.Tinv, w.tld, nw, w.dI, 1.0, nullptr, w.idx, w.yf, w.dlam);
     LCQ_SYNC();
     // second K^-1 on [r1 - A_I' lI; r2_E]
     op_mv(mt.oAt, w.yf, w.r1, -1.0, w.t);
     LCQ_SYNC();
     op_mv(mt.oHinv, w.t, nullptr, 1.0, mE > 0 ? w.u : w.dx);
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.yf[w.idx[a]] = 0.0;
+    LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.yf[w.idx[a]] = 0.0;
     if (mE > 0) {
         op_mv(mt.oAHE, w.t, w.r2, -1.0, w.cE, mt.eidx);
         LCQ_SYNC();
-        se_solve([&](int a, double v) { w.vE[a] = -v; w.dlam[mt.eidx[a]] = -v; });
+        sym_apply(SE, seld, mE, w.cE, -1.0, w.vE, mt.eidx, w.dlam, nullptr);
         LCQ_SYNC();
         op_mv(mt.oAHtE, w.vE, w.u, -1.0, w.dx);
     }
@@ -1252,21 +1262,21 @@ LCQ_DEVN void kkt_solve(QP& s)
 // Returns the infinity norm of (r1, r2).
 LCQ_DEVN double kkt_residual(QP& s, const signed char* W, const double* x, const double* lam)
 {
-    const int n = s.d.n, m = s.d.m;
-    Work& w = s.w;
+    const int n = s.d->n, m = s.d->m;
+    const Work& w = *s.w;
     const Mats& mt = *s.mt;
     op_mv(mt.oP, x, w.q, 1.0, w.px);            // q + P x
     op_mv(mt.oAt, lam, nullptr, 1.0, w.u);      // A' lam
     op_mv(mt.oA, x, nullptr, 1.0, w.zx);
     LCQ_SYNC();
     double rn = 0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
         double r = 0.0;
         if (W[i]) r = ((W[i] == 1) ? w.l[i] : w.ub[i]) - w.zx[i];
         w.r2[i] = r;
         rn = fmax(rn, fabs(r));
     }
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) {
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) {
         const double r = -w.px[j] - w.u[j];
         w.r1[j] = r;
         rn = fmax(rn, fabs(r));
@@ -1279,17 +1289,17 @@ LCQ_DEVN double kkt_residual(QP& s, const signed char* W, const double* x, const
 // (*worst = position in idx to drop).
 LCQ_DEVN int kkt_check(QP& s, const signed char* W, const double* lam, int* worst)
 {
-    const int n = s.d.n, m = s.d.m, nw = s.nw;
-    Work& w = s.w;
+    const int n = s.d->n, m = s.d->m, nw = s.nw;
+    const Work& w = *s.w;
     const double ftol = s.o->qp_feas_tol, dtol = s.o->qp_dual_tol;
     double ln = 0, rs = 0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) ln = fmax(ln, fabs(lam[i]));
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) rs = fmax(rs, fabs(w.r1[j]));
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) ln = fmax(ln, fabs(lam[i]));
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) rs = fmax(rs, fabs(w.r1[j]));
     ln = block_max(ln, w.sc);
     rs = block_max(rs, w.sc);
     if (!(rs <= kResTol * (1.0 + ln))) return 2;
     int bad = 0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
         const double zi = w.zx[i];
         if (W[i]) {
             const double b = (W[i] == 1) ? w.l[i] : w.ub[i];
@@ -1308,7 +1318,7 @@ LCQ_DEVN int kkt_check(QP& s, const signed char* W, const double* lam, int* wors
     const double thr = dtol * (1.0 + ln);
     double bv = -1.0;
     int bi = -1;
-    for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
+    LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
         const int i = w.idx[a];
         if (w.pin[i] & 1) continue;
         const double v = (W[i] == 1) ? lam[i] : -lam[i];  // OSQP sign: lower-active needs lam <= 0
@@ -1324,17 +1334,17 @@ LCQ_DEVN int kkt_check(QP& s, const signed char* W, const double* lam, int* wors
 // (xa, lam) is the exact optimum on working set W: make it the accepted solution of this QP.
 LCQ_DEVN void accept_solution(QP& s, const signed char* W)
 {
-    const int n = s.d.n, m = s.d.m;
-    Work& w = s.w;
+    const int n = s.d->n, m = s.d->m;
+    const Work& w = *s.w;
     const Mats& mt = *s.mt;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
         w.W[i] = W[i];
         const double yi = W[i] ? w.lam[i] : 0.0;
         w.y[i] = yi;
         w.ys[i] = -(mt.E[i] * yi);   // un-scale (osqp auxil.c:524-562, c = 1), qpOASES sign
         w.z[i] = w.zx[i];
     }
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = w.xa[j];
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = w.xa[j];
     s.have_W = 1;
     LCQ_SYNC();
 }
@@ -1346,24 +1356,24 @@ LCQ_DEVN void accept_solution(QP& s, const signed char* W)
 //   ratio_test = true : the full primal active-set method; returns 0 with the solution accepted, 1 if it gave up.
 LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
 {
-    const int n = s.d.n, m = s.d.m;
-    Work& w = s.w;
+    const int n = s.d->n, m = s.d->m;
+    const Work& w = *s.w;
     const Mats& mt = *s.mt;
     const int cap_it = 20 * (n + m) + 100;
     int last_dropped = -1;
     double best = INFINITY;
     int passes = 0;      // corrections since the last working-set change
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }   // invariants of kkt_solve
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }   // invariants of kkt_solve
     LCQ_SYNC();
     bool dirty = ratio_test;   // (xa, lam) is not the from-zero solution on W
     bool clean = false;        // the from-zero recomputation is running: no ratio tests
-    for (int it = 0; it < cap_it; it++) {
+    LCQ_LOOP for (int it = 0; it < cap_it; it++) {
         const double rn = kkt_residual(s, W, w.xa, w.lam);
         bool converged = false;
         if (passes > 0 && !(rn < best)) {
             // the last correction did not help: undo it and take that point as the EQP solution
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] -= w.dx[j];
-            for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] -= w.dlam[i];
+            LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] -= w.dx[j];
+            LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] -= w.dlam[i];
             LCQ_SYNC();
             kkt_residual(s, W, w.xa, w.lam);
             converged = true;
@@ -1383,8 +1393,8 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                 // round-off that a symmetric problem would amplify, and the oracle computes it this way).
                 // Where the EQP on W has no unique solution the recomputation may land elsewhere; then the
                 // point accepted above stands.
-                for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
-                for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
+                LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
+                LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
                 LCQ_SYNC();
                 dirty = false;
                 best = INFINITY;
@@ -1397,7 +1407,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                 const int row = w.idx[worst];
                 LCQ_SYNC();
                 if (LCQ_TID == 0) { W[row] = 0; w.lam[row] = 0.0; w.dlam[row] = 0.0; }
-                for (int i = LCQ_TID; i < m; i += LCQ_NT) w.pin[i] &= 1;
+                LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.pin[i] &= 1;
                 tinv_remove(s, worst);
 #ifdef LCQP_HOST_EMU
                 if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d drop row %d (reason %d) rn=%.3e\n", it, s.nw, row, reason, rn);
@@ -1424,14 +1434,14 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             // ratio test against the inactive rows (Nocedal & Wright alg. 16.3)
             op_mv(mt.oA, w.dx, nullptr, 1.0, w.zp);
             LCQ_SYNC();
-            for (int i = LCQ_TID; i < m; i += LCQ_NT) apn = fmax(apn, fabs(w.zp[i]));
+            LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) apn = fmax(apn, fabs(w.zp[i]));
             apn = fast_max(apn, w.sc, s.ph);
             const double seps = 1e-13 * (1.0 + apn);
-            for (;;) {
+            LCQ_LOOP for (;;) {
                 // the smallest step length; among the rows attaining it the largest |s|, then the smallest row
                 double ba = 2.0, bs = 0.0;
                 int bi = -1;
-                for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+                LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
                     if (W[i] || w.ctype[i] != 0 || (w.pin[i] & 2)) continue;
                     const double sv = w.zp[i];
                     double a;
@@ -1444,7 +1454,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                 block = fast_argmin_lex(ba, bs, bi, &am, w.sc, s.ph);
                 amin = block >= 0 ? am : 1.0;
                 if (block < 0) break;
-                if (s.nw >= s.d.cap) return 1;
+                if (s.nw >= s.d->cap) return 1;
                 if (tinv_append(s, block) == 0) break;
                 // The blocking row is a combination of the active rows (e.g. a box bound duplicating an active
                 // selection row): along the working set it cannot move; the apparent motion is the leak of the
@@ -1459,8 +1469,8 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
         }
         if (block >= 0) {
             const signed char side = (w.zp[block] < 0) ? 1 : 2;
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += amin * w.dx[j];
-            for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] += amin * w.dlam[i];
+            LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += amin * w.dx[j];
+            LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] += amin * w.dlam[i];
             // a row that comes straight back after a zero-length step was dropped on multiplier noise:
             // it is weakly active; exempt it from the sign test for the rest of this QP (anti-cycling)
             if (LCQ_TID == 0) { W[block] = side; if (block == last_dropped && amin * (1.0 + apn) <= 1e-12) w.pin[block] |= 1; }
@@ -1474,8 +1484,8 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             passes = 0;
             continue;
         }
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += w.dx[j];
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] += w.dlam[i];
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += w.dx[j];
+        LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] += w.dlam[i];
         LCQ_SYNC();
         passes++;
     }
@@ -1485,37 +1495,37 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
 // H-metric projection of xin onto the rows of the working set + feasibility test of every row -> xa.
 LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin)
 {
-    const int n = s.d.n, m = s.d.m;
-    Work& w = s.w;
+    const int n = s.d->n, m = s.d->m;
+    const Work& w = *s.w;
     const Mats& mt = *s.mt;
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = xin[j];
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }   // invariants of kkt_solve
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = xin[j];
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }   // invariants of kkt_solve
     LCQ_SYNC();
-    for (int pass = 0; pass < 4; pass++) {
+    LCQ_LOOP for (int pass = 0; pass < 4; pass++) {
         op_mv(mt.oA, w.xa, nullptr, 1.0, w.zx);
         LCQ_SYNC();
         double rn = 0;
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+        LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
             double r = 0.0;
             if (W[i]) r = ((W[i] == 1) ? w.l[i] : w.ub[i]) - w.zx[i];
             w.r2[i] = r;
             rn = fmax(rn, fabs(r));
         }
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.r1[j] = 0.0;
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.r1[j] = 0.0;
         rn = block_max(rn, w.sc);
 #ifdef LCQP_HOST_EMU
         if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu project pass %d rn=%.3e nw=%d\n", pass, rn, s.nw);
 #endif
         if (rn < 1e-15) break;
         kkt_solve(s);
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += w.dx[j];
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += w.dx[j];
         LCQ_SYNC();
     }
     op_mv(mt.oA, w.xa, nullptr, 1.0, w.zx);
     LCQ_SYNC();
     const double ftol = s.o->qp_feas_tol;
     int bad = 0;
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
         const double tol = ftol * (1.0 + fabs(w.zx[i]));
         if (w.zx[i] < w.l[i] - tol || w.zx[i] > w.ub[i] + tol) bad = 1;
         if (W[i]) {
@@ -1535,20 +1545,20 @@ LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin)
 // *iterations = ADMM iterations + working-set changes.
 LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, const double* y0A, const double* y0box, int* iterations, bool infeasible)
 {
-    const int n = s.d.n, m = s.d.m, mA = s.d.mA;
-    Work& w = s.w;
+    const int n = s.d->n, m = s.d->m, mA = s.d->mA;
+    const Work& w = *s.w;
     const Mats& mt = *s.mt;
     const lcqp_cuda_options& o = *s.o;
     *iterations = 0;
     if (infeasible) return 37;
     const long long ch0 = s.n_changes;
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) w.q[j] = mt.D[j] * g[j];  // osqp.c:752-779, c = 1
-    for (int i = LCQ_TID; i < m; i += LCQ_NT) w.pin[i] = 0;
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.q[j] = mt.D[j] * g[j];  // osqp.c:752-779, c = 1
+    LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.pin[i] = 0;
     LCQ_SYNC();
     if (initial) {
         // osqp_warm_start_x/_y (osqp.c:700-745)
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = x0 ? x0[j] / mt.D[j] : 0.0;
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) {
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = x0 ? x0[j] / mt.D[j] : 0.0;
+        LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
             double yv = 0.0;
             if (i < mA) { if (y0A) yv = y0A[i]; }
             else if (y0box) yv = y0box[i - mA];
@@ -1562,16 +1572,16 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
     } else if (s.have_W && s.tinv_valid) {
         // hot start: the previous working set is tried first (EQP from zero: the usual case late in the
         // homotopy, where the active set no longer changes) ...
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.Wtry[i] = w.W[i]; w.lam[i] = 0.0; }
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
+        LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.Wtry[i] = w.W[i]; w.lam[i] = 0.0; }
         LCQ_SYNC();
         const int reason = active_set(s, w.Wtry, false, nullptr);
         if (reason == 0) { accept_solution(s, w.Wtry); return 0; }
         if (reason != 5 && reason != 6) {
             // ... else the active-set iteration continues from the previous optimum (feasible: the bounds did
             // not change) with its multipliers; a feasible EQP point with a wrong-signed multiplier is kept
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = w.x[j];
-            for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = w.y[i];
+            LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = w.x[j];
+            LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = w.y[i];
             LCQ_SYNC();
         }
         if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = (int)(s.n_changes - ch0); return 0; }
@@ -1583,21 +1593,21 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
     int have_fail = 0;
     int it = 0;
     while (it < o.qp_max_iter) {
-        for (int k = 0; k < o.qp_check_interval && it < o.qp_max_iter; k++, it++) admm_iter(s);
+        LCQ_LOOP for (int k = 0; k < o.qp_check_interval && it < o.qp_max_iter; k++, it++) admm_iter(s);
         s.n_admm += o.qp_check_interval;
         guess_working_set(s, w.Wtry);
         if (have_fail) {
             int diff = 0;
-            for (int i = LCQ_TID; i < m; i += LCQ_NT) diff |= (w.Wtry[i] != w.Wfail[i]);
+            LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) diff |= (w.Wtry[i] != w.Wfail[i]);
             if (!block_or(diff, w.sc)) continue;
         }
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) w.Wfail[i] = w.Wtry[i];
+        LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.Wfail[i] = w.Wtry[i];
         have_fail = 1;
         LCQ_SYNC();
         tinv_build(s, w.Wtry);
         // EQP on the guessed set, from zero
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
-        for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] = 0.0;
+        LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
         LCQ_SYNC();
         const int reason = active_set(s, w.Wtry, false, nullptr);
 #ifdef LCQP_HOST_EMU
@@ -1609,7 +1619,7 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
             if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = it + (int)(s.n_changes - ch0); return 0; }
             s.tinv_valid = 0;
         } else if (project_feasible(s, w.Wtry, w.x)) {
-            for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
+            LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
             LCQ_SYNC();
             if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = it + (int)(s.n_changes - ch0); return 0; }
             s.tinv_valid = 0;
@@ -1639,7 +1649,7 @@ struct LoopOut {
 };
 
 // out = Q v + rho * (L' (R v) + R' (L v)) + add   (i.e. Qk v + add); leaves Lx = L v, Rx = R v
-LCQ_DEVN void qk_apply(const RawOps& ro, double rho, const double* v, const double* add, double* out, Work& w)
+LCQ_DEVN void qk_apply(const RawOps& ro, double rho, const double* v, const double* add, double* out, const Work& w)
 {
     op_mv(ro.Q, v, add, 1.0, w.tn);
     op_mv(ro.L, v, nullptr, 1.0, w.Lx);
@@ -1654,9 +1664,9 @@ LCQ_DEVN void qk_apply(const RawOps& ro, double rho, const double* v, const doub
 LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long long instance,
                        bool infeasible, double* xout, double* yout, LoopOut& out)
 {
-    const Dims& d = s.d;
+    const Dims& d = *s.d;
     const int n = d.n, nC = d.nC, nComp = d.nComp, mA = d.mA;
-    Work& w = s.w;
+    const Work& w = *s.w;
     const Mats& mt = *s.mt;
     const lcqp_cuda_options& o = *s.o;
     const bool osqp_flavour = (o.qpSolver == 2);
@@ -1669,7 +1679,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
     out.rhoOpt = 0.0;
     const bool have_gphi = (in.lbL != nullptr) || (in.lbR != nullptr);
 
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) {
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) {
         w.xk[j] = in.x0 ? in.x0[j] : 0.0;   // LCQProblem.ipp:138-142
         w.gt[j] = in.g[j];                  // g_tilde = g (LCQProblem.cpp:966-967)
         w.pk[j] = 0.0;
@@ -1678,7 +1688,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
     LCQ_SYNC();
     if (have_gphi) {  // LCQProblem.cpp:970-996
         double part = 0;
-        for (int i = LCQ_TID; i < nComp; i += LCQ_NT) part += (in.lbL ? in.lbL[i] : 0.0) * (in.lbR ? in.lbR[i] : 0.0);
+        LCQ_LOOP for (int i = LCQ_TID; i < nComp; i += LCQ_NT) part += (in.lbL ? in.lbL[i] : 0.0) * (in.lbR ? in.lbR[i] : 0.0);
         phi_const = block_sum(part, w.sc);
         if (in.lbL) { op_mv(ro.Rt, in.lbL, w.gphi, -1.0, w.gphi); LCQ_SYNC(); }
         if (in.lbR) { op_mv(ro.Lt, in.lbR, w.gphi, -1.0, w.gphi); LCQ_SYNC(); }
@@ -1689,8 +1699,8 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
         op_mv(ro.R, w.xk, nullptr, 1.0, w.Rx);
         LCQ_SYNC();
         double part = 0;
-        for (int i = LCQ_TID; i < nComp; i += LCQ_NT) part += w.Lx[i] * w.Rx[i];
-        if (have_gphi) for (int j = LCQ_TID; j < n; j += LCQ_NT) part += w.gphi[j] * w.xk[j];
+        LCQ_LOOP for (int i = LCQ_TID; i < nComp; i += LCQ_NT) part += w.Lx[i] * w.Rx[i];
+        if (have_gphi) LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) part += w.gphi[j] * w.xk[j];
         return phi_const + block_sum(part, w.sc);
     };
     auto update_penalty = [&]() {  // :1199-1214
@@ -1698,7 +1708,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
         rho *= o.penaltyUpdateFactor;
         out.rhoOpt = rho;
         if (have_gphi) {
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) w.gt[j] = in.g[j] + rho * w.gphi[j];
+            LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.gt[j] = in.g[j] + rho * w.gphi[j];
             LCQ_SYNC();
         }
     };
@@ -1719,14 +1729,14 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
         subIter += qpIter;
         exitFlag = osqp_flavour ? (fl == 0 ? 1 : fl) : fl;
         if (fl != 0) { ret = (osqp_flavour && infeasible) ? RET_OSQP_GUESS : RET_SUBPROBLEM; return false; }
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.pk[j] = mt.D[j] * w.x[j] - w.xk[j];  // xnew = D xbar (auxil.c:524-562)
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.pk[j] = mt.D[j] * w.x[j] - w.xk[j];  // xnew = D xbar (auxil.c:524-562)
         LCQ_SYNC();
 #ifdef LCQP_HOST_EMU
         if (getenv("LCQP_EMU_DEBUG")) {
             fprintf(stderr, "emu qp i=%d rho=%g it=%d x=[", totalIter, rho, qpIter);
-            for (int j = 0; j < (n < 4 ? n : 4); j++) fprintf(stderr, "%.17g ", mt.D[j] * w.x[j]);
+            LCQ_LOOP for (int j = 0; j < (n < 4 ? n : 4); j++) fprintf(stderr, "%.17g ", mt.D[j] * w.x[j]);
             fprintf(stderr, "] ys=[");
-            for (int j = 0; j < (s.d.m < 4 ? s.d.m : 4); j++) fprintf(stderr, "%.17g ", w.ys[j]);
+            LCQ_LOOP for (int j = 0; j < (s.d->m < 4 ? s.d->m : 4); j++) fprintf(stderr, "%.17g ", w.ys[j]);
             fprintf(stderr, "] passes=%lld changes=%lld\n", s.n_pass, s.n_changes);
         }
 #endif
@@ -1736,7 +1746,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
     bool failed = false, success = false;
     // first QP (:452-467)
     if (o.solveZeroPenaltyFirst) {
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.gk[j] = in.g[j];
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.gk[j] = in.g[j];
         LCQ_SYNC();
     } else {
         linearize();
@@ -1746,7 +1756,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
 
     while (!failed) {
         // updateStep :1240-1243
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xk[j] = w.xk[j] + alphak * w.pk[j];
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xk[j] = w.xk[j] + alphak * w.pk[j];
         LCQ_SYNC();
         // updateStationarity :1246-1272 : stat = Qk xk + g_tilde - A_full' yk_A - yk_box
         qk_apply(ro, rho, w.xk, w.gt, w.stat, w);
@@ -1756,7 +1766,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
         op_mv(ro.Rt, w.ys + nC + nComp, w.stat, -1.0, w.stat);
         LCQ_SYNC();
         if (d.has_box) {
-            for (int c = LCQ_TID; c < n; c += LCQ_NT) w.stat[c] -= w.ys[mA + c];
+            LCQ_LOOP for (int c = LCQ_TID; c < n; c += LCQ_NT) w.stat[c] -= w.ys[mA + c];
             LCQ_SYNC();
         }
         totalIter++;  // :493-496
@@ -1771,9 +1781,9 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
                 else {
                     if (!(cur < o.complementarityTolerance)) {
                         fire = true;
-                        for (int i = 0; i < nd; i++) if (cur < o.etaDynamicPenalty * hist[i]) { fire = false; break; }
+                        LCQ_LOOP for (int i = 0; i < nd; i++) if (cur < o.etaDynamicPenalty * hist[i]) { fire = false; break; }
                     }
-                    for (int i = 0; i + 1 < nd; i++) hist[i] = hist[i + 1];
+                    LCQ_LOOP for (int i = 0; i + 1 < nd; i++) hist[i] = hist[i + 1];
                     hist[nd - 1] = cur;
                 }
             }
@@ -1782,7 +1792,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
         // (the reference linearises here, :508, and again at :545 before the QP; only the second one is used)
 
         double sm = 0;
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) sm = fmax(sm, fabs(w.stat[j]));
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) sm = fmax(sm, fabs(w.stat[j]));
         sm = block_max(sm, w.sc);
         if (sm < o.stationarityTolerance) {  // :511
             if (phi() < o.complementarityTolerance) {
@@ -1790,7 +1800,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
                 // weak set :1456-1482 (phi() left Lx, Rx in shared memory)
                 const double tc = o.complementarityTolerance;
                 int fl = 0;  // bit0: s fails, bit1: m fails, bit2: weakly stationary only
-                for (int i = LCQ_TID; i < nComp; i += LCQ_NT) {
+                LCQ_LOOP for (int i = LCQ_TID; i < nComp; i += LCQ_NT) {
                     if (!(w.Lx[i] <= tc && w.Rx[i] <= tc)) continue;
                     const double yl = w.ys[nC + i], yr = w.ys[nC + nComp + i];
                     const double prod = yl * yr, mn = fmin(yl, yr);
@@ -1815,7 +1825,7 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
         if (!solve_qp(false)) { failed = true; break; }  // :548
 
         if (o.perturbStep) {  // :553-555, :1353-1362
-            for (int j = LCQ_TID; j < n; j += LCQ_NT)
+            LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT)
                 w.xk[j] += perturb_draw(o.perturb_seed, instance, (unsigned)totalIter, (unsigned)j) * kEPS;
             LCQ_SYNC();
         }
@@ -1823,11 +1833,11 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
         {
             qk_apply(ro, rho, w.pk, nullptr, w.stat, w);  // Qk pk
             double p1 = 0;
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) p1 += w.stat[j] * w.pk[j];
+            LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) p1 += w.stat[j] * w.pk[j];
             const double qk = block_sum(p1, w.sc);
             qk_apply(ro, rho, w.xk, w.gt, w.stat, w);     // Qk xk + g_tilde
             p1 = 0;
-            for (int j = LCQ_TID; j < n; j += LCQ_NT) p1 += w.stat[j] * w.pk[j];
+            LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) p1 += w.stat[j] * w.pk[j];
             const double lk = block_sum(p1, w.sc);
             alphak = 1.0;
             if (qk > 0 && lk < 0) alphak = fmin(-lk / qk, 1.0);
@@ -1835,20 +1845,20 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
     }
 
     // outputs: x = xk ; y = [box duals ; yk_A] (transformDuals :1381-1409 applied on success)
-    for (int j = LCQ_TID; j < n; j += LCQ_NT) xout[j] = w.xk[j];
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) xout[j] = w.xk[j];
     const bool have_y = !infeasible && s.have_W;
     if (!osqp_flavour)
-        for (int j = LCQ_TID; j < n; j += LCQ_NT) yout[j] = (d.has_box && have_y) ? w.ys[mA + j] : 0.0;
+        LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) yout[j] = (d.has_box && have_y) ? w.ys[mA + j] : 0.0;
     if (success) {
         // Lx, Rx from the last phi() call hold L xk, R xk
-        for (int i = LCQ_TID; i < mA; i += LCQ_NT) {
+        LCQ_LOOP for (int i = LCQ_TID; i < mA; i += LCQ_NT) {
             double v = w.ys[i];
             if (i >= nC && i < nC + nComp) v -= rho * w.Rx[i - nC];
             else if (i >= nC + nComp) v -= rho * w.Lx[i - nC - nComp];
             yout[boxOff + i] = v;
         }
     } else {
-        for (int i = LCQ_TID; i < mA; i += LCQ_NT) yout[boxOff + i] = have_y ? w.ys[i] : 0.0;
+        LCQ_LOOP for (int i = LCQ_TID; i < mA; i += LCQ_NT) yout[boxOff + i] = have_y ? w.ys[i] : 0.0;
     }
     LCQ_SYNC();
     out.ret = ret;
@@ -1955,8 +1965,8 @@ LCQ_DEV void carve_mats(Mats& mt, double* base, const Dims& d)
 LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, const RawOps& ro, unsigned long long instance,
                            double* xo, double* yo, LoopOut& out)
 {
-    const Dims& d = s.d;
-    Work& w = s.w;
+    const Dims& d = *s.d;
+    const Work& w = *s.w;
     const lcqp_cuda_options& o = *s.o;
     const int nD = d.n + d.mA;
     s.mt = &mt;
@@ -1982,12 +1992,12 @@ LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, co
                 LCQ_SYNC();
             } else {
                 int diff = (mt.status != 0);
-                for (int i = LCQ_TID; i < d.m; i += LCQ_NT) diff |= ((w.ctype[i] == 1) != (mt.ctype[i] >= 1)) || ((w.ctype[i] < 0) != (mt.ctype[i] < 0));
+                LCQ_LOOP for (int i = LCQ_TID; i < d.m; i += LCQ_NT) diff |= ((w.ctype[i] == 1) != (mt.ctype[i] >= 1)) || ((w.ctype[i] < 0) != (mt.ctype[i] < 0));
                 prep_rc = block_or(diff, w.sc);
             }
             if (!prep_rc) {
                 // rows found dependent at prepare time keep their type 2
-                for (int i = LCQ_TID; i < d.m; i += LCQ_NT) w.ctype[i] = mt.ctype[i];
+                LCQ_LOOP for (int i = LCQ_TID; i < d.m; i += LCQ_NT) w.ctype[i] = mt.ctype[i];
                 LCQ_SYNC();
             }
         }
@@ -1997,8 +2007,8 @@ LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, co
         }
     }
     if (skip) {
-        for (int j = LCQ_TID; j < d.n; j += LCQ_NT) xo[j] = in.x0 ? in.x0[j] : 0.0;
-        for (int j = LCQ_TID; j < nD; j += LCQ_NT) yo[j] = 0.0;
+        LCQ_LOOP for (int j = LCQ_TID; j < d.n; j += LCQ_NT) xo[j] = in.x0 ? in.x0[j] : 0.0;
+        LCQ_LOOP for (int j = LCQ_TID; j < nD; j += LCQ_NT) yo[j] = 0.0;
     }
     LCQ_SYNC();
 }

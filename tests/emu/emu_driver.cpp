@@ -94,9 +94,11 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
     std::vector<double> gl(plan.gl_doubles + 1);
     std::vector<double> ws(mats_shared ? 1 : mats_doubles(d));
     QP s;
-    s.d = d;
+    Work wk;
+    s.d = &d;
     s.o = o;
-    carve(s.w, d, plan, smem, gl.data());
+    s.w = &wk;
+    carve(wk, d, plan, smem, gl.data());
     Mats mt;
     if (mats_shared) mt = shared_mt; else carve_mats(mt, ws.data(), d);
     RawOps ro = shared_ro;
