@@ -13,10 +13,11 @@
 
 namespace lcqp {
 
-constexpr int kThreads = 256;           // solver CTA
+constexpr int kThreads = 256;           // plugin-door CTA (one group)
+constexpr int kMaxCtaThreads = 512;     // solver CTA: groups x threads per group (128 registers per thread)
+constexpr int kMaxGroups = 8;           // groups (instances in flight) per solver CTA
 constexpr int kPrepThreads = 1024;      // batch-level preparation CTA
 constexpr size_t kSmemMax = 227 * 1024; // opt-in dynamic shared memory per CTA on sm_100
-constexpr size_t kSmemSM = 228 * 1024;  // shared memory per SM (1 KB per resident CTA is reserved)
 
 struct KernelArgs {
     Dims d;
@@ -27,7 +28,8 @@ struct KernelArgs {
     unsigned shared_mask;        // loadLCQP arguments shared by the batch
     int mats_shared;             // Q, L, R, A all shared: one preparation for the batch
     SmemPlan plan;
-    unsigned long long cache_offset;     // byte offset of the operator cache in dynamic shared memory
+    unsigned long long group_bytes;      // dynamic shared memory of one group (its instance state)
+    unsigned long long cache_offset;     // byte offset of the operator cache in dynamic shared memory (after the groups)
     unsigned long long cache_bytes;      // its size (0: operators stay in L2)
     int cache_what;                      // bit0 packed SEinv, bit1 inner-pass operators, bit2 outer-loop operators
     Mats* shared_mats;           // prepared operands of the batch (device struct, written by prepare_shared_kernel)
@@ -97,44 +99,55 @@ __global__ void __launch_bounds__(kPrepThreads) prepare_shared_kernel(const __gr
     }
 }
 
-// The solver: persistent CTAs, one LCQP instance at a time per CTA.
-__global__ void __launch_bounds__(kThreads, 2) lcqp_solve_kernel(const __grid_constant__ KernelArgs a)
+// The solver: persistent CTAs of blockDim.y groups x blockDim.x threads; every group works on one LCQP
+// instance at a time (pulled from a global counter) with its own control flow and its own named barrier.
+// The groups of a CTA share the operator cache (CSR copies of the batch-shared operators, packed SEinv).
+__global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_solve_kernel(const __grid_constant__ KernelArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ Mats mt;
-    __shared__ RawOps ro;
-    __shared__ Work wk;
+    __shared__ Mats mt_s[kMaxGroups];
+    __shared__ RawOps ro_s[kMaxGroups];
+    __shared__ Work wk_s[kMaxGroups];
     __shared__ Dims dm;
     __shared__ lcqp_cuda_options opt;
+    const int g = threadIdx.y, G = blockDim.y;
+    Mats& mt = mt_s[g];
+    RawOps& ro = ro_s[g];
+    Work& wk = wk_s[g];
     QP s;
     s.d = &dm;
     s.o = &opt;
     s.w = &wk;
-    double* ws = a.workspace + a.ws_stride * blockIdx.x;
+    double* ws = a.workspace + a.ws_stride * ((unsigned long long)blockIdx.x * G + g);
     if (threadIdx.x == 0) {
-        dm = a.d;
-        opt = a.o;
-        carve(wk, a.d, a.plan, smem, ws + a.ws_mats_doubles);
+        if (g == 0) { dm = a.d; opt = a.o; }
+        carve(wk, a.d, a.plan, smem + (size_t)g * a.group_bytes, ws + a.ws_mats_doubles);
         if (a.mats_shared) mt = *a.shared_mats;
         else carve_mats(mt, ws, a.d);
         ro = *a.shared_raw;
     }
     __syncthreads();
-    if (a.mats_shared && a.cache_bytes > 0 && mt.status == 0) cache_shared_operators(a.d, mt, ro, smem + a.cache_offset, (size_t)a.cache_bytes, a.cache_what);
+    if (a.mats_shared && a.cache_bytes > 0 && mt_s[0].status == 0) {
+        // group 0 fills the cache; the others take over its operator descriptors
+        if (g == 0) cache_shared_operators(a.d, mt, ro, smem + a.cache_offset, (size_t)a.cache_bytes, a.cache_what);
+        __syncthreads();
+        if (g > 0 && threadIdx.x == 0) { mt = mt_s[0]; ro = ro_s[0]; }
+        __syncthreads();
+    }
     const int nD = a.d.n + a.d.mA;
     const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (1u << LCQP_A);
     const bool raw_all_shared = (a.shared_mask & mat_bits) == mat_bits || (a.d.nC == 0 && (a.shared_mask & mat_bits) == (mat_bits & ~(1u << LCQP_A)));
 
     for (;;) {
-        __syncthreads();
+        LCQ_SYNC();
         if (threadIdx.x == 0) wk.sc->bidx = (int)atomicAdd(a.counter, 1u);
-        __syncthreads();
+        LCQ_SYNC();
         const int b = wk.sc->bidx;
         if (b >= a.batch) break;
         const Inst in = make_inst(a, b);
         if (!raw_all_shared) {
             if (threadIdx.x == 0) raw_dense_ops(a.d, in, ro, a.shared_mask);
-            __syncthreads();
+            LCQ_SYNC();
         }
         LoopOut out;
         double* xo = a.xout + (size_t)b * a.d.n;
@@ -531,61 +544,75 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     h->last_mE = mE;
     CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
 
-    // Shared-memory plan.  Candidates, best first:
-    //   B: the working-set inverse in L2 (full storage), the inner-pass operators cached in shared memory,
-    //      as many CTAs per SM as fit (several independent instances per SM hide each other's latencies);
-    //   A: everything of the instance in shared memory + all operators + packed SEinv, one CTA per SM;
-    //   C: no operator cache (matrices not shared by the batch, or nothing fits): instance state in shared
-    //      memory, two CTAs per SM when possible.
-    // LCQP_CUDA_PLAN=A|B|C overrides the choice (tuning aid).
+    // Shared-memory plan.  A CTA is G groups of T threads (G*T <= 512: the solver needs 128 registers per
+    // thread); each group holds the state of one instance in shared memory, the operator cache behind the
+    // groups is shared by all of them.  G is maximised first (independent instances hide each other's
+    // latencies), then, as far as shared memory goes: the working-set inverse of each group (else it lives in
+    // L2, full storage), the inner-pass operators, the packed inverse of the static equality block, the
+    // outer-loop vectors, the outer-loop operators.
+    // Tuning aids: LCQP_CUDA_THREADS (T), LCQP_CUDA_GROUPS (upper bound on G), LCQP_CUDA_TINV=l2|smem,
+    // LCQP_CUDA_CACHE (bit mask: 1 SEinv, 2 inner-pass operators, 4 outer-loop operators).
     const bool can_cache = a.mats_shared && h->host_mats->status == 0;
     const size_t c_se = can_cache ? (size_t)h->host_mats->cache_bytes_se : 0;
     const size_t c_hot = can_cache ? (size_t)h->host_mats->cache_bytes_hot : 0;
     const size_t c_raw = can_cache ? (size_t)h->host_mats->cache_bytes_raw : 0;
-    const char* force = getenv("LCQP_CUDA_PLAN");
+    int threads = 128;
+    if (const char* t = getenv("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) threads = v; }
+    int gmax = kMaxCtaThreads / threads;
+    if (gmax > kMaxGroups) gmax = kMaxGroups;
+    if (const char* t = getenv("LCQP_CUDA_GROUPS")) { const int v = atoi(t); if (v >= 1 && v < gmax) gmax = v; }
+    if (gmax > h->batch) gmax = h->batch;
+    int tinv_pref = -1;   // -1: in shared memory when it fits
+    if (const char* t = getenv("LCQP_CUDA_TINV")) tinv_pref = (t[0] == 's') ? 1 : (t[0] == 'l' ? 0 : -1);
+    int cache_allow = 7;
+    if (const char* t = getenv("LCQP_CUDA_CACHE")) cache_allow = atoi(t) & 7;
+    cudaFuncAttributes fattr;
+    CK(cudaFuncGetAttributes(&fattr, lcqp_solve_kernel), LCQP_CUDA_LAUNCH_FAILED);
+    const size_t budget = kSmemMax - fattr.sharedSizeBytes;   // static shared memory: the descriptors of the groups
     SmemPlan plan;
+    int groups = 0;
     a.cache_bytes = 0; a.cache_what = 0; a.cache_offset = 0;
-    bool chosen = false;
-    auto fits_per_sm = [&](size_t bytes) { return (int)((kSmemSM) / (bytes + 1024 + 2048)); };  // + reserved + static
-    if (can_cache && c_hot > 0 && (!force || force[0] == 'B')) {
-        SmemPlan pb = make_plan(d, 0, true);   // Tinv and the outer-loop vectors in global memory
-        const size_t base = (pb.bytes + 15) / 16 * 16;
-        if (base + c_hot <= kSmemMax && (force || fits_per_sm(base + c_hot) >= 2)) {
-            plan = pb; a.cache_offset = base; a.cache_bytes = c_hot; a.cache_what = 2; chosen = true;
-        }
+    const SmemPlan pmin = make_plan(d, 0, true);   // the instance's QP vectors only
+    for (int G = gmax; G >= 1 && !groups; G--) {
+        if ((size_t)G * ((pmin.bytes + 15) / 16 * 16) > budget) continue;
+        // per-group extras, in order of preference
+        size_t per = (pmin.bytes + 15) / 16 * 16;
+        size_t cache = 0;
+        int what = 0;
+        bool tinv_smem = false, outer_smem = false;
+        const size_t tb = tinv_doubles(d) * sizeof(double), ob = outer_doubles(d) * sizeof(double);
+        auto fits = [&](size_t per_new, size_t cache_new) { return (size_t)G * ((per_new + 15) / 16 * 16) + cache_new <= budget; };
+        if (tinv_pref != 0 && fits(per + tb, cache)) { per += tb; tinv_smem = true; }
+        if (tinv_pref == 1 && !tinv_smem) continue;
+        if ((cache_allow & 2) && c_hot && fits(per, cache + c_hot)) { cache += c_hot; what |= 2; }
+        if ((cache_allow & 1) && c_se && fits(per, cache + c_se)) { cache += c_se; what |= 1; }
+        if (fits(per + ob, cache)) { per += ob; outer_smem = true; }
+        if ((cache_allow & 4) && c_raw && (what & 2) && fits(per, cache + c_raw)) { cache += c_raw; what |= 4; }
+        plan = pmin;
+        plan.tinv_in_smem = tinv_smem;
+        plan.outer_in_smem = outer_smem;
+        plan.gl_doubles = (tinv_smem ? 0 : (size_t)d.cap * d.cap) + (outer_smem ? 0 : outer_doubles(d));
+        plan.bytes = (per + 15) / 16 * 16;
+        groups = G;
+        a.cache_bytes = cache; a.cache_what = what;
     }
-    if (!chosen && can_cache && c_hot > 0 && (!force || force[0] == 'A')) {
-        SmemPlan pa = make_plan(d, kSmemMax);
-        const size_t base = (pa.bytes + 15) / 16 * 16;
-        if (pa.tinv_in_smem && base + c_hot <= kSmemMax) {
-            plan = pa; a.cache_offset = base; a.cache_bytes = c_hot; a.cache_what = 2;
-            if (base + a.cache_bytes + c_se <= kSmemMax) { a.cache_bytes += c_se; a.cache_what |= 1; }
-            if (base + a.cache_bytes + c_raw <= kSmemMax) { a.cache_bytes += c_raw; a.cache_what |= 4; }
-            chosen = true;
-        }
-    }
-    if (!chosen) {
-        plan = make_plan(d, kSmemSM / 2 - 1024);
-        if (!(plan.tinv_in_smem && plan.outer_in_smem)) {
-            const SmemPlan p1 = make_plan(d, kSmemMax);
-            if (p1.tinv_in_smem && !plan.tinv_in_smem) plan = p1;
-        }
-    }
-    if (plan.bytes > kSmemMax) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
+    if (!groups) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
     a.plan = plan;
-    const size_t smem = a.cache_bytes ? (size_t)(a.cache_offset + a.cache_bytes) : plan.bytes;
+    a.group_bytes = plan.bytes;
+    a.cache_offset = (unsigned long long)groups * plan.bytes;
+    const size_t smem = (size_t)a.cache_offset + a.cache_bytes;
     CK(cudaFuncSetAttribute(lcqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_solve_kernel, kThreads, smem), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_solve_kernel, threads * groups, smem), LCQP_CUDA_LAUNCH_FAILED);
     if (const char* t = getenv("LCQP_CUDA_CTAS_PER_SM")) { const int v = atoi(t); if (v >= 1 && v < per_sm) per_sm = v; }  // tuning aid
     if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
     int grid = per_sm * h->num_sms;
-    if (grid > h->batch) grid = h->batch;
+    if ((long long)grid * groups > h->batch) grid = (h->batch + groups - 1) / groups;
 
     // per-CTA global scratch
     a.ws_mats_doubles = a.mats_shared ? 0 : md;
     a.ws_stride = a.ws_mats_doubles + plan.gl_doubles;
-    const size_t ws_total = a.ws_stride * (size_t)grid;
+    const size_t ws_total = a.ws_stride * (size_t)grid * groups;
     if (ws_total > h->workspace_cap) {
         if (h->workspace) cudaFree(h->workspace);
         h->workspace = nullptr; h->workspace_cap = 0;
@@ -594,14 +621,16 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     }
     a.workspace = h->workspace;
 
-    int threads = kThreads;
-    if (const char* t = getenv("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v == 64 || v == 128 || v == 256) threads = v; }  // tuning aid
-    lcqp_solve_kernel<<<grid, threads, smem, stream>>>(a);
+    if (getenv("LCQP_CUDA_VERBOSE"))
+        fprintf(stderr, "lcqp_cuda: grid %d x (%d threads x %d groups), %d CTA/SM, smem %zu B = %d x %zu (tinv %s, outer %s) + cache %llu (what %d; se %zu hot %zu raw %zu), mE %d cap %d\n",
+                grid, threads, groups, per_sm, smem, groups, (size_t)plan.bytes, plan.tinv_in_smem ? "smem" : "L2", plan.outer_in_smem ? "smem" : "L2",
+                a.cache_bytes, a.cache_what, c_se, c_hot, c_raw, mE, d.cap);
+    lcqp_solve_kernel<<<grid, dim3(threads, groups), smem, stream>>>(a);
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
     h->last_stream = stream;
-    h->last_grid = grid;
+    h->last_grid = grid * groups;
     h->last_smem = (int)smem;
     h->ran = true;
     return LCQP_CUDA_OK;

@@ -62,7 +62,11 @@
 #define LCQ_WARP ((int)(threadIdx.x >> 5))
 #define LCQ_NWARP ((int)(blockDim.x >> 5))
 #define LCQ_LANES 32
-#define LCQ_SYNC() __syncthreads()
+// A CTA holds blockDim.y independent GROUPS of blockDim.x threads; a group owns one instance at a time and
+// synchronises on its own named barrier (id 1 + group), so that groups run their own control flow while
+// sharing the CTA's operator cache.
+#define LCQ_GROUP ((int)threadIdx.y)
+#define LCQ_SYNC() asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)threadIdx.y), "r"((int)blockDim.x) : "memory")
 // The solver is bound by instruction fetch, not by issue slots: its hot path must stay inside the 32 KB
 // L1.5 instruction cache, so no loop is unrolled.
 #define LCQ_LOOP _Pragma("unroll 1")
@@ -71,6 +75,34 @@
 #include "../../include/lcqp_cuda.h"
 
 namespace lcqp {
+
+// Pointer into the CTA's shared memory.  The accessors tell the compiler the address space
+// (__builtin_assume(__isShared)), so that element accesses compile to LDS/STS with 32-bit addresses instead of
+// generic loads; it converts implicitly to a plain (generic) pointer where a callee takes one.
+template <class T> struct SPtr {
+    T* p;
+    LCQ_HD SPtr() : p(nullptr) {}
+    LCQ_HD SPtr(T* q) : p(q) {}
+#ifdef LCQP_HOST_EMU
+    T& operator[](int i) const { return p[i]; }
+    T* operator->() const { return p; }
+    T& operator*() const { return *p; }
+#else
+    __device__ __forceinline__ T& operator[](int i) const { __builtin_assume(__isShared(p)); return p[i]; }
+    __device__ __forceinline__ T* operator->() const { __builtin_assume(__isShared(p)); return p; }
+    __device__ __forceinline__ T& operator*() const { __builtin_assume(__isShared(p)); return *p; }
+#endif
+    LCQ_HD operator T*() const { return p; }
+};
+typedef SPtr<double> SVec;
+
+#ifdef LCQP_HOST_EMU
+#define LCQ_ASSUME_SHARED(ptr) ((void)0)
+#define LCQ_ASSUME_GLOBAL(ptr) ((void)0)
+#else
+#define LCQ_ASSUME_SHARED(ptr) __builtin_assume(__isShared(ptr))
+#define LCQ_ASSUME_GLOBAL(ptr) __builtin_assume(__isGlobal(ptr))
+#endif
 
 constexpr double kEPS = 2.221e-16;       // LCQPow Utilities::EPS (Utilities.hpp:350)
 constexpr double kQPInf = 1e20;          // Utilities::INFTY (Utilities.hpp:362)
@@ -101,13 +133,14 @@ struct Op {
     const double* va;
     const int* lrows;
     int rows, cols, ld, trans, nlong;
+    int smem;   // the CSR arrays were copied into shared memory (operator cache)
 };
 
 LCQ_DEV Op dense_op(const double* M, int rows, int cols, int ld, int trans)
 {
     Op o;
     o.dense = M; o.rp = nullptr; o.ci = nullptr; o.va = nullptr; o.lrows = nullptr;
-    o.rows = rows; o.cols = cols; o.ld = ld; o.trans = trans; o.nlong = 0;
+    o.rows = rows; o.cols = cols; o.ld = ld; o.trans = trans; o.nlong = 0; o.smem = 0;
     return o;
 }
 
@@ -188,6 +221,7 @@ struct Scalars {
     int ired[32];
     double fred[2][3][8];   // double-buffered partials of the single-barrier reductions (solver CTAs: <= 8 warps)
     int fired[2][8];
+    int ior[32];
     int bidx;
     int flag;
     int pad[2];
@@ -195,20 +229,20 @@ struct Scalars {
 
 // Working set of one instance (shared memory, except the outer-loop vectors and Tinv when they do not fit).
 struct Work {
-    // QP (scaled space)
-    double *q, *x, *xa, *px, *r1, *u, *t, *dx;                      // n
-    double *z, *y, *l, *ub, *lam, *dlam, *r2, *zx, *zp, *w, *yf;    // m
-    double *dI, *lI;                                                // cap
-    double *cE, *vE;                                                // mE
-    signed char *W, *Wtry, *Wfail, *ctype, *pin;                    // m
-    int* idx;                                                       // cap: rows of the inequality working set
-    double* Tinv;                                                   // shared memory: packed lower triangle, cap*(cap+1)/2;
-    int tld;                                                        // global memory: full storage, leading dimension tld (0 = packed)
-    double* ys;                                                     // m  accepted multipliers, unscaled, qpOASES sign
-    // outer loop (unscaled)
-    double *xk, *pk, *gk, *gt, *gphi, *stat, *tn;                   // n
-    double *Lx, *Rx;                                                // nComp
-    Scalars* sc;
+    // QP (scaled space): always in shared memory
+    SVec q, x, xa, px, r1, u, t, dx;                               // n
+    SVec z, y, l, ub, lam, dlam, r2, zx, zp, w, yf;                // m
+    SVec dI, lI;                                                   // cap
+    SVec cE, vE;                                                   // mE
+    SPtr<signed char> W, Wtry, Wfail, ctype, pin;                  // m
+    SPtr<int> idx;                                                 // cap: rows of the inequality working set
+    double* Tinv;                                                  // shared memory: packed lower triangle, cap*(cap+1)/2;
+    int tld;                                                       // global memory: full storage, leading dimension tld (0 = packed)
+    SVec ys;                                                       // m  accepted multipliers, unscaled, qpOASES sign
+    // outer loop (unscaled): shared memory when it fits, else global scratch
+    double *xk, *pk, *gk, *gt, *gphi, *stat, *tn;                  // n
+    double *Lx, *Rx;                                               // nComp
+    SPtr<Scalars> sc;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -270,9 +304,15 @@ LCQ_DEV void block_sum2(double& a, double& b, Scalars* sc)
 LCQ_DEV int block_or(int v, Scalars* sc)
 {
 #ifndef LCQP_HOST_EMU
-    v = __syncthreads_or(v);
-#endif
+    v = (int)__reduce_or_sync(0xffffffffu, (unsigned)v);
+    LCQ_SYNC();
+    if (LCQ_LANE == 0) sc->ior[LCQ_WARP] = v;
+    LCQ_SYNC();
+    v = 0;
+    LCQ_LOOP for (int k = 0; k < LCQ_NWARP; k++) v |= sc->ior[k];
+#else
     (void)sc;
+#endif
     return v;
 }
 
@@ -369,26 +409,57 @@ LCQ_DEV int fast_argmin_lex(double a, double wgt, int i, double* aout, Scalars* 
 // operator application
 // ------------------------------------------------------------------------------------------------
 // out[r] = (init ? init[iidx ? iidx[r] : r] : 0) + scale * sum_c M[r][c] v[c]      (no barrier inside)
-LCQ_DEVN void op_mv(const Op& op, const double* v, const double* init, double scale, double* out, const int* iidx = nullptr)
+// VS: v, init and out live in shared memory (the inner passes of the QP solver); OS: so do the CSR arrays
+// (operator cache).  The address spaces are compile-time facts of each instantiation, so that the loops
+// compile to LDS/STS (or LDG) instead of generic accesses.
+template <bool VS, bool OS>
+LCQ_DEV void csr_mv(const int* __restrict__ rp, const unsigned short* __restrict__ ci, const double* __restrict__ va,
+                    const int* __restrict__ lrows, int rows, int nlong, const double* v, const double* init, bool has_init,
+                    double scale, double* out, const int* iidx)
 {
-#define LCQ_INIT(r) (init ? init[iidx ? iidx[r] : (r)] : 0.0)
-    if (op.rp) {
-        LCQ_LOOP for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
-            const int k0 = op.rp[r], k1 = op.rp[r + 1];
-            if (k1 - k0 > kLongRow && LCQ_LANES > 1) continue;
-            double s = 0;
-            LCQ_LOOP for (int k = k0; k < k1; k++) s += op.va[k] * v[op.ci[k]];
-            out[r] = LCQ_INIT(r) + scale * s;
+#ifndef LCQP_HOST_EMU
+    if (VS) { LCQ_ASSUME_SHARED(v); LCQ_ASSUME_SHARED(init); LCQ_ASSUME_SHARED(out); }
+    if (OS) { LCQ_ASSUME_SHARED(rp); LCQ_ASSUME_SHARED(ci); LCQ_ASSUME_SHARED(va); LCQ_ASSUME_SHARED(lrows); }
+    else { LCQ_ASSUME_GLOBAL(rp); LCQ_ASSUME_GLOBAL(ci); LCQ_ASSUME_GLOBAL(va); LCQ_ASSUME_GLOBAL(lrows); }
+#endif
+#define LCQ_INIT(r) (has_init ? init[iidx ? iidx[r] : (r)] : 0.0)
+    LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
+        const int k0 = rp[r], k1 = rp[r + 1];
+        if (k1 - k0 > kLongRow && LCQ_LANES > 1) continue;
+        double s = 0;
+        LCQ_LOOP for (int k = k0; k < k1; k++) s += va[k] * v[ci[k]];
+        out[r] = LCQ_INIT(r) + scale * s;
+    }
+    if (LCQ_LANES > 1)
+        LCQ_LOOP for (int a = LCQ_WARP; a < nlong; a += LCQ_NWARP) {
+            const int r = lrows[a];
+            const int k1 = rp[r + 1];
+            double s0 = 0, s1 = 0;
+            int k = rp[r] + LCQ_LANE;
+            LCQ_LOOP for (; k + LCQ_LANES < k1; k += 2 * LCQ_LANES) { s0 += va[k] * v[ci[k]]; s1 += va[k + LCQ_LANES] * v[ci[k + LCQ_LANES]]; }
+            if (k < k1) s0 += va[k] * v[ci[k]];
+            const double s = warp_sum(s0 + s1);
+            if (LCQ_LANE == 0) out[r] = LCQ_INIT(r) + scale * s;
         }
-        if (LCQ_LANES > 1)
-            LCQ_LOOP for (int a = LCQ_WARP; a < op.nlong; a += LCQ_NWARP) {
-                const int r = op.lrows[a];
-                double s = 0;
-                LCQ_LOOP for (int k = op.rp[r] + LCQ_LANE; k < op.rp[r + 1]; k += LCQ_LANES) s += op.va[k] * v[op.ci[k]];
-                s = warp_sum(s);
-                if (LCQ_LANE == 0) out[r] = LCQ_INIT(r) + scale * s;
-            }
-    } else if (!op.trans) {
+#undef LCQ_INIT
+}
+
+template <bool VS>
+LCQ_DEVN void op_mv_t(const Op& opr, const double* v, const double* init, double scale, double* out, const int* iidx = nullptr)
+{
+    const Op op = opr;
+    const bool has_init = init != nullptr;
+    if (!has_init) init = v;   // a valid address for the address-space assumption; never read
+    if (op.rp) {
+        if (op.smem) csr_mv<VS, true>(op.rp, op.ci, op.va, op.lrows, op.rows, op.nlong, v, init, has_init, scale, out, iidx);
+        else csr_mv<VS, false>(op.rp, op.ci, op.va, op.lrows, op.rows, op.nlong, v, init, has_init, scale, out, iidx);
+        return;
+    }
+#ifndef LCQP_HOST_EMU
+    if (VS) { LCQ_ASSUME_SHARED(v); LCQ_ASSUME_SHARED(init); LCQ_ASSUME_SHARED(out); }
+#endif
+#define LCQ_INIT(r) (has_init ? init[iidx ? iidx[r] : (r)] : 0.0)
+    if (!op.trans) {
         const int rows = op.rows, cols = op.cols, ld = op.ld;
         LCQ_LOOP for (int r0 = LCQ_WARP; r0 < rows; r0 += 4 * LCQ_NWARP) {
             const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
@@ -420,24 +491,55 @@ LCQ_DEVN void op_mv(const Op& op, const double* v, const double* init, double sc
 #undef LCQ_INIT
 }
 
-// out[a] = sum_c M[idx[a]][c] v[c] - (sub ? sub[idx[a]] : 0)   for a < na   (rows selected by idx; op not transposed)
-LCQ_DEVN void op_mv_rows(const Op& op, const int* idx, int na, const double* v, const double* sub, double* out)
+// generic address spaces (outer loop, preparation) / everything in shared memory (inner passes)
+LCQ_DEV void op_mv(const Op& op, const double* v, const double* init, double scale, double* out, const int* iidx = nullptr)
 {
+    op_mv_t<false>(op, v, init, scale, out, iidx);
+}
+LCQ_DEV void op_mv_s(const Op& op, const double* v, const double* init, double scale, double* out, const int* iidx = nullptr)
+{
+    op_mv_t<true>(op, v, init, scale, out, iidx);
+}
+
+// out[a] = sum_c M[idx[a]][c] v[c] - (sub ? sub[idx[a]] : 0)   for a < na   (rows selected by idx; op not transposed)
+// idx, v, sub, out live in shared memory (inner passes only).
+template <bool OS>
+LCQ_DEV void csr_mv_rows(const int* __restrict__ rp, const unsigned short* __restrict__ ci, const double* __restrict__ va,
+                         const int* idx, int na, const double* v, const double* sub, bool has_sub, double* out)
+{
+#ifndef LCQP_HOST_EMU
+    LCQ_ASSUME_SHARED(idx); LCQ_ASSUME_SHARED(v); LCQ_ASSUME_SHARED(sub); LCQ_ASSUME_SHARED(out);
+    if (OS) { LCQ_ASSUME_SHARED(rp); LCQ_ASSUME_SHARED(ci); LCQ_ASSUME_SHARED(va); }
+    else { LCQ_ASSUME_GLOBAL(rp); LCQ_ASSUME_GLOBAL(ci); LCQ_ASSUME_GLOBAL(va); }
+#endif
+    LCQ_LOOP for (int a = LCQ_TID; a < na; a += LCQ_NT) {
+        const int r = idx[a];
+        double s = 0;
+        const int k1 = rp[r + 1];
+        LCQ_LOOP for (int k = rp[r]; k < k1; k++) s += va[k] * v[ci[k]];
+        out[a] = s - (has_sub ? sub[r] : 0.0);
+    }
+}
+
+LCQ_DEVN void op_mv_rows(const Op& opr, const int* idx, int na, const double* v, const double* sub, double* out)
+{
+    const Op op = opr;
+    const bool has_sub = sub != nullptr;
+    if (!has_sub) sub = v;
     if (op.rp) {
-        LCQ_LOOP for (int a = LCQ_TID; a < na; a += LCQ_NT) {
-            const int r = idx[a];
-            double s = 0;
-            LCQ_LOOP for (int k = op.rp[r]; k < op.rp[r + 1]; k++) s += op.va[k] * v[op.ci[k]];
-            out[a] = s - (sub ? sub[r] : 0.0);
-        }
+        if (op.smem) csr_mv_rows<true>(op.rp, op.ci, op.va, idx, na, v, sub, has_sub, out);
+        else csr_mv_rows<false>(op.rp, op.ci, op.va, idx, na, v, sub, has_sub, out);
     } else {
+#ifndef LCQP_HOST_EMU
+        LCQ_ASSUME_SHARED(idx); LCQ_ASSUME_SHARED(v); LCQ_ASSUME_SHARED(sub); LCQ_ASSUME_SHARED(out);
+#endif
         LCQ_LOOP for (int a = LCQ_WARP; a < na; a += LCQ_NWARP) {
             const int r = idx[a];
             const double* row = op.dense + (size_t)r * op.ld;
             double s = 0;
             LCQ_LOOP for (int c = LCQ_LANE; c < op.cols; c += LCQ_LANES) s += row[c] * v[c];
             s = warp_sum(s);
-            if (LCQ_LANE == 0) out[a] = s - (sub ? sub[r] : 0.0);
+            if (LCQ_LANE == 0) out[a] = s - (has_sub ? sub[r] : 0.0);
         }
     }
 }
@@ -473,12 +575,8 @@ LCQ_DEV size_t pidx(int a, int b) { return a >= b ? (size_t)a * (a + 1) / 2 + b 
 
 // y = sgn * S v for a symmetric matrix S of order nw, scattered to up to three places:
 //     out[a] = y_a;   o2[sidx[a]] = y_a;   o3[sidx[a]] = y_a          (null pointers are skipped)
-// ld == 0: S is a packed lower triangle in shared memory.  Two threads per row, each over half of the
-//          columns: below the diagonal the row is contiguous, above it the column is walked with an
-//          incrementally updated offset.
-// ld  > 0: S is in full storage with leading dimension ld in global memory (L2): one warp per row with
-//          coalesced row reads, four rows of a warp in flight.
-// One non-inlined copy serves every call site (the solver is instruction-fetch bound).
+// ld == 0: S is a packed lower triangle (shared memory);  ld > 0: full storage with leading dimension ld
+// (global memory / L2), exactly symmetric.  One non-inlined copy serves every call site.
 LCQ_DEVN void sym_apply(const double* __restrict__ S, int ld, int nw, const double* v, double sgn,
                         double* out, const int* sidx, double* o2, double* o3)
 {
@@ -492,57 +590,59 @@ LCQ_DEVN void sym_apply(const double* __restrict__ S, int ld, int nw, const doub
             if (o3) o3[i_] = y_;                          \
         }                                                 \
     } while (0)
-    if (ld) {
-        LCQ_LOOP for (int r0 = LCQ_WARP; r0 < nw; r0 += 4 * LCQ_NWARP) {
-            const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
-            const double* a0 = S + (size_t)r0 * ld;
-            const double* a1 = S + (size_t)(r1 < nw ? r1 : r0) * ld;
-            const double* a2 = S + (size_t)(r2 < nw ? r2 : r0) * ld;
-            const double* a3 = S + (size_t)(r3 < nw ? r3 : r0) * ld;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            LCQ_LOOP for (int c = LCQ_LANE; c < nw; c += LCQ_LANES) {
-                const double vc = v[c];
-                const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
-                s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
-            }
-            s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
-            if (LCQ_LANE == 0) {
-                LCQ_EMIT(r0, s0);
-                if (r1 < nw) LCQ_EMIT(r1, s1);
-                if (r2 < nw) LCQ_EMIT(r2, s2);
-                if (r3 < nw) LCQ_EMIT(r3, s3);
-            }
-        }
-        return;
-    }
 #ifdef LCQP_HOST_EMU
     for (int a = 0; a < nw; a++) {
         double s = 0;
-        for (int b = 0; b < nw; b++) s += S[pidx(a, b)] * v[b];
+        for (int b = 0; b < nw; b++) s += (ld ? S[(size_t)a * ld + b] : S[pidx(a, b)]) * v[b];
         LCQ_EMIT(a, s);
     }
 #else
-    const int half = (nw + 1) >> 1;
-    LCQ_LOOP for (int base = 0; base < 2 * nw; base += LCQ_NT) {
-        const int t = base + LCQ_TID;
-        const int a = t >> 1, h = t & 1;
-        double s = 0;
-        if (a < nw) {
-            const int b0 = h ? half : 0, b1 = h ? nw : half;
-            const double* row = S + (size_t)a * (a + 1) / 2;
-            const int be = b1 < a + 1 ? b1 : a + 1;
-            double s2 = 0;
-            int b = b0;
-            LCQ_LOOP for (; b + 1 < be; b += 2) { s += row[b] * v[b]; s2 += row[b + 1] * v[b + 1]; }
-            if (b < be) s += row[b] * v[b];
-            b = b0 > a + 1 ? b0 : a + 1;
-            const double* q = S + (size_t)b * (b + 1) / 2 + a;
-            LCQ_LOOP for (; b + 1 < b1; b += 2) { s += q[0] * v[b]; s2 += q[b + 1] * v[b + 1]; q += 2 * b + 3; }
-            if (b < b1) s += q[0] * v[b];
-            s += s2;
+    // One thread per row, no cross-lane reduction.  S is symmetric, so row a is read as column a:
+    //   full storage: S[b*ld + a] -- consecutive threads read consecutive addresses (coalesced L2 sectors),
+    //                 eight loads in flight per thread;
+    //   packed      : b <= a walks the contiguous row a (the triangular offsets of 16 consecutive rows fall
+    //                 into 16 distinct 8-byte banks), b > a reads S(b,a) at T(b)+a (consecutive across threads).
+    LCQ_ASSUME_SHARED(v);
+    if (out) LCQ_ASSUME_SHARED(out);
+    if (o2) LCQ_ASSUME_SHARED(o2);
+    if (o3) LCQ_ASSUME_SHARED(o3);
+    if (ld) {
+        LCQ_ASSUME_GLOBAL(S);
+        LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            const double* col = S + a;
+            int b = 0;
+            LCQ_LOOP for (; b + 16 <= nw; b += 16) {
+                double m[16];
+#pragma unroll
+                for (int k = 0; k < 16; k++) m[k] = col[(size_t)(b + k) * ld];
+#pragma unroll
+                for (int k = 0; k < 16; k += 4) {
+                    s0 += m[k] * v[b + k]; s1 += m[k + 1] * v[b + k + 1]; s2 += m[k + 2] * v[b + k + 2]; s3 += m[k + 3] * v[b + k + 3];
+                }
+            }
+            LCQ_LOOP for (; b + 4 <= nw; b += 4) {
+                const double m0 = col[(size_t)b * ld], m1 = col[(size_t)(b + 1) * ld], m2 = col[(size_t)(b + 2) * ld], m3 = col[(size_t)(b + 3) * ld];
+                s0 += m0 * v[b]; s1 += m1 * v[b + 1]; s2 += m2 * v[b + 2]; s3 += m3 * v[b + 3];
+            }
+            LCQ_LOOP for (; b < nw; b++) s0 += col[(size_t)b * ld] * v[b];
+            LCQ_EMIT(a, (s0 + s1) + (s2 + s3));
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        if (a < nw && h == 0) LCQ_EMIT(a, s);
+    } else {
+        LCQ_ASSUME_SHARED(S);
+        LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
+            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            const double* row = S + (size_t)a * (a + 1) / 2;
+            int b = 0;
+            LCQ_LOOP for (; b + 4 <= a + 1; b += 4) {
+                s0 += row[b] * v[b]; s1 += row[b + 1] * v[b + 1]; s2 += row[b + 2] * v[b + 2]; s3 += row[b + 3] * v[b + 3];
+            }
+            LCQ_LOOP for (; b <= a; b++) s0 += row[b] * v[b];
+            const double* q = S + (size_t)b * (b + 1) / 2 + a;   // S(b, a), b = a + 1
+            LCQ_LOOP for (; b + 2 <= nw; b += 2) { s1 += q[0] * v[b]; s2 += q[b + 1] * v[b + 1]; q += 2 * b + 3; }
+            if (b < nw) s3 += q[0] * v[b];
+            LCQ_EMIT(a, (s0 + s1) + (s2 + s3));
+        }
     }
 #endif
 #undef LCQ_EMIT
@@ -985,7 +1085,7 @@ LCQ_DEVN void cache_op(Op& op, unsigned char*& cur, unsigned char* end)
     LCQ_LOOP for (int k = LCQ_TID; k < nnz; k += LCQ_NT) { va[k] = op.va[k]; ci[k] = op.ci[k]; }
     LCQ_LOOP for (int r = LCQ_TID; r <= rows; r += LCQ_NT) rp[r] = op.rp[r];
     LCQ_LOOP for (int a = LCQ_TID; a < nl; a += LCQ_NT) lr[a] = op.lrows[a];
-    op.va = va; op.rp = rp; op.ci = ci; op.lrows = lr;
+    op.va = va; op.rp = rp; op.ci = ci; op.lrows = lr; op.smem = 1;
     cur += need;
 }
 
@@ -1046,10 +1146,10 @@ LCQ_DEV void cache_requirements(Mats& mt, const RawOps& ro)
 // working set, the prepared operands) is block-shared and only POINTED to from here, so that the non-inlined
 // device functions find their operands in shared memory instead of a per-thread stack frame in L2.
 struct QP {
-    const Dims* d;
-    const Mats* mt;
-    const Work* w;
-    const lcqp_cuda_options* o;
+    SPtr<const Dims> d;
+    SPtr<const Mats> mt;
+    SPtr<const Work> w;
+    SPtr<const lcqp_cuda_options> o;
     int nw;           // rows in the inequality working set = order of Tinv (idx[0..nw))
     int have_W;
     int tinv_valid;   // Tinv matches idx/W
@@ -1067,11 +1167,11 @@ LCQ_DEVN void admm_iter(QP& s)
     LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.w[i] = rho_of(w.ctype[i], rho) * w.z[i] - w.y[i];
     LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.u[j] = sigma * w.x[j] - w.q[j];
     LCQ_SYNC();
-    op_mv(mt.oAt, w.w, w.u, 1.0, w.t);        // rhs = sigma x - q + A'w
+    op_mv_s(mt.oAt, w.w, w.u, 1.0, w.t);        // rhs = sigma x - q + A'w
     LCQ_SYNC();
-    op_mv(mt.oMinv, w.t, nullptr, 1.0, w.dx); // xt
+    op_mv_s(mt.oMinv, w.t, nullptr, 1.0, w.dx); // xt
     LCQ_SYNC();
-    op_mv(mt.oA, w.dx, nullptr, 1.0, w.zp);   // zt = A xt
+    op_mv_s(mt.oA, w.dx, nullptr, 1.0, w.zp);   // zt = A xt
     LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = alpha * w.dx[j] + (1.0 - alpha) * w.x[j];
     LCQ_SYNC();
     LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
@@ -1101,6 +1201,47 @@ LCQ_DEVN void guess_working_set(QP& s, signed char* W)
     LCQ_SYNC();
 }
 
+// S += c * u u' on the leading nw x nw block of a full-storage matrix in global memory (leading dimension ld).
+// (u_a u_b) c is commutative in a, b: S stays exactly symmetric.  Eight independent load -> update -> store
+// chains per thread, so that eight L2 round trips overlap instead of one.
+LCQ_DEVN void rank1_update_full(double* __restrict__ S, int ld, int nw, const double* u, double c)
+{
+#ifndef LCQP_HOST_EMU
+    LCQ_ASSUME_GLOBAL(S);
+    LCQ_ASSUME_SHARED(u);
+    // a warp takes two rows at a time and four 32-column chunks of each: eight elements in flight per thread
+    LCQ_LOOP for (int a0 = LCQ_WARP; a0 < nw; a0 += 2 * LCQ_NWARP) {
+        const int a1 = a0 + LCQ_NWARP;
+        const bool two = a1 < nw;
+        const double u0 = u[a0], u1 = two ? u[a1] : 0.0;
+        double* r0 = S + (size_t)a0 * ld;
+        double* r1 = S + (size_t)(two ? a1 : a0) * ld;
+        LCQ_LOOP for (int b0 = LCQ_LANE; b0 < nw; b0 += 4 * LCQ_LANES) {
+            double m0[4], m1[4], ub[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int b = b0 + k * LCQ_LANES;
+                const bool in = b < nw;
+                ub[k] = in ? u[b] : 0.0;
+                m0[k] = in ? r0[b] : 0.0;
+                m1[k] = (in && two) ? r1[b] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int b = b0 + k * LCQ_LANES;
+                if (b < nw) {
+                    r0[b] = m0[k] + (u0 * ub[k]) * c;
+                    if (two) r1[b] = m1[k] + (u1 * ub[k]) * c;
+                }
+            }
+        }
+    }
+#else
+    for (int a = 0; a < nw; a++)
+        for (int b = 0; b < nw; b++) S[(size_t)a * ld + b] += (u[a] * u[b]) * c;
+#endif
+}
+
 // ---- explicit inverse of T[W,W] + delta I (packed), maintained by bordering ------------------------
 // Append inequality row j to the working set (position nw).  A row that is numerically a combination of
 // the rows already active -- Schur pivot kappa at the level of the regularisation, kappa <= 10 delta
@@ -1124,14 +1265,9 @@ LCQ_DEVN int tinv_append(QP& s, int j)
     const double ik = 1.0 / kappa;
     if (w.tld) {
         const int ld = w.tld;
-        LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
-            const double ua = w.lI[a] * ik;
-            double* row = Si + (size_t)a * ld;
-            LCQ_LOOP for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) row[b] += ua * w.lI[b];
-            if (LCQ_LANE == 0) row[nw] = -ua;
-        }
+        rank1_update_full(Si, ld, nw, w.lI, ik);   // S += ik * lI lI'
         double* row = Si + (size_t)nw * ld;
-        LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
+        LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) { const double v = -w.lI[a] * ik; row[a] = v; Si[(size_t)a * ld + nw] = v; }
         if (LCQ_TID == 0) { row[nw] = ik; w.idx[nw] = j; }
     } else {
         LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
@@ -1158,16 +1294,13 @@ LCQ_DEVN void tinv_remove(QP& s, int p)
     LCQ_LOOP for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.dI[b] = ld ? Si[(size_t)b * ld + p] : Si[pidx(b, p)];
     LCQ_SYNC();
     const double ic = 1.0 / w.dI[p];
-    LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
-        const double ca = w.dI[a] * ic;
-        if (ld) {
-            double* row = Si + (size_t)a * ld;
-            LCQ_LOOP for (int b = LCQ_LANE; b < nw; b += LCQ_LANES) row[b] -= ca * w.dI[b];
-        } else {
+    if (ld) rank1_update_full(Si, ld, nw, w.dI, -ic);   // S -= ic * dI dI'
+    else
+        LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
+            const double ca = w.dI[a] * ic;
             double* row = Si + (size_t)a * (a + 1) / 2;
             LCQ_LOOP for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] -= ca * w.dI[b];
         }
-    }
     LCQ_SYNC();
     if (p != last) {
         // move row/column `last` into position p
@@ -1224,13 +1357,13 @@ LCQ_DEVN void kkt_solve(QP& s)
     const double* SE = mt.SEinvP ? mt.SEinvP : mt.SEinv;
     const int seld = mt.SEinvP ? 0 : ldE;
     // K^-1 [r1; r2_E]:  u = Hinv r1, vE = SEinv (A_E u - r2_E), t = u - (Hinv A_E') vE
-    op_mv(mt.oHinv, w.r1, nullptr, 1.0, (mE > 0 || nw > 0) ? w.u : w.dx);
+    op_mv_s(mt.oHinv, w.r1, nullptr, 1.0, (mE > 0 || nw > 0) ? w.u : w.dx);
     if (mE > 0) {
-        op_mv(mt.oAHE, w.r1, w.r2, -1.0, w.cE, mt.eidx);   // cE = r2_E - AHE r1: the sign is undone below
+        op_mv_s(mt.oAHE, w.r1, w.r2, -1.0, w.cE, mt.eidx);   // cE = r2_E - AHE r1: the sign is undone below
         LCQ_SYNC();
         sym_apply(SE, seld, mE, w.cE, -1.0, w.vE, nw == 0 ? mt.eidx : nullptr, w.dlam, nullptr);
         LCQ_SYNC();
-        op_mv(mt.oAHtE, w.vE, w.u, -1.0, nw == 0 ? w.dx : w.t);
+        op_mv_s(mt.oAHtE, w.vE, w.u, -1.0, nw == 0 ? w.dx : w.t);
     } else if (nw > 0) {
         LCQ_SYNC();
         LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.t[j] = w.u[j];
@@ -1243,16 +1376,16 @@ LCQ_DEVN void kkt_solve(QP& s)
     sym_apply(w.Tinv, w.tld, nw, w.dI, 1.0, nullptr, w.idx, w.yf, w.dlam);
     LCQ_SYNC();
     // second K^-1 on [r1 - A_I' lI; r2_E]
-    op_mv(mt.oAt, w.yf, w.r1, -1.0, w.t);
+    op_mv_s(mt.oAt, w.yf, w.r1, -1.0, w.t);
     LCQ_SYNC();
-    op_mv(mt.oHinv, w.t, nullptr, 1.0, mE > 0 ? w.u : w.dx);
+    op_mv_s(mt.oHinv, w.t, nullptr, 1.0, mE > 0 ? w.u : w.dx);
     LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.yf[w.idx[a]] = 0.0;
     if (mE > 0) {
-        op_mv(mt.oAHE, w.t, w.r2, -1.0, w.cE, mt.eidx);
+        op_mv_s(mt.oAHE, w.t, w.r2, -1.0, w.cE, mt.eidx);
         LCQ_SYNC();
         sym_apply(SE, seld, mE, w.cE, -1.0, w.vE, mt.eidx, w.dlam, nullptr);
         LCQ_SYNC();
-        op_mv(mt.oAHtE, w.vE, w.u, -1.0, w.dx);
+        op_mv_s(mt.oAHtE, w.vE, w.u, -1.0, w.dx);
     }
     LCQ_SYNC();
 }
@@ -1265,9 +1398,9 @@ LCQ_DEVN double kkt_residual(QP& s, const signed char* W, const double* x, const
     const int n = s.d->n, m = s.d->m;
     const Work& w = *s.w;
     const Mats& mt = *s.mt;
-    op_mv(mt.oP, x, w.q, 1.0, w.px);            // q + P x
-    op_mv(mt.oAt, lam, nullptr, 1.0, w.u);      // A' lam
-    op_mv(mt.oA, x, nullptr, 1.0, w.zx);
+    op_mv_s(mt.oP, x, w.q, 1.0, w.px);            // q + P x
+    op_mv_s(mt.oAt, lam, nullptr, 1.0, w.u);      // A' lam
+    op_mv_s(mt.oA, x, nullptr, 1.0, w.zx);
     LCQ_SYNC();
     double rn = 0;
     LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
@@ -1432,7 +1565,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
         double apn = 0;
         if (ratio_test && !clean) {
             // ratio test against the inactive rows (Nocedal & Wright alg. 16.3)
-            op_mv(mt.oA, w.dx, nullptr, 1.0, w.zp);
+            op_mv_s(mt.oA, w.dx, nullptr, 1.0, w.zp);
             LCQ_SYNC();
             LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) apn = fmax(apn, fabs(w.zp[i]));
             apn = fast_max(apn, w.sc, s.ph);
@@ -1502,7 +1635,7 @@ LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin)
     LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) { w.yf[i] = 0.0; w.dlam[i] = 0.0; }   // invariants of kkt_solve
     LCQ_SYNC();
     LCQ_LOOP for (int pass = 0; pass < 4; pass++) {
-        op_mv(mt.oA, w.xa, nullptr, 1.0, w.zx);
+        op_mv_s(mt.oA, w.xa, nullptr, 1.0, w.zx);
         LCQ_SYNC();
         double rn = 0;
         LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) {
@@ -1521,7 +1654,7 @@ LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin)
         LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += w.dx[j];
         LCQ_SYNC();
     }
-    op_mv(mt.oA, w.xa, nullptr, 1.0, w.zx);
+    op_mv_s(mt.oA, w.xa, nullptr, 1.0, w.zx);
     LCQ_SYNC();
     const double ftol = s.o->qp_feas_tol;
     int bad = 0;
@@ -1565,7 +1698,7 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
             w.y[i] = -yv / mt.E[i];
         }
         LCQ_SYNC();
-        op_mv(mt.oA, w.x, nullptr, 1.0, w.z);
+        op_mv_s(mt.oA, w.x, nullptr, 1.0, w.z);
         s.have_W = 0;
         s.tinv_valid = 0;
         LCQ_SYNC();
@@ -1587,7 +1720,7 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
         if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = (int)(s.n_changes - ch0); return 0; }
         // fall through to ADMM from the previous solution
         s.tinv_valid = 0;
-        op_mv(mt.oA, w.x, nullptr, 1.0, w.z);
+        op_mv_s(mt.oA, w.x, nullptr, 1.0, w.z);
         LCQ_SYNC();
     }
     int have_fail = 0;
