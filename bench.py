@@ -342,8 +342,12 @@ def main():
     total = batch * world * args.steps
 
     if rank == 0:
-        value = total / (elapsed_ms * 1e-3)
-        e2e_v = total / (e2e_ms * 1e-3)
+        # the metric counts SOLVED LCQPs (terminal ReturnValue SUCCESSFUL_RETURN), every step solves the same batch
+        if n_solved < 0.5 * batch * world:
+            raise SystemExit(f"bench.py: only {n_solved:.0f} of {batch * world} instances were solved -- the CUDA path is broken, "
+                             "refusing to report a throughput")
+        value = n_solved * args.steps / (elapsed_ms * 1e-3)
+        e2e_v = n_solved * args.steps / (e2e_ms * 1e-3)
         # roofline of the dominant kernel (lcqp_solve_kernel), SURVEY.md 8(d) row "Shared-factor multi-RHS (C2)":
         # one unit = one KKT solve for one instance = 2 N^2 flop with N = nV + nC + 2 nComp = 503.
         N = NV + NC + 2 * NCOMP

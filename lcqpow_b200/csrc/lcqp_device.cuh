@@ -83,10 +83,10 @@ template <class T> struct SPtr {
     T* p;
     LCQ_HD SPtr() : p(nullptr) {}
     LCQ_HD SPtr(T* q) : p(q) {}
-#ifdef LCQP_HOST_EMU
-    T& operator[](int i) const { return p[i]; }
-    T* operator->() const { return p; }
-    T& operator*() const { return *p; }
+#if defined(LCQP_HOST_EMU) || defined(LCQP_NO_ASSUME)
+    LCQ_HD T& operator[](int i) const { return p[i]; }
+    LCQ_HD T* operator->() const { return p; }
+    LCQ_HD T& operator*() const { return *p; }
 #else
     __device__ __forceinline__ T& operator[](int i) const { __builtin_assume(__isShared(p)); return p[i]; }
     __device__ __forceinline__ T* operator->() const { __builtin_assume(__isShared(p)); return p; }
@@ -96,7 +96,7 @@ template <class T> struct SPtr {
 };
 typedef SPtr<double> SVec;
 
-#ifdef LCQP_HOST_EMU
+#if defined(LCQP_HOST_EMU) || defined(LCQP_NO_ASSUME)
 #define LCQ_ASSUME_SHARED(ptr) ((void)0)
 #define LCQ_ASSUME_GLOBAL(ptr) ((void)0)
 #else
