@@ -240,13 +240,15 @@ def main():
             batch = int(tb.item())
 
     # ---- inputs: the same family on every rank, instances [rank*batch, (rank+1)*batch) ------------
+    from lcqpow_b200 import sharding
+    lo, hi = sharding.shard_range(batch * world, rank, world)
     pb_all = P.circle_batch_fast(batch * world)
-    pb = pb_all.slice(rank * batch, (rank + 1) * batch).normalised()
+    pb = pb_all.slice(lo, hi).normalised()
     del pb_all
     shared = tuple(pb.shared)
     prob = L.LCQProblemBatch(NV, NC, NCOMP, batch, device=local_rank)
     assert prob.setOptions(make_options()) == 0
-    prob.setInstanceOffset(rank * batch)
+    prob.setInstanceOffset(lo)   # perturbStep draws are keyed by the global instance index
 
     # device-resident copies (torch is only the allocator here)
     dev_t = {}
@@ -331,14 +333,10 @@ def main():
     e2e_s = time.perf_counter() - t0
 
     # max over ranks
-    tt = torch.tensor([elapsed_ms, e2e_s * 1e3, float(k_ms)], device=dev, dtype=torch.float64)
-    solved = torch.tensor([float((st["ret"] == 0).sum()), float(st["kktSolves"].sum()) + float(st["admmIters"].sum()),
-                           float(st["iterTotal"].sum()), float(st["subproblemIter"].sum())], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(solved, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms, k_ms = [float(v) for v in tt.tolist()]
-    n_solved, n_units, n_outer, n_sub = [float(v) for v in solved.tolist()]
+    elapsed_ms, e2e_ms, k_ms = sharding.reduce_scalars([elapsed_ms, e2e_s * 1e3, float(k_ms)], "max", dev)
+    n_solved, n_units, n_outer, n_sub = sharding.reduce_scalars(
+        [float((st["ret"] == 0).sum()), float(st["kktSolves"].sum()) + float(st["admmIters"].sum()),
+         float(st["iterTotal"].sum()), float(st["subproblemIter"].sum())], "sum", dev)
     total = batch * world * args.steps
 
     if rank == 0:

@@ -28,6 +28,10 @@ static size_t field_len(int k, int n, int c, int p)
     return 0;
 }
 
+// global index of instance 0 (lcqp_cuda_set_instance_offset of the product): keys the perturbStep draws
+static unsigned long long g_instance_offset = 0;
+extern "C" void lcqp_emu_set_instance_offset(unsigned long long off) { g_instance_offset = off; }
+
 extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsigned shared_mask_in,
                                     const double* Q, const double* g, const double* L, const double* R,
                                     const double* lbL, const double* ubL, const double* lbR, const double* ubR,
@@ -109,7 +113,7 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
         const Inst in = inst(b);
         raw_dense_ops(d, in, ro, shared_mask);
         LoopOut out;
-        run_instance(s, mt, mats_shared, in, ro, (unsigned long long)b, x + (size_t)b * nV, y + (size_t)b * nD, out);
+        run_instance(s, mt, mats_shared, in, ro, g_instance_offset + (unsigned long long)b, x + (size_t)b * nV, y + (size_t)b * nD, out);
         lcqp_cuda_stats st;
         st.ret = out.ret; st.status = out.status; st.iterTotal = out.iterTotal; st.iterOuter = out.iterOuter;
         st.subproblemIter = out.subIter; st.qpExitFlag = out.exitFlag;
