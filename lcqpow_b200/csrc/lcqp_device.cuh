@@ -1502,7 +1502,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
     bool clean = false;        // the from-zero recomputation is running: no ratio tests
     LCQ_LOOP for (int it = 0; it < cap_it; it++) {
         const double rn = kkt_residual(s, W, w.xa, w.lam);
-        bool converged = false;
+        bool converged = false, slow = false;
         if (passes > 0 && !(rn < best)) {
             // the last correction did not help: undo it and take that point as the EQP solution
             LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] -= w.dx[j];
@@ -1511,6 +1511,10 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             kkt_residual(s, W, w.xa, w.lam);
             converged = true;
         } else {
+            // A correction that barely helps means the remaining residual lies along directions whose
+            // curvature is far below the regularisation delta (the refinement contracts by delta/(c+delta)):
+            // the next direction is stretched to the exact minimiser along it (see below).
+            slow = passes > 0 && rn > 0.25 * best && rn > 1e-13;
             best = rn;
             if (rn < 1e-15 || passes >= s.o->qp_refine_iter) converged = true;
         }
@@ -1560,6 +1564,20 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
         }
         s.n_pass++;
         kkt_solve(s);   // r1, r2 -> dx, dlam
+        if (slow && ratio_test && !clean) {
+            // exact line search along dx (the working-set rows are satisfied, so dx moves inside them):
+            // tau = r1'dx / dx'P dx >= 1; the ratio test below then cuts the stretched step at the first bound
+            op_mv_s(mt.oP, w.dx, nullptr, 1.0, w.px);
+            LCQ_SYNC();
+            double pd = 0, cd = 0;
+            LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) { pd += w.r1[j] * w.dx[j]; cd += w.px[j] * w.dx[j]; }
+            fast_sum2(pd, cd, w.sc, s.ph);
+            if (pd > 0.0) {
+                const double tau = (cd > 0.0 && pd < 1e12 * cd) ? pd / cd : 1e12;
+                if (tau > 1.0) LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.dx[j] *= tau;
+                LCQ_SYNC();
+            }
+        }
         double amin = 1.0;
         int block = -1;
         double apn = 0;

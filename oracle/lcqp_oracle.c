@@ -612,6 +612,9 @@ static int eqp_solve(qp_inst* q, const int* W)
             for (int a = 0; a < nw; a++) lam[a] -= q->dl[a];
             break;
         }
+        /* a correction that barely helped: the residual lies along directions whose curvature is far below
+         * delta (the refinement contracts by delta/(c+delta) there); stretch the next one (below) */
+        const int slow = pass > 0 && rn > 0.25 * best && rn > 1e-13;
         best = rn;
         if (rn < 1e-15 || pass == q->o->qp_refine_iter) break;
         /* dlam = S^-1 (Aw Hinv r1 - r2);  dx = Hinv (r1 - Aw' dlam) */
@@ -629,6 +632,17 @@ static int eqp_solve(qp_inst* q, const int* W)
             for (int k = M->Ap[i]; k < M->Ap[i + 1]; k++) q->t2[M->Aj[k]] -= M->Ax[k] * q->dl[a];
         }
         matvec(M->Hinv, q->t2, q->dx, n, n);
+        if (slow) {
+            /* exact line search along dx (the rows of W are satisfied, dx moves inside them):
+             * tau = r1'dx / dx'P dx >= 1 */
+            matvec(M->P, q->dx, q->px, n, n);
+            double pd = 0, cd = 0;
+            for (int j = 0; j < n; j++) { pd += q->r1[j] * q->dx[j]; cd += q->px[j] * q->dx[j]; }
+            if (pd > 0.0) {
+                const double tau = (cd > 0.0 && pd < 1e12 * cd) ? pd / cd : 1e12;
+                if (tau > 1.0) for (int j = 0; j < n; j++) q->dx[j] *= tau;
+            }
+        }
         for (int j = 0; j < n; j++) x[j] += q->dx[j];
         for (int a = 0; a < nw; a++) lam[a] += q->dl[a];
     }
