@@ -591,7 +591,7 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
         plan = pmin;
         plan.tinv_in_smem = tinv_smem;
         plan.outer_in_smem = outer_smem;
-        plan.gl_doubles = (tinv_smem ? 0 : (size_t)d.cap * d.cap) + (outer_smem ? 0 : outer_doubles(d));
+        plan.gl_doubles = (tinv_smem ? 0 : tinv_gl_doubles(d)) + (outer_smem ? 0 : outer_doubles(d));
         plan.bytes = (per + 15) / 16 * 16;
         groups = G;
         a.cache_bytes = cache; a.cache_what = what;
@@ -735,7 +735,7 @@ static Dims qp_dims(int nV, int nCtot, int has_box)
     Dims d = make_dims(nV, 0, 0, has_box);
     d.nC = nCtot; d.mA = nCtot;
     d.m = d.mA + (has_box ? d.n : 0);
-    d.ldE = d.m < d.n ? d.m : d.n;
+    d.ldE = ((d.m < d.n ? d.m : d.n) + 1) & ~1;
     d.capE = d.ldE > 0 ? d.ldE : 1;
     d.cap = d.m < d.n + 8 ? d.m : d.n + 8;
     if (d.cap < 1) d.cap = 1;

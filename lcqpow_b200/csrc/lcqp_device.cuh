@@ -104,6 +104,28 @@ typedef SPtr<double> SVec;
 #define LCQ_ASSUME_GLOBAL(ptr) __builtin_assume(__isGlobal(ptr))
 #endif
 
+#ifndef LCQP_HOST_EMU
+// Explicit address-space accessors (inline PTX).  The hot loops address shared memory by 32-bit shared-window
+// addresses (LDS/STS, immediate offsets) and the L2-resident matrices by ld.global/st.global, instead of generic
+// 64-bit loads.  The asm statements are volatile (kept in program order among themselves and against the named
+// barriers, which clobber memory); the stores clobber memory.  A function that uses them reaches an array ONLY
+// through them between two barriers.
+LCQ_DEV unsigned saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+LCQ_DEV double lds64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
+LCQ_DEV void lds128(unsigned a, double& x, double& y) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a)); }
+LCQ_DEV int lds32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+LCQ_DEV unsigned ldsu16(unsigned a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
+LCQ_DEV void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+LCQ_DEV double ldg64(const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
+LCQ_DEV void ldg128(const double* p, double& x, double& y) { asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p)); }
+// volatile: ptxas keeps volatile loads in program order, i.e. a batch of them is ISSUED before the first use (it
+// otherwise sinks each load to its use when the enclosing function is large) -- that is what hides the L2 latency
+LCQ_DEV void ldg128v(const double* p, double& x, double& y) { asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p)); }
+LCQ_DEV void lds128v(unsigned a, double& x, double& y) { asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a)); }
+LCQ_DEV void stg64(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+LCQ_DEV void stg128(double* p, double x, double y) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory"); }
+#endif
+
 constexpr double kEPS = 2.221e-16;       // LCQPow Utilities::EPS (Utilities.hpp:350)
 constexpr double kQPInf = 1e20;          // Utilities::INFTY (Utilities.hpp:362)
 constexpr double kRhoMin = 1e-6;         // osqp constants.h:48
@@ -198,7 +220,7 @@ inline LCQ_HD Dims make_dims(int nV, int nC, int nComp, int has_box)
     Dims d;
     d.n = nV; d.nC = nC; d.nComp = nComp; d.mA = nC + 2 * nComp; d.has_box = has_box;
     d.m = d.mA + (has_box ? nV : 0);
-    d.ldE = d.m < d.n ? d.m : d.n;
+    d.ldE = ((d.m < d.n ? d.m : d.n) + 1) & ~1;   // even: the full-storage SEinv is read by 16-byte loads
     d.capE = d.ldE > 0 ? d.ldE : 1;
     d.cap = d.m < d.n + 8 ? d.m : d.n + 8;   // a linearly independent working set has at most n rows
     if (d.cap < 1) d.cap = 1;
@@ -418,9 +440,37 @@ LCQ_DEV void csr_mv(const int* __restrict__ rp, const unsigned short* __restrict
                     double scale, double* out, const int* iidx)
 {
 #ifndef LCQP_HOST_EMU
-    if (VS) { LCQ_ASSUME_SHARED(v); LCQ_ASSUME_SHARED(init); LCQ_ASSUME_SHARED(out); }
-    if (OS) { LCQ_ASSUME_SHARED(rp); LCQ_ASSUME_SHARED(ci); LCQ_ASSUME_SHARED(va); LCQ_ASSUME_SHARED(lrows); }
-    else { LCQ_ASSUME_GLOBAL(rp); LCQ_ASSUME_GLOBAL(ci); LCQ_ASSUME_GLOBAL(va); LCQ_ASSUME_GLOBAL(lrows); }
+    if (VS && OS) {
+        // everything but iidx lives in shared memory: 32-bit shared addresses, LDS/STS (same operation order
+        // as the generic loops below, so the results are bit-identical)
+        const unsigned rps = saddr(rp), cis = saddr(ci), vas = saddr(va), vs = saddr(v), is = saddr(init), os = saddr(out), lrs = saddr(lrows);
+        LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
+            const int k0 = lds32(rps + 4u * (unsigned)r), k1 = lds32(rps + 4u * (unsigned)r + 4u);
+            if (k1 - k0 > kLongRow) continue;
+            double s = 0;
+            unsigned ca = cis + 2u * (unsigned)k0, xa = vas + 8u * (unsigned)k0;
+            LCQ_LOOP for (int k = k0; k < k1; k++) { s += lds64(xa) * lds64(vs + 8u * ldsu16(ca)); ca += 2u; xa += 8u; }
+            const double i0 = has_init ? lds64(is + 8u * (unsigned)(iidx ? iidx[r] : r)) : 0.0;
+            sts64(os + 8u * (unsigned)r, i0 + scale * s);
+        }
+        LCQ_LOOP for (int a = LCQ_WARP; a < nlong; a += LCQ_NWARP) {
+            const int r = lds32(lrs + 4u * (unsigned)a);
+            const int k1 = lds32(rps + 4u * (unsigned)r + 4u);
+            double s0 = 0, s1 = 0;
+            int k = lds32(rps + 4u * (unsigned)r) + LCQ_LANE;
+            LCQ_LOOP for (; k + LCQ_LANES < k1; k += 2 * LCQ_LANES) {
+                s0 += lds64(vas + 8u * (unsigned)k) * lds64(vs + 8u * ldsu16(cis + 2u * (unsigned)k));
+                s1 += lds64(vas + 8u * (unsigned)(k + LCQ_LANES)) * lds64(vs + 8u * ldsu16(cis + 2u * (unsigned)(k + LCQ_LANES)));
+            }
+            if (k < k1) s0 += lds64(vas + 8u * (unsigned)k) * lds64(vs + 8u * ldsu16(cis + 2u * (unsigned)k));
+            const double s = warp_sum(s0 + s1);
+            if (LCQ_LANE == 0) {
+                const double i0 = has_init ? lds64(is + 8u * (unsigned)(iidx ? iidx[r] : r)) : 0.0;
+                sts64(os + 8u * (unsigned)r, i0 + scale * s);
+            }
+        }
+        return;
+    }
 #endif
 #define LCQ_INIT(r) (has_init ? init[iidx ? iidx[r] : (r)] : 0.0)
     LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
@@ -508,9 +558,18 @@ LCQ_DEV void csr_mv_rows(const int* __restrict__ rp, const unsigned short* __res
                          const int* idx, int na, const double* v, const double* sub, bool has_sub, double* out)
 {
 #ifndef LCQP_HOST_EMU
-    LCQ_ASSUME_SHARED(idx); LCQ_ASSUME_SHARED(v); LCQ_ASSUME_SHARED(sub); LCQ_ASSUME_SHARED(out);
-    if (OS) { LCQ_ASSUME_SHARED(rp); LCQ_ASSUME_SHARED(ci); LCQ_ASSUME_SHARED(va); }
-    else { LCQ_ASSUME_GLOBAL(rp); LCQ_ASSUME_GLOBAL(ci); LCQ_ASSUME_GLOBAL(va); }
+    if (OS) {
+        const unsigned rps = saddr(rp), cis = saddr(ci), vas = saddr(va), vs = saddr(v), ss = saddr(sub), os = saddr(out), xs = saddr(idx);
+        LCQ_LOOP for (int a = LCQ_TID; a < na; a += LCQ_NT) {
+            const int r = lds32(xs + 4u * (unsigned)a);
+            const int k0 = lds32(rps + 4u * (unsigned)r), k1 = lds32(rps + 4u * (unsigned)r + 4u);
+            double s = 0;
+            unsigned ca = cis + 2u * (unsigned)k0, xa = vas + 8u * (unsigned)k0;
+            LCQ_LOOP for (int k = k0; k < k1; k++) { s += lds64(xa) * lds64(vs + 8u * ldsu16(ca)); ca += 2u; xa += 8u; }
+            sts64(os + 8u * (unsigned)a, s - (has_sub ? lds64(ss + 8u * (unsigned)r) : 0.0));
+        }
+        return;
+    }
 #endif
     LCQ_LOOP for (int a = LCQ_TID; a < na; a += LCQ_NT) {
         const int r = idx[a];
@@ -577,7 +636,7 @@ LCQ_DEV size_t pidx(int a, int b) { return a >= b ? (size_t)a * (a + 1) / 2 + b 
 //     out[a] = y_a;   o2[sidx[a]] = y_a;   o3[sidx[a]] = y_a          (null pointers are skipped)
 // ld == 0: S is a packed lower triangle (shared memory);  ld > 0: full storage with leading dimension ld
 // (global memory / L2), exactly symmetric.  One non-inlined copy serves every call site.
-LCQ_DEVN void sym_apply(const double* __restrict__ S, int ld, int nw, const double* v, double sgn,
+LCQ_DEV void sym_apply(const double* __restrict__ S, int ld, int nw, const double* v, double sgn,
                         double* out, const int* sidx, double* o2, double* o3)
 {
 #define LCQ_EMIT(a, val)                                  \
@@ -597,50 +656,100 @@ LCQ_DEVN void sym_apply(const double* __restrict__ S, int ld, int nw, const doub
         LCQ_EMIT(a, s);
     }
 #else
-    // One thread per row, no cross-lane reduction.  S is symmetric, so row a is read as column a:
-    //   full storage: S[b*ld + a] -- consecutive threads read consecutive addresses (coalesced L2 sectors),
-    //                 eight loads in flight per thread;
-    //   packed      : b <= a walks the contiguous row a (the triangular offsets of 16 consecutive rows fall
-    //                 into 16 distinct 8-byte banks), b > a reads S(b,a) at T(b)+a (consecutive across threads).
-    LCQ_ASSUME_SHARED(v);
-    if (out) LCQ_ASSUME_SHARED(out);
-    if (o2) LCQ_ASSUME_SHARED(o2);
-    if (o3) LCQ_ASSUME_SHARED(o3);
+    // v, out, o2, o3 live in shared memory; sidx may be global (generic access).
+    const unsigned vs = saddr(v);
     if (ld) {
-        LCQ_ASSUME_GLOBAL(S);
-        LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            const double* col = S + a;
-            int b = 0;
-            LCQ_LOOP for (; b + 16 <= nw; b += 16) {
-                double m[16];
+        // Full storage in global memory (L2-resident), exactly symmetric, ld even and S 16-byte aligned: row a is
+        // read as column a.  A pair of adjacent lanes owns two adjacent columns (one 16-byte load per row) and
+        // splits the rows in two halves; sixteen loads (32 values) are in flight per thread.  The two half sums
+        // are exchanged by one shuffle; lane h of the pair emits column 2c + h.
+        // (the first half has an even number of rows, so that both halves of v are 16-byte aligned)
+        const int npair = (nw + 1) >> 1;
+        int half = (((nw + 1) >> 1) + 1) & ~1;
+        if (half > nw) half = nw;
+        LCQ_LOOP for (int t0 = 0; t0 < 2 * npair; t0 += LCQ_NT) {
+            const int t = t0 + LCQ_TID;
+            const bool act = t < 2 * npair;
+            const int c = t >> 1, h = t & 1;
+            int b = act ? (h ? half : 0) : 0;
+            const int b1 = act ? (h ? nw : half) : 0;
+            const double* p = S + (size_t)((unsigned)b * (unsigned)ld + 2u * (unsigned)c);
+            unsigned va = vs + 8u * (unsigned)b;
+            double x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+            const unsigned ldu = (unsigned)ld;
+            LCQ_LOOP for (; b + 12 <= b1; b += 12) {
+                double m0[12], m1[12];
 #pragma unroll
-                for (int k = 0; k < 16; k++) m[k] = col[(size_t)(b + k) * ld];
+                for (int k = 0; k < 12; k++) { ldg128v(p, m0[k], m1[k]); p += ldu; }
 #pragma unroll
-                for (int k = 0; k < 16; k += 4) {
-                    s0 += m[k] * v[b + k]; s1 += m[k + 1] * v[b + k + 1]; s2 += m[k + 2] * v[b + k + 2]; s3 += m[k + 3] * v[b + k + 3];
+                for (int k = 0; k < 12; k += 2) {
+                    double v0, v1;
+                    lds128v(va + 8u * k, v0, v1);
+                    x0 += m0[k] * v0; y0 += m1[k] * v0;
+                    x1 += m0[k + 1] * v1; y1 += m1[k + 1] * v1;
                 }
+                va += 96u;
             }
-            LCQ_LOOP for (; b + 4 <= nw; b += 4) {
-                const double m0 = col[(size_t)b * ld], m1 = col[(size_t)(b + 1) * ld], m2 = col[(size_t)(b + 2) * ld], m3 = col[(size_t)(b + 3) * ld];
-                s0 += m0 * v[b]; s1 += m1 * v[b + 1]; s2 += m2 * v[b + 2]; s3 += m3 * v[b + 3];
+            LCQ_LOOP for (; b + 4 <= b1; b += 4) {
+                double m0[4], m1[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { ldg128v(p, m0[k], m1[k]); p += ldu; }
+#pragma unroll
+                for (int k = 0; k < 4; k += 2) {
+                    double v0, v1;
+                    lds128(va + 8u * k, v0, v1);
+                    x0 += m0[k] * v0; y0 += m1[k] * v0;
+                    x1 += m0[k + 1] * v1; y1 += m1[k + 1] * v1;
+                }
+                va += 32u;
             }
-            LCQ_LOOP for (; b < nw; b++) s0 += col[(size_t)b * ld] * v[b];
-            LCQ_EMIT(a, (s0 + s1) + (s2 + s3));
+            LCQ_LOOP for (; b + 2 <= b1; b += 2) {
+                double m00, m10, m01, m11, v0, v1;
+                ldg128v(p, m00, m10); p += ldu;
+                ldg128v(p, m01, m11); p += ldu;
+                lds128(va, v0, v1);
+                va += 16u;
+                x0 += m00 * v0; y0 += m10 * v0;
+                x1 += m01 * v1; y1 += m11 * v1;
+            }
+            LCQ_LOOP for (; b < b1; b++) {
+                double m0, m1;
+                ldg128(p, m0, m1);
+                p += ldu;
+                const double v0 = lds64(va);
+                va += 8u;
+                x0 += m0 * v0; y0 += m1 * v0;
+            }
+            double sa = x0 + x1, sb = y0 + y1;
+            sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+            sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+            const int a = 2 * c + h;
+            if (act && a < nw) LCQ_EMIT(a, h ? sb : sa);
         }
     } else {
-        LCQ_ASSUME_SHARED(S);
+        // Packed lower triangle in shared memory, one thread per row: b <= a walks the contiguous row a (the
+        // triangular offsets of 16 consecutive rows fall into 16 distinct 8-byte banks), b > a reads S(b,a) at
+        // T(b)+a (consecutive across threads).
+        const unsigned Ss = saddr(S);
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            const double* row = S + (size_t)a * (a + 1) / 2;
+            unsigned row = Ss + 8u * (unsigned)(a * (a + 1) / 2);
+            unsigned va = vs;
             int b = 0;
             LCQ_LOOP for (; b + 4 <= a + 1; b += 4) {
-                s0 += row[b] * v[b]; s1 += row[b + 1] * v[b + 1]; s2 += row[b + 2] * v[b + 2]; s3 += row[b + 3] * v[b + 3];
+                const double r0 = lds64(row), r1 = lds64(row + 8u), r2 = lds64(row + 16u), r3 = lds64(row + 24u);
+                const double v0 = lds64(va), v1 = lds64(va + 8u), v2 = lds64(va + 16u), v3 = lds64(va + 24u);
+                s0 += r0 * v0; s1 += r1 * v1; s2 += r2 * v2; s3 += r3 * v3;
+                row += 32u; va += 32u;
             }
-            LCQ_LOOP for (; b <= a; b++) s0 += row[b] * v[b];
-            const double* q = S + (size_t)b * (b + 1) / 2 + a;   // S(b, a), b = a + 1
-            LCQ_LOOP for (; b + 2 <= nw; b += 2) { s1 += q[0] * v[b]; s2 += q[b + 1] * v[b + 1]; q += 2 * b + 3; }
-            if (b < nw) s3 += q[0] * v[b];
+            LCQ_LOOP for (; b <= a; b++) { s0 += lds64(row) * lds64(va); row += 8u; va += 8u; }
+            unsigned q = Ss + 8u * (unsigned)(b * (b + 1) / 2 + a);   // S(b, a), b = a + 1
+            LCQ_LOOP for (; b + 2 <= nw; b += 2) {
+                s1 += lds64(q) * lds64(va);
+                s2 += lds64(q + 8u * (unsigned)(b + 1)) * lds64(va + 8u);
+                q += 8u * (unsigned)(2 * b + 3); va += 16u;
+            }
+            if (b < nw) s3 += lds64(q) * lds64(va);
             LCQ_EMIT(a, (s0 + s1) + (s2 + s3));
         }
     }
@@ -1207,31 +1316,45 @@ LCQ_DEVN void guess_working_set(QP& s, signed char* W)
 LCQ_DEVN void rank1_update_full(double* __restrict__ S, int ld, int nw, const double* u, double c)
 {
 #ifndef LCQP_HOST_EMU
-    LCQ_ASSUME_GLOBAL(S);
-    LCQ_ASSUME_SHARED(u);
-    // a warp takes two rows at a time and four 32-column chunks of each: eight elements in flight per thread
-    LCQ_LOOP for (int a0 = LCQ_WARP; a0 < nw; a0 += 2 * LCQ_NWARP) {
-        const int a1 = a0 + LCQ_NWARP;
-        const bool two = a1 < nw;
-        const double u0 = u[a0], u1 = two ? u[a1] : 0.0;
-        double* r0 = S + (size_t)a0 * ld;
-        double* r1 = S + (size_t)(two ? a1 : a0) * ld;
-        LCQ_LOOP for (int b0 = LCQ_LANE; b0 < nw; b0 += 4 * LCQ_LANES) {
-            double m0[4], m1[4], ub[4];
+    // ld even, S 16-byte aligned, u in shared memory (16-byte aligned).  A warp takes four rows at a time, a lane
+    // two adjacent columns of each (16-byte loads/stores): all loads of a row block are issued before the stores.
+    const unsigned us = saddr(u);
+    const int nchunk = (nw + 63) >> 6;
+    LCQ_LOOP for (int a0 = LCQ_WARP; a0 < nw; a0 += 4 * LCQ_NWARP) {
+        double ua[4];
+        double* row[4];
+        bool ok[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int b = b0 + k * LCQ_LANES;
-                const bool in = b < nw;
-                ub[k] = in ? u[b] : 0.0;
-                m0[k] = in ? r0[b] : 0.0;
-                m1[k] = (in && two) ? r1[b] : 0.0;
+        for (int r = 0; r < 4; r++) {
+            const int a = a0 + r * LCQ_NWARP;
+            ok[r] = a < nw;
+            ua[r] = ok[r] ? lds64(us + 8u * (unsigned)a) : 0.0;
+            row[r] = S + (size_t)((unsigned)(ok[r] ? a : a0) * (unsigned)ld);
+        }
+        LCQ_LOOP for (int cb = 0; cb < nchunk; cb += 2) {
+            double m0[2][4], m1[2][4], u0[2], u1[2];
+            int col[2];
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                col[q] = 64 * (cb + q) + 2 * LCQ_LANE;
+                if (col[q] < nw) {
+                    lds128(us + 8u * (unsigned)col[q], u0[q], u1[q]);
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (ok[r]) ldg128(row[r] + col[q], m0[q][r], m1[q][r]);
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int b = b0 + k * LCQ_LANES;
-                if (b < nw) {
-                    r0[b] = m0[k] + (u0 * ub[k]) * c;
-                    if (two) r1[b] = m1[k] + (u1 * ub[k]) * c;
+            for (int q = 0; q < 2; q++) {
+                if (col[q] < nw) {
+                    const bool two = col[q] + 1 < nw;
+#pragma unroll
+                    for (int r = 0; r < 4; r++)
+                        if (ok[r]) {
+                            // (column nw of an odd block is not part of the matrix: the caller may be writing it)
+                            if (two) stg128(row[r] + col[q], m0[q][r] + (ua[r] * u0[q]) * c, m1[q][r] + (ua[r] * u1[q]) * c);
+                            else stg64(row[r] + col[q], m0[q][r] + (ua[r] * u0[q]) * c);
+                        }
                 }
             }
         }
@@ -2032,9 +2155,14 @@ struct SmemPlan {
     size_t gl_doubles;   // doubles of global scratch per CTA for what did not fit
 };
 
-inline LCQ_HD size_t qp_doubles(const Dims& d) { return 7ull * d.n + 10ull * d.m + 2ull * d.cap + 2ull * d.capE + d.m /*ys*/; }
-inline LCQ_HD size_t outer_doubles(const Dims& d) { return 7ull * d.n + 2ull * d.nComp; }
-inline LCQ_HD size_t tinv_doubles(const Dims& d) { return (size_t)d.cap * (d.cap + 1) / 2; }
+// every vector starts on a 16-byte boundary (vector loads): lengths are rounded up to even
+inline LCQ_HD size_t ev(size_t k) { return (k + 1) & ~(size_t)1; }
+inline LCQ_HD size_t qp_doubles(const Dims& d) { return 7ull * ev(d.n) + 10ull * ev(d.m) + 2ull * ev(d.cap) + 2ull * ev(d.capE) + ev(d.m) /*ys*/; }
+inline LCQ_HD size_t outer_doubles(const Dims& d) { return 7ull * ev(d.n) + 2ull * ev(d.nComp); }
+inline LCQ_HD size_t tinv_doubles(const Dims& d) { return ev((size_t)d.cap * (d.cap + 1) / 2); }
+// working-set inverse in global memory: full storage, even leading dimension (16-byte loads of column pairs)
+inline LCQ_HD int tinv_ld(const Dims& d) { return (d.cap + 1) & ~1; }
+inline LCQ_HD size_t tinv_gl_doubles(const Dims& d) { return (size_t)d.cap * tinv_ld(d); }
 inline LCQ_HD size_t misc_bytes(const Dims& d)
 {
     return (size_t)d.cap * sizeof(int) + 5ull * ((d.m + 15) / 16) * 16 + sizeof(Scalars) + 64;
@@ -2047,7 +2175,7 @@ inline LCQ_HD SmemPlan make_plan(const Dims& d, size_t budget, bool tinv_global 
     size_t b = qp_doubles(d) * sizeof(double) + misc_bytes(d);
     p.gl_doubles = 0;
     p.tinv_in_smem = !tinv_global && (b + tinv_doubles(d) * sizeof(double) <= budget);
-    if (p.tinv_in_smem) b += tinv_doubles(d) * sizeof(double); else p.gl_doubles += (size_t)d.cap * d.cap;
+    if (p.tinv_in_smem) b += tinv_doubles(d) * sizeof(double); else p.gl_doubles += tinv_gl_doubles(d);
     p.outer_in_smem = (b + outer_doubles(d) * sizeof(double) <= budget);
     if (p.outer_in_smem) b += outer_doubles(d) * sizeof(double); else p.gl_doubles += outer_doubles(d);
     p.bytes = b;
@@ -2057,8 +2185,8 @@ inline LCQ_HD SmemPlan make_plan(const Dims& d, size_t budget, bool tinv_global 
 LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* base, double* gl)
 {
     double* q = reinterpret_cast<double*>(base);
-    auto take = [&](size_t k) { double* r = q; q += k; return r; };
-    auto takeg = [&](size_t k) { double* r = gl; gl += k; return r; };
+    auto take = [&](size_t k) { double* r = q; q += ev(k); return r; };
+    auto takeg = [&](size_t k) { double* r = gl; gl += ev(k); return r; };
     const int n = d.n, m = d.m;
     w.q = take(n); w.x = take(n); w.xa = take(n); w.r1 = take(n); w.u = take(n); w.t = take(n); w.dx = take(n);
     w.px = w.t;   // q + P x lives only inside kkt_residual, t only inside kkt_solve / admm_iter
@@ -2068,8 +2196,8 @@ LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* bas
     w.dI = take(d.cap); w.lI = take(d.cap);
     w.cE = take(d.capE); w.vE = take(d.capE);
     w.ys = take(m);
-    w.Tinv = p.tinv_in_smem ? take(tinv_doubles(d)) : takeg((size_t)d.cap * d.cap);
-    w.tld = p.tinv_in_smem ? 0 : d.cap;
+    w.Tinv = p.tinv_in_smem ? take(tinv_doubles(d)) : takeg(tinv_gl_doubles(d));
+    w.tld = p.tinv_in_smem ? 0 : tinv_ld(d);
     auto tk = [&](size_t k) { return p.outer_in_smem ? take(k) : takeg(k); };
     w.xk = tk(n); w.pk = tk(n); w.gk = tk(n); w.gt = tk(n); w.gphi = tk(n); w.stat = tk(n); w.tn = tk(n);
     w.Lx = tk(d.nComp); w.Rx = tk(d.nComp);
@@ -2086,24 +2214,25 @@ LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* bas
 inline LCQ_HD size_t mats_doubles(const Dims& d)
 {
     const size_t n = d.n, m = d.m;
-    return 3 * n * n + 2 * m * n + n + m + m * m + (size_t)d.ldE * d.ldE + (size_t)d.ldE * n + (m + 1) / 2 /*eidx*/ + (m + 7) / 8 /*ctype*/ + 2;
+    return 3 * ev(n * n) + 2 * ev(m * n) + ev(n) + ev(m) + ev(m * m) + ev((size_t)d.ldE * d.ldE) + ev((size_t)d.ldE * n) + ev((m + 1) / 2) /*eidx*/ + ev((m + 7) / 8) /*ctype*/ + 2;
 }
 
+// every block starts on a 16-byte boundary (the store itself comes from cudaMalloc / an even offset)
 LCQ_DEV void carve_mats(Mats& mt, double* base, const Dims& d)
 {
     const int mEcap = d.ldE;
     const size_t n = d.n, m = d.m;
-    mt.P = base; base += n * n;
-    mt.A = base; base += m * n;
-    mt.D = base; base += n;
-    mt.E = base; base += m;
-    mt.Hinv = base; base += n * n;
-    mt.AH = base; base += m * n;
-    mt.T = base; base += m * m;
-    mt.Minv = base; base += n * n;
-    mt.SEinv = base; base += (size_t)mEcap * mEcap;
-    mt.AHE = base; base += (size_t)mEcap * n;
-    mt.eidx = reinterpret_cast<int*>(base); base += (m + 1) / 2;
+    mt.P = base; base += ev(n * n);
+    mt.A = base; base += ev(m * n);
+    mt.D = base; base += ev(n);
+    mt.E = base; base += ev(m);
+    mt.Hinv = base; base += ev(n * n);
+    mt.AH = base; base += ev(m * n);
+    mt.T = base; base += ev(m * m);
+    mt.Minv = base; base += ev(n * n);
+    mt.SEinv = base; base += ev((size_t)mEcap * mEcap);
+    mt.AHE = base; base += ev((size_t)mEcap * n);
+    mt.eidx = reinterpret_cast<int*>(base); base += ev((m + 1) / 2);
     mt.ctype = reinterpret_cast<signed char*>(base);
     mt.SEinvP = nullptr;
     mt.mE = 0; mt.status = 0; mt.cache_bytes_se = 0; mt.cache_bytes_hot = 0; mt.cache_bytes_raw = 0;
