@@ -72,7 +72,8 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
         else:
             raise RuntimeError(f"{LIB_PATH} is missing: run `python -m lcqpow_b200.build` (the CUDA library is the "
                                "only implementation; there is no CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    # LCQP_CUDA_LIB: development aid (e.g. the -DLCQP_PROFILE build of the same sources)
+    lib = C.CDLL(os.environ.get("LCQP_CUDA_LIB", LIB_PATH))
     dp = C.POINTER(C.c_double)
     vp = C.c_void_p
     lib.lcqp_cuda_abi_version.restype = C.c_int

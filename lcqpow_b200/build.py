@@ -20,7 +20,7 @@ DEPS = SOURCES + [os.path.join(CSRC, "lcqp_device.cuh"), os.path.join(HERE, ".."
 # them nvcc 12.9 miscompiles the solver for sm_100a (garbage return values of the non-inlined device functions;
 # seen on the B200, gpurun_out/dbg1.log vs dbg2.log of round 1).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-              "-DLCQP_NO_ASSUME", "-diag-suppress", "20054", "-shared", "-Xcompiler", "-fPIC"]
+              "-DLCQP_NO_ASSUME", "-diag-suppress", "20054", "-diag-suppress", "128", "-shared", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc() -> str:

@@ -13,9 +13,13 @@
 
 namespace lcqp {
 
+#ifdef LCQP_PROFILE
+__device__ unsigned long long g_prof[16];
+#endif
+
 constexpr int kThreads = 256;           // plugin-door CTA (one group)
 constexpr int kMaxCtaThreads = 512;     // solver CTA: groups x threads per group (128 registers per thread)
-constexpr int kMaxGroups = 8;           // groups (instances in flight) per solver CTA
+constexpr int kMaxGroups = 4;           // groups (instances in flight) per solver CTA
 constexpr int kPrepThreads = 1024;      // batch-level preparation CTA
 constexpr size_t kSmemMax = 227 * 1024; // opt-in dynamic shared memory per CTA on sm_100
 
@@ -149,10 +153,17 @@ __global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_solve_kernel(const __g
             if (threadIdx.x == 0) raw_dense_ops(a.d, in, ro, a.shared_mask);
             LCQ_SYNC();
         }
+#ifdef LCQP_PROFILE
+        if (threadIdx.x == 0) { for (int k = 0; k < 16; k++) wk.sc->prof[k] = 0; wk.sc->prof_last = clock64(); wk.sc->prof_cur = 13; }
+#endif
         LoopOut out;
         double* xo = a.xout + (size_t)b * a.d.n;
         double* yo = a.yout + (size_t)b * nD;
         run_instance(s, mt, a.mats_shared != 0, in, ro, a.instance_offset + (unsigned long long)b, xo, yo, out);
+#ifdef LCQP_PROFILE
+        LCQ_PROF(wk.sc, 13);
+        if (threadIdx.x == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_prof[k], (unsigned long long)wk.sc->prof[k]);
+#endif
         if (threadIdx.x == 0) {
             lcqp_cuda_stats st;
             st.ret = out.ret; st.status = out.status; st.iterTotal = out.iterTotal; st.iterOuter = out.iterOuter;
@@ -629,6 +640,20 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
+#ifdef LCQP_PROFILE
+    if (getenv("LCQP_CUDA_VERBOSE")) {
+        cudaStreamSynchronize(stream);
+        unsigned long long pr[16];
+        cudaMemcpyFromSymbol(pr, g_prof, sizeof(pr));
+        unsigned long long z[16] = {};
+        cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+        double tot = 0;
+        for (int k = 0; k < 16; k++) tot += (double)pr[k];
+        static const char* nm[16] = {"kkt_residual", "kkt1 K^-1", "kkt2 rows+Tinv", "kkt3 At+K^-1", "linesearch", "ratio", "tinv_append", "as misc/update", "kkt_check", "tinv_remove", "admm", "outer", "qp misc", "setup/out", "res: oP+oA", "res: oAt"};
+        fprintf(stderr, "lcqp_cuda profile (group cycles per LCQP, %% of total):\n");
+        for (int k = 0; k < 16; k++) fprintf(stderr, "   %-16s %12.0f  %5.1f%%\n", nm[k], (double)pr[k] / h->batch, 100.0 * pr[k] / (tot > 0 ? tot : 1));
+    }
+#endif
     h->last_stream = stream;
     h->last_grid = grid * groups;
     h->last_smem = (int)smem;
