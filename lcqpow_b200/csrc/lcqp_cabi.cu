@@ -115,15 +115,15 @@ __global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_solve_kernel(const __g
     __shared__ Dims dm;
     __shared__ lcqp_cuda_options opt;
     const int g = threadIdx.y, G = blockDim.y;
+    __shared__ QP qp_s[kMaxGroups];
     Mats& mt = mt_s[g];
     RawOps& ro = ro_s[g];
     Work& wk = wk_s[g];
-    QP s;
-    s.d = &dm;
-    s.o = &opt;
-    s.w = &wk;
+    QP& s = qp_s[g];
     double* ws = a.workspace + a.ws_stride * ((unsigned long long)blockIdx.x * G + g);
     if (threadIdx.x == 0) {
+        s.d = &dm; s.o = &opt; s.w = &wk; s.mt = &mt;
+        s.nw = 0; s.have_W = 0; s.tinv_valid = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
         if (g == 0) { dm = a.d; opt = a.o; }
         carve(wk, a.d, a.plan, smem + (size_t)g * a.group_bytes, ws + a.ws_mats_doubles);
         if (a.mats_shared) mt = *a.shared_mats;
@@ -205,24 +205,22 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
     __shared__ Work wk;
     __shared__ Dims dm;
     __shared__ lcqp_cuda_options opt;
-    QP s;
-    s.d = &dm;
-    s.o = &opt;
-    s.w = &wk;
-    if (threadIdx.x == 0) { dm = a.d; opt = a.o; carve(wk, a.d, a.plan, smem, a.gl); }
+    __shared__ QP s;
+    if (threadIdx.x == 0) {
+        dm = a.d; opt = a.o; carve(wk, a.d, a.plan, smem, a.gl);
+        s.d = &dm; s.o = &opt; s.w = &wk; s.mt = &mt;
+        s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
+    }
     __syncthreads();
-    s.ph = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
     if (!a.initial) {
         for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
             reinterpret_cast<double*>(smem)[k] = reinterpret_cast<const double*>(a.saved_smem)[k];
-        s.nw = a.state->nw; s.have_W = a.state->have_W; s.tinv_valid = a.state->tinv_valid;
-        if (threadIdx.x == 0) mt = *a.mats;
+        if (threadIdx.x == 0) { s.nw = a.state->nw; s.have_W = a.state->have_W; s.tinv_valid = a.state->tinv_valid; mt = *a.mats; }
     } else {
-        s.nw = 0; s.have_W = 0; s.tinv_valid = 0;
-        if (threadIdx.x == 0) { carve_mats(mt, a.mats_store, a.d); mats_dense_ops(a.d, mt); }
+        if (threadIdx.x == 0) { s.nw = 0; s.have_W = 0; s.tinv_valid = 0; carve_mats(mt, a.mats_store, a.d); mats_dense_ops(a.d, mt); }
     }
+    if (threadIdx.x < 8) wk.sc->wph[threadIdx.x] = 0;
     __syncthreads();
-    s.mt = &mt;
     int infeasible = a.initial ? 0 : a.state->infeasible;
     int flag = 0, iters = 0;
     if (a.initial) {
@@ -577,6 +575,8 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     if (const char* t = getenv("LCQP_CUDA_TINV")) tinv_pref = (t[0] == 's') ? 1 : (t[0] == 'l' ? 0 : -1);
     int cache_allow = 7;
     if (const char* t = getenv("LCQP_CUDA_CACHE")) cache_allow = atoi(t) & 7;
+    bool use_ell = true;   // ELL form of the cached inner-pass operators (LCQP_CUDA_ELL=0: CSR)
+    if (const char* t = getenv("LCQP_CUDA_ELL")) use_ell = atoi(t) != 0;
     cudaFuncAttributes fattr;
     CK(cudaFuncGetAttributes(&fattr, lcqp_solve_kernel), LCQP_CUDA_LAUNCH_FAILED);
     const size_t budget = kSmemMax - fattr.sharedSizeBytes;   // static shared memory: the descriptors of the groups
@@ -605,7 +605,7 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
         plan.gl_doubles = (tinv_smem ? 0 : tinv_gl_doubles(d)) + (outer_smem ? 0 : outer_doubles(d));
         plan.bytes = (per + 15) / 16 * 16;
         groups = G;
-        a.cache_bytes = cache; a.cache_what = what;
+        a.cache_bytes = cache; a.cache_what = what | (use_ell ? 8 : 0);
     }
     if (!groups) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
     a.plan = plan;

@@ -74,6 +74,18 @@
 
 #include "../../include/lcqp_cuda.h"
 
+// inlining of the two dense kernels (code size vs. register allocation)
+#ifdef LCQP_SYM_NOINLINE
+#define LCQ_SYM_INL LCQ_DEVN
+#else
+#define LCQ_SYM_INL LCQ_DEV
+#endif
+#ifdef LCQP_R1_INLINE
+#define LCQ_R1_INL LCQ_DEV
+#else
+#define LCQ_R1_INL LCQ_DEVN
+#endif
+
 namespace lcqp {
 
 // Pointer into the CTA's shared memory.  The accessors tell the compiler the address space
@@ -257,6 +269,7 @@ struct Scalars {
     int bidx;
     int flag;
     int pad[2];
+    int wph[8];   // per-warp phase of the single-barrier reductions (lane 0 toggles it after the barrier)
 #ifdef LCQP_PROFILE
     long long prof[16];   // cycles per section (thread 0 of the group), see LCQ_PROF
     long long prof_last;
@@ -398,27 +411,29 @@ LCQ_DEV int block_argmax(double v, int i, double* vout, Scalars* sc)
 // The partials go to one of two buffers, alternating from call to call (`ph` is a per-thread copy of the
 // same counter): the barrier of call k+1 separates the reads of call k from the writes of call k+2.
 // Only for CTAs of at most 8 warps.
-LCQ_DEV double fast_max(double v, Scalars* sc, int& ph)
+LCQ_DEV double fast_max(double v, Scalars* sc)
 {
     v = warp_max(v);
+    const int ph = sc->wph[LCQ_WARP];
     double* buf = sc->fred[ph][0];
-    ph ^= 1;
     if (LCQ_LANE == 0) buf[LCQ_WARP] = v;
     LCQ_SYNC();
+    if (LCQ_LANE == 0) sc->wph[LCQ_WARP] = ph ^ 1;
     double r = buf[0];
     LCQ_LOOP for (int k = 1; k < LCQ_NWARP; k++) r = fmax(r, buf[k]);
     return r;
 }
 
-LCQ_DEV void fast_sum2(double& a, double& b, Scalars* sc, int& ph)
+LCQ_DEV void fast_sum2(double& a, double& b, Scalars* sc)
 {
     a = warp_sum(a);
     b = warp_sum(b);
+    const int ph = sc->wph[LCQ_WARP];
     double* b0 = sc->fred[ph][0];
     double* b1 = sc->fred[ph][1];
-    ph ^= 1;
     if (LCQ_LANE == 0) { b0[LCQ_WARP] = a; b1[LCQ_WARP] = b; }
     LCQ_SYNC();
+    if (LCQ_LANE == 0) sc->wph[LCQ_WARP] = ph ^ 1;
     double x = 0, y = 0;
     LCQ_LOOP for (int k = 0; k < LCQ_NWARP; k++) { x += b0[k]; y += b1[k]; }
     a = x; b = y;
@@ -434,7 +449,7 @@ LCQ_DEV bool lex_better(double a, double wgt, int i, double a2, double w2, int i
     return i2 < i;
 }
 
-LCQ_DEV int fast_argmin_lex(double a, double wgt, int i, double* aout, Scalars* sc, int& ph)
+LCQ_DEV int fast_argmin_lex(double a, double wgt, int i, double* aout, Scalars* sc)
 {
 #ifndef LCQP_HOST_EMU
     for (int o = 16; o > 0; o >>= 1) {
@@ -444,12 +459,13 @@ LCQ_DEV int fast_argmin_lex(double a, double wgt, int i, double* aout, Scalars* 
         if (lex_better(a, wgt, i, a2, w2, i2)) { a = a2; wgt = w2; i = i2; }
     }
 #endif
+    const int ph = sc->wph[LCQ_WARP];
     double* ba = sc->fred[ph][0];
     double* bw = sc->fred[ph][1];
     int* bi = sc->fired[ph];
-    ph ^= 1;
     if (LCQ_LANE == 0) { ba[LCQ_WARP] = a; bw[LCQ_WARP] = wgt; bi[LCQ_WARP] = i; }
     LCQ_SYNC();
+    if (LCQ_LANE == 0) sc->wph[LCQ_WARP] = ph ^ 1;
     double ra = ba[0], rw = bw[0];
     int ri = bi[0];
     LCQ_LOOP for (int k = 1; k < LCQ_NWARP; k++)
@@ -811,7 +827,7 @@ LCQ_DEV size_t pidx(int a, int b) { return a >= b ? (size_t)a * (a + 1) / 2 + b 
 //     out[a] = y_a;   o2[sidx[a]] = y_a;   o3[sidx[a]] = y_a          (null pointers are skipped)
 // ld == 0: S is a packed lower triangle (shared memory);  ld > 0: full storage with leading dimension ld
 // (global memory / L2), exactly symmetric.  One non-inlined copy serves every call site.
-LCQ_DEV void sym_apply(const double* __restrict__ S, int ld, int nw, const double* v, double sgn,
+LCQ_SYM_INL void sym_apply(const double* __restrict__ S, int ld, int nw, const double* v, double sgn,
                         double* out, const int* sidx, double* o2, double* o3)
 {
 #define LCQ_EMIT(a, val)                                  \
@@ -1468,8 +1484,13 @@ LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsign
     }
     if (what & 2) {
 #ifndef LCQP_HOST_EMU
+        if (!(what & 8)) {
+            cache_op(oA, cur, end); cache_op(oAt, cur, end); cache_op(oAHE, cur, end); cache_op(oAHtE, cur, end);
+            cache_op(oHinv, cur, end); cache_op(oP, cur, end);
+        } else {
         cache_op_ell(oA, cur, end); cache_op_ell(oAt, cur, end); cache_op_ell(oAHE, cur, end); cache_op_ell(oAHtE, cur, end);
         cache_op_ell(oHinv, cur, end); cache_op_ell(oP, cur, end);
+        }
 #else
         cache_op(oA, cur, end); cache_op(oAt, cur, end); cache_op(oAHE, cur, end); cache_op(oAHtE, cur, end);
         cache_op(oHinv, cur, end); cache_op(oP, cur, end);
@@ -1508,9 +1529,11 @@ LCQ_DEV void cache_requirements(Mats& mt, const RawOps& ro)
 // ------------------------------------------------------------------------------------------------
 // QP solver state machine
 // ------------------------------------------------------------------------------------------------
-// Per-thread view of the solver state.  Everything large or read-only (dimensions, the pointers of the
-// working set, the prepared operands) is block-shared and only POINTED to from here, so that the non-inlined
-// device functions find their operands in shared memory instead of a per-thread stack frame in L2.
+// State of the QP solver of one group.  It lives in SHARED memory (one per group): the non-inlined device
+// functions receive a reference to it, and a per-thread copy would sit in local memory, i.e. behind an L2 round
+// trip at every function entry (the L1 left beside 220 KB of shared memory does not hold the stacks of 512 threads).
+// All threads read it; thread 0 alone writes it, always with a group barrier between a write and the reads on
+// either side of it.
 struct QP {
     SPtr<const Dims> d;
     SPtr<const Mats> mt;
@@ -1519,7 +1542,7 @@ struct QP {
     int nw;           // rows in the inequality working set = order of Tinv (idx[0..nw))
     int have_W;
     int tinv_valid;   // Tinv matches idx/W
-    int ph;           // phase of the single-barrier reductions
+    int pad;
     long long n_admm, n_pass, n_changes;
 };
 
@@ -1570,49 +1593,38 @@ LCQ_DEVN void guess_working_set(QP& s, signed char* W)
 // S += c * u u' on the leading nw x nw block of a full-storage matrix in global memory (leading dimension ld).
 // (u_a u_b) c is commutative in a, b: S stays exactly symmetric.  Eight independent load -> update -> store
 // chains per thread, so that eight L2 round trips overlap instead of one.
-LCQ_DEV void rank1_update_full(double* __restrict__ S, int ld, int nw, const double* u, double c)
+LCQ_R1_INL void rank1_update_full(double* __restrict__ S, int ld, int nw, const double* u, double c)
 {
 #ifndef LCQP_HOST_EMU
-    // ld even, S 16-byte aligned, u in shared memory (16-byte aligned).  A warp takes four rows at a time, a lane
-    // two adjacent columns of each (16-byte loads/stores): all loads of a row block are issued before the stores.
+    // ld even, S 16-byte aligned, u in shared memory (16-byte aligned).  The nw x ceil(nw/2) pairs of adjacent
+    // columns are dealt out round-robin (element e -> row e / npair, pair e % npair: every thread gets the same
+    // share); BATCH 16-byte loads are issued (volatile: kept together by ptxas) before the first store.
+    constexpr int BATCH = 8;
     const unsigned us = saddr(u);
-    const int nchunk = (nw + 63) >> 6;
-    LCQ_LOOP for (int a0 = LCQ_WARP; a0 < nw; a0 += 4 * LCQ_NWARP) {
-        double ua[4];
-        double* row[4];
-        bool ok[4];
+    const int npair = (nw + 1) >> 1, total = nw * npair;
+    const int dq = LCQ_NT / npair, dr = LCQ_NT - dq * npair;   // (row, pair) advance per LCQ_NT elements
+    int row = LCQ_TID / npair, cp = LCQ_TID - row * npair;
+    LCQ_LOOP for (int e0 = LCQ_TID; e0 < total; e0 += BATCH * LCQ_NT) {
+        double m0[BATCH], m1[BATCH];
+        int key[BATCH];
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-            const int a = a0 + r * LCQ_NWARP;
-            ok[r] = a < nw;
-            ua[r] = ok[r] ? lds64(us + 8u * (unsigned)a) : 0.0;
-            row[r] = S + (size_t)((unsigned)(ok[r] ? a : a0) * (unsigned)ld);
+        for (int k = 0; k < BATCH; k++) {
+            key[k] = (e0 + k * LCQ_NT < total) ? ((row << 16) | cp) : -1;
+            ldg128v(S + (key[k] >= 0 ? (unsigned)(row * ld + 2 * cp) : 0u), m0[k], m1[k]);   // (unconditional: keeps m0/m1 in registers)
+            cp += dr; row += dq;
+            if (cp >= npair) { cp -= npair; row++; }
         }
-        LCQ_LOOP for (int cb = 0; cb < nchunk; cb += 2) {
-            double m0[2][4], m1[2][4], u0[2], u1[2];
-            int col[2];
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                col[q] = 64 * (cb + q) + 2 * LCQ_LANE;
-                if (col[q] < nw) {
-                    lds128(us + 8u * (unsigned)col[q], u0[q], u1[q]);
-#pragma unroll
-                    for (int r = 0; r < 4; r++)
-                        if (ok[r]) ldg128(row[r] + col[q], m0[q][r], m1[q][r]);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                if (col[q] < nw) {
-                    const bool two = col[q] + 1 < nw;
-#pragma unroll
-                    for (int r = 0; r < 4; r++)
-                        if (ok[r]) {
-                            // (column nw of an odd block is not part of the matrix: the caller may be writing it)
-                            if (two) stg128(row[r] + col[q], m0[q][r] + (ua[r] * u0[q]) * c, m1[q][r] + (ua[r] * u1[q]) * c);
-                            else stg64(row[r] + col[q], m0[q][r] + (ua[r] * u0[q]) * c);
-                        }
-                }
+        for (int k = 0; k < BATCH; k++) {
+            if (key[k] >= 0) {
+                const int r = key[k] >> 16, c2 = key[k] & 0xffff;
+                const double ua = lds64(us + 8u * (unsigned)r);
+                double u0, u1;
+                lds128(us + 16u * (unsigned)c2, u0, u1);
+                double* q = S + (unsigned)(r * ld + 2 * c2);
+                // (column nw of an odd block is not part of the matrix: the caller may be writing it)
+                if (2 * c2 + 1 < nw) stg128(q, m0[k] + (ua * u0) * c, m1[k] + (ua * u1) * c);
+                else stg64(q, m0[k] + (ua * u0) * c);
             }
         }
     }
@@ -1639,7 +1651,7 @@ LCQ_DEVN int tinv_append(QP& s, int j)
     LCQ_SYNC();
     double p1 = 0, p2 = 0;
     LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) { const double v = w.lI[a]; p1 += w.dI[a] * v; p2 += v * v; }
-    fast_sum2(p1, p2, w.sc, s.ph);
+    fast_sum2(p1, p2, w.sc);
     const double kappa = Tj[j] + s.o->qp_delta - p1;
     if (!(kappa > 10.0 * s.o->qp_delta * (1.0 + p2))) return 1;
     const double ik = 1.0 / kappa;
@@ -1659,7 +1671,7 @@ LCQ_DEVN int tinv_append(QP& s, int j)
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
         if (LCQ_TID == 0) { row[nw] = ik; w.idx[nw] = j; }
     }
-    s.nw = nw + 1;
+    if (LCQ_TID == 0) s.nw = nw + 1;
     LCQ_SYNC();
     return 0;
 }
@@ -1693,7 +1705,7 @@ LCQ_DEVN void tinv_remove(QP& s, int p)
         }
         if (LCQ_TID == 0) w.idx[p] = w.idx[last];
     }
-    s.nw = last;
+    if (LCQ_TID == 0) s.nw = last;
     LCQ_SYNC();
 }
 
@@ -1702,8 +1714,8 @@ LCQ_DEVN void tinv_remove(QP& s, int p)
 LCQ_DEVN void tinv_build(QP& s, signed char* W)
 {
     const int m = s.d->m;
-    s.nw = 0;
-    s.tinv_valid = 0;
+    LCQ_SYNC();
+    if (LCQ_TID == 0) { s.nw = 0; s.tinv_valid = 0; }
     LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT)
         if (s.w->ctype[i] >= 1) W[i] = (s.w->ctype[i] == 1) ? 1 : 0;
     LCQ_SYNC();
@@ -1718,7 +1730,9 @@ LCQ_DEVN void tinv_build(QP& s, signed char* W)
             LCQ_SYNC();
         }
     }
-    s.tinv_valid = 1;
+    LCQ_SYNC();
+    if (LCQ_TID == 0) s.tinv_valid = 1;
+    LCQ_SYNC();
 }
 
 // Solve the regularised KKT system of the working set,
@@ -1801,7 +1815,7 @@ LCQ_DEVN double kkt_residual(QP& s, const signed char* W, const double* x, const
         w.r1[j] = r;
         rn = fmax(rn, fabs(r));
     }
-    return fast_max(rn, w.sc, s.ph);
+    return fast_max(rn, w.sc);
 }
 
 // KKT conditions of the full QP at (x, lam) with zx, r1 as left by kkt_residual.  0 = satisfied;
@@ -1865,7 +1879,7 @@ LCQ_DEVN void accept_solution(QP& s, const signed char* W)
         w.z[i] = w.zx[i];
     }
     LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.x[j] = w.xa[j];
-    s.have_W = 1;
+    if (LCQ_TID == 0) s.have_W = 1;
     LCQ_SYNC();
 }
 
@@ -1943,7 +1957,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                 if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d drop row %d (reason %d) rn=%.3e\n", it, s.nw, row, reason, rn);
 #endif
                 last_dropped = row;
-                s.n_changes++;
+                if (LCQ_TID == 0) s.n_changes++;
                 best = INFINITY;
                 passes = 0;
                 dirty = true;
@@ -1955,7 +1969,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
 #endif
             return 1;  // EQP not solvable to tolerance on this set
         }
-        s.n_pass++;
+        if (LCQ_TID == 0) s.n_pass++;
         kkt_solve(s);   // r1, r2 -> dx, dlam
         LCQ_PROF(w.sc, 4);
         if (slow && ratio_test && !clean) {
@@ -1965,7 +1979,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             LCQ_SYNC();
             double pd = 0, cd = 0;
             LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) { pd += w.r1[j] * w.dx[j]; cd += w.px[j] * w.dx[j]; }
-            fast_sum2(pd, cd, w.sc, s.ph);
+            fast_sum2(pd, cd, w.sc);
             if (pd > 0.0) {
                 const double tau = (cd > 0.0 && pd < 1e12 * cd) ? pd / cd : 1e12;
                 if (tau > 1.0) LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.dx[j] *= tau;
@@ -1981,7 +1995,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             op_mv_s(mt.oA, w.dx, nullptr, 1.0, w.zp);
             LCQ_SYNC();
             LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) apn = fmax(apn, fabs(w.zp[i]));
-            apn = fast_max(apn, w.sc, s.ph);
+            apn = fast_max(apn, w.sc);
             const double seps = 1e-13 * (1.0 + apn);
             LCQ_LOOP for (;;) {
                 // the smallest step length; among the rows attaining it the largest |s|, then the smallest row
@@ -1997,7 +2011,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                     if (a < 1.0 && lex_better(ba, bs, bi, a, fabs(sv), i)) { ba = a; bs = fabs(sv); bi = i; }
                 }
                 double am;
-                block = fast_argmin_lex(ba, bs, bi, &am, w.sc, s.ph);
+                block = fast_argmin_lex(ba, bs, bi, &am, w.sc);
                 amin = block >= 0 ? am : 1.0;
                 if (block < 0) break;
                 if (s.nw >= s.d->cap) return 1;
@@ -2026,7 +2040,7 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             if (LCQ_TID == 0) { W[block] = side; if (block == last_dropped && amin * (1.0 + apn) <= 1e-12) w.pin[block] |= 1; }
             last_dropped = -1;
             LCQ_SYNC();
-            s.n_changes++;
+            if (LCQ_TID == 0) s.n_changes++;
 #ifdef LCQP_HOST_EMU
             if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d add row %d side %d alpha=%.3e rn=%.3e\n", it, s.nw, block, (int)side, amin, rn);
 #endif
@@ -2116,8 +2130,7 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
         }
         LCQ_SYNC();
         op_mv_s(mt.oA, w.x, nullptr, 1.0, w.z);
-        s.have_W = 0;
-        s.tinv_valid = 0;
+        if (LCQ_TID == 0) { s.have_W = 0; s.tinv_valid = 0; }
         LCQ_SYNC();
     } else if (s.have_W && s.tinv_valid) {
         // hot start: the previous working set is tried first (EQP from zero: the usual case late in the
@@ -2136,7 +2149,8 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
         }
         if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = (int)(s.n_changes - ch0); return 0; }
         // fall through to ADMM from the previous solution
-        s.tinv_valid = 0;
+        LCQ_SYNC();
+        if (LCQ_TID == 0) s.tinv_valid = 0;
         op_mv_s(mt.oA, w.x, nullptr, 1.0, w.z);
         LCQ_SYNC();
     }
@@ -2146,7 +2160,7 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
         LCQ_PROF(w.sc, 10);
         LCQ_LOOP for (int k = 0; k < o.qp_check_interval && it < o.qp_max_iter; k++, it++) admm_iter(s);
         LCQ_PROF(w.sc, 12);
-        s.n_admm += o.qp_check_interval;
+        if (LCQ_TID == 0) s.n_admm += o.qp_check_interval;
         guess_working_set(s, w.Wtry);
         if (have_fail) {
             int diff = 0;
@@ -2169,12 +2183,16 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
         if (reason == 5 || reason == 6) {
             // primal feasible EQP point with a wrong-signed multiplier: a valid active-set start
             if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = it + (int)(s.n_changes - ch0); return 0; }
-            s.tinv_valid = 0;
+            LCQ_SYNC();
+            if (LCQ_TID == 0) s.tinv_valid = 0;
+            LCQ_SYNC();
         } else if (project_feasible(s, w.Wtry, w.x)) {
             LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
             LCQ_SYNC();
             if (active_set(s, w.Wtry, true, nullptr) == 0) { *iterations = it + (int)(s.n_changes - ch0); return 0; }
-            s.tinv_valid = 0;
+            LCQ_SYNC();
+            if (LCQ_TID == 0) s.tinv_valid = 0;
+            LCQ_SYNC();
         }
     }
     *iterations = it + (int)(s.n_changes - ch0);
@@ -2529,8 +2547,10 @@ LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, co
     const Work& w = *s.w;
     const lcqp_cuda_options& o = *s.o;
     const int nD = d.n + d.mA;
-    s.mt = &mt;
-    s.nw = 0; s.have_W = 0; s.tinv_valid = 0; s.ph = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
+    LCQ_SYNC();
+    if (LCQ_TID == 0) { s.mt = &mt; s.nw = 0; s.have_W = 0; s.tinv_valid = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0; }
+    LCQ_LOOP for (int k = LCQ_TID; k < 8; k += LCQ_NT) w.sc->wph[k] = 0;
+    LCQ_SYNC();
     out.ret = 0; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
     bool skip = false;
     // initializeSolver checks (LCQProblem.cpp:930-957): the OSQP-style layout has no box constraints
