@@ -33,6 +33,7 @@ struct KernelArgs {
     int mats_shared;             // Q, L, R, A all shared: one preparation for the batch
     SmemPlan plan;
     unsigned long long group_bytes;      // dynamic shared memory of one group (its instance state)
+    unsigned long long bounds_offset;    // byte offset of the bounds shared by the groups (plan.bounds_shared), before the cache
     unsigned long long cache_offset;     // byte offset of the operator cache in dynamic shared memory (after the groups)
     unsigned long long cache_bytes;      // its size (0: operators stay in L2)
     int cache_what;                      // bit0 packed SEinv, bit1 inner-pass operators, bit2 outer-loop operators
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_solve_kernel(const __g
         s.d = &dm; s.o = &opt; s.w = &wk; s.mt = &mt;
         s.nw = 0; s.have_W = 0; s.tinv_valid = 0; s.n_admm = 0; s.n_pass = 0; s.n_changes = 0;
         if (g == 0) { dm = a.d; opt = a.o; }
-        carve(wk, a.d, a.plan, smem + (size_t)g * a.group_bytes, ws + a.ws_mats_doubles);
+        carve(wk, a.d, a.plan, smem + (size_t)g * a.group_bytes, ws + a.ws_mats_doubles,
+              a.plan.bounds_shared ? reinterpret_cast<double*>(smem + a.bounds_offset) : nullptr);
         if (a.mats_shared) mt = *a.shared_mats;
         else carve_mats(mt, ws, a.d);
         ro = *a.shared_raw;
@@ -575,8 +577,6 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     if (const char* t = getenv("LCQP_CUDA_TINV")) tinv_pref = (t[0] == 's') ? 1 : (t[0] == 'l' ? 0 : -1);
     int cache_allow = 7;
     if (const char* t = getenv("LCQP_CUDA_CACHE")) cache_allow = atoi(t) & 7;
-    bool use_ell = true;   // ELL form of the cached inner-pass operators (LCQP_CUDA_ELL=0: CSR)
-    if (const char* t = getenv("LCQP_CUDA_ELL")) use_ell = atoi(t) != 0;
     cudaFuncAttributes fattr;
     CK(cudaFuncGetAttributes(&fattr, lcqp_solve_kernel), LCQP_CUDA_LAUNCH_FAILED);
     const size_t budget = kSmemMax - fattr.sharedSizeBytes;   // static shared memory: the descriptors of the groups
@@ -584,33 +584,54 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     int groups = 0;
     a.cache_bytes = 0; a.cache_what = 0; a.cache_offset = 0;
     const SmemPlan pmin = make_plan(d, 0, true);   // the instance's QP vectors only
+    // Bounds that the whole batch shares (every bound array shared or absent, and shared scaling) scale to the
+    // same l / ub for every instance: the groups alias ONE copy (each group rewrites it with identical values).
+    const unsigned bound_bits = (1u << LCQP_LBL) | (1u << LCQP_UBL) | (1u << LCQP_LBR) | (1u << LCQP_UBR) | (1u << LCQP_LBA) | (1u << LCQP_UBA) | (1u << LCQP_LB) | (1u << LCQP_UB);
+    bool bounds_shared = can_cache;
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++)
+        if (((bound_bits >> k) & 1u) && h->dev_in[k] && !((a.shared_mask >> k) & 1u)) bounds_shared = false;
+    if (getenv("LCQP_CUDA_NO_SLIM")) bounds_shared = false;   // tuning aid
+    const size_t bnd_bytes = bounds_shared ? 2 * ev((size_t)d.m) * sizeof(double) : 0;
+    const size_t ys_bytes = ev((size_t)d.m) * sizeof(double);
+    size_t bounds_bytes_used = 0;
     for (int G = gmax; G >= 1 && !groups; G--) {
-        if ((size_t)G * ((pmin.bytes + 15) / 16 * 16) > budget) continue;
+        const size_t base = (pmin.bytes - bnd_bytes + 15) / 16 * 16;
+        if ((size_t)G * base + bnd_bytes > budget) continue;
         // per-group extras, in order of preference
-        size_t per = (pmin.bytes + 15) / 16 * 16;
-        size_t cache = 0;
+        size_t per = base;
+        size_t cache = bnd_bytes;
         int what = 0;
-        bool tinv_smem = false, outer_smem = false;
+        bool tinv_smem = false, outer_smem = false, ys_global = false;
         const size_t tb = tinv_doubles(d) * sizeof(double), ob = outer_doubles(d) * sizeof(double);
         auto fits = [&](size_t per_new, size_t cache_new) { return (size_t)G * ((per_new + 15) / 16 * 16) + cache_new <= budget; };
         if (tinv_pref != 0 && fits(per + tb, cache)) { per += tb; tinv_smem = true; }
         if (tinv_pref == 1 && !tinv_smem) continue;
         if ((cache_allow & 2) && c_hot && fits(per, cache + c_hot)) { cache += c_hot; what |= 2; }
-        if ((cache_allow & 1) && c_se && fits(per, cache + c_se)) { cache += c_se; what |= 1; }
-        if (fits(per + ob, cache)) { per += ob; outer_smem = true; }
+        if ((cache_allow & 1) && c_se) {
+            if (fits(per, cache + c_se)) { cache += c_se; what |= 1; }
+            else if (!getenv("LCQP_CUDA_NO_SLIM") && fits(per - ys_bytes, cache + c_se)) {
+                // the accepted duals move to the global scratch (with the outer-loop vectors) to make room
+                per -= ys_bytes; ys_global = true; cache += c_se; what |= 1;
+            }
+        }
+        if (!ys_global && fits(per + ob, cache)) { per += ob; outer_smem = true; }
         if ((cache_allow & 4) && c_raw && (what & 2) && fits(per, cache + c_raw)) { cache += c_raw; what |= 4; }
         plan = pmin;
         plan.tinv_in_smem = tinv_smem;
         plan.outer_in_smem = outer_smem;
-        plan.gl_doubles = (tinv_smem ? 0 : tinv_gl_doubles(d)) + (outer_smem ? 0 : outer_doubles(d));
+        plan.ys_global = ys_global;
+        plan.bounds_shared = bounds_shared;
+        plan.gl_doubles = (tinv_smem ? 0 : tinv_gl_doubles(d)) + (outer_smem ? 0 : outer_doubles(d)) + (ys_global ? ev((size_t)d.m) : 0);
         plan.bytes = (per + 15) / 16 * 16;
         groups = G;
-        a.cache_bytes = cache; a.cache_what = what | (use_ell ? 8 : 0);
+        a.cache_bytes = cache - bnd_bytes; a.cache_what = what;
+        bounds_bytes_used = bnd_bytes;
     }
     if (!groups) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
     a.plan = plan;
     a.group_bytes = plan.bytes;
-    a.cache_offset = (unsigned long long)groups * plan.bytes;
+    a.bounds_offset = (unsigned long long)groups * plan.bytes;
+    a.cache_offset = a.bounds_offset + bounds_bytes_used;
     const size_t smem = (size_t)a.cache_offset + a.cache_bytes;
     CK(cudaFuncSetAttribute(lcqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
     int per_sm = 0;
@@ -633,8 +654,9 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     a.workspace = h->workspace;
 
     if (getenv("LCQP_CUDA_VERBOSE"))
-        fprintf(stderr, "lcqp_cuda: grid %d x (%d threads x %d groups), %d CTA/SM, smem %zu B = %d x %zu (tinv %s, outer %s) + cache %llu (what %d; se %zu hot %zu raw %zu), mE %d cap %d\n",
+        fprintf(stderr, "lcqp_cuda: grid %d x (%d threads x %d groups), %d CTA/SM, smem %zu B = %d x %zu (tinv %s, outer %s, ys %s, bounds %s) + cache %llu (what %d; se %zu hot %zu raw %zu), mE %d cap %d\n",
                 grid, threads, groups, per_sm, smem, groups, (size_t)plan.bytes, plan.tinv_in_smem ? "smem" : "L2", plan.outer_in_smem ? "smem" : "L2",
+                plan.ys_global ? "L2" : "smem", plan.bounds_shared ? "shared" : "own",
                 a.cache_bytes, a.cache_what, c_se, c_hot, c_raw, mE, d.cap);
     lcqp_solve_kernel<<<grid, dim3(threads, groups), smem, stream>>>(a);
     h->launches++;

@@ -127,7 +127,6 @@ LCQ_DEV double lds64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1
 LCQ_DEV void lds128(unsigned a, double& x, double& y) { asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a)); }
 LCQ_DEV int lds32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 LCQ_DEV unsigned ldsu16(unsigned a) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return v; }
-LCQ_DEV unsigned ldsu8(unsigned a) { unsigned v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 LCQ_DEV void sts64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
 LCQ_DEV double ldg64(const double* p) { double v; asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
 LCQ_DEV void ldg128(const double* p, double& x, double& y) { asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p)); }
@@ -150,7 +149,6 @@ constexpr int kScalingIters = 10;        // constants.h:56
 constexpr int kMaxLeyffer = 16;
 constexpr double kResTol = 1e-9;         // residual of an EQP solve that still counts as solved
 constexpr int kLongRow = 32;             // CSR rows longer than this are reduced by a warp
-constexpr int kEllMax = 4;               // ELL form: rows up to this length are 'short' (one thread, unrolled)
 
 enum { RET_OK = 0, RET_INVALID_OSQP_BOX = 110, RET_INVALID_LOWER_COMP = 120, RET_MAX_ITER = 200, RET_MAX_PEN = 201,
        RET_SUBPROBLEM = 203, RET_OSQP_GUESS = 208 };
@@ -169,13 +167,7 @@ struct Op {
     const double* va;
     const int* lrows;
     int rows, cols, ld, trans, nlong;
-    int smem;   // 1: the CSR arrays were copied into shared memory (operator cache); 2: ELL copy in shared memory
-    // Shape of the ELL form (set when the CSR is built): rows with at most kEllMax entries are 'short' (ellK = the
-    // longest of them), the others ('long': ell_nl rows, ell_lnnz entries) stay in a compact CSR.
-    int ellK, ell_nl, ell_lnnz;
-    // smem == 2: 32-bit shared-window addresses of the ELL copy.  Short rows column-major by entry (entry k of
-    // row r at k*rows + r, zero padded), one length byte per row (255 = long row).
-    unsigned e_va, e_ci, e_len, e_lva, e_lci, e_lrp, e_lrows;
+    int smem;   // the CSR arrays were copied into shared memory (operator cache)
 };
 
 LCQ_DEV Op dense_op(const double* M, int rows, int cols, int ld, int trans)
@@ -183,8 +175,6 @@ LCQ_DEV Op dense_op(const double* M, int rows, int cols, int ld, int trans)
     Op o;
     o.dense = M; o.rp = nullptr; o.ci = nullptr; o.va = nullptr; o.lrows = nullptr;
     o.rows = rows; o.cols = cols; o.ld = ld; o.trans = trans; o.nlong = 0; o.smem = 0;
-    o.ellK = 0; o.ell_nl = 0; o.ell_lnnz = 0;
-    o.e_va = o.e_ci = o.e_len = o.e_lva = o.e_lci = o.e_lrp = o.e_lrows = 0u;
     return o;
 }
 
@@ -541,126 +531,6 @@ LCQ_DEV void csr_mv(const int* __restrict__ rp, const unsigned short* __restrict
 #undef LCQ_INIT
 }
 
-#ifndef LCQP_HOST_EMU
-// ---- ELL mat-vec (operator and vectors in shared memory) --------------------------------------------------
-// out[r] = (init ? init[iidx ? iidx[r] : r] : 0) + scale * sum_k M[r][k] v[c(r,k)], entries summed in column order
-// (the order of the CSR loops: bit-identical results).  Four rows per thread are in flight: all index/value loads,
-// then all gathers, then the sums -- the latencies of the rows overlap instead of adding up.
-template <int K>
-LCQ_DEV void ell_mv(const Op& op, unsigned vs, unsigned is, bool has_init, const int* iidx, double scale, unsigned os)
-{
-    const int rows = op.rows;
-    const unsigned eva = op.e_va, eci = op.e_ci, elen = op.e_len;
-    LCQ_LOOP for (int r0 = LCQ_TID; r0 < rows; r0 += 4 * LCQ_NT) {
-        unsigned len[4], c[4][K];
-        double a[4][K], x[4][K], i0[4];
-        int rr[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int r = r0 + t * LCQ_NT;
-            rr[t] = r < rows ? r : r0;
-            len[t] = ldsu8(elen + (unsigned)rr[t]);
-            if (r >= rows) len[t] = 255u;
-        }
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const unsigned e = (unsigned)(k * rows + rr[t]);
-                c[t][k] = ldsu16(eci + 2u * e);
-                a[t][k] = lds64(eva + 8u * e);
-            }
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-#pragma unroll
-            for (int k = 0; k < K; k++) x[t][k] = lds64(vs + 8u * c[t][k]);
-            i0[t] = (has_init && len[t] != 255u) ? lds64(is + 8u * (unsigned)(iidx ? iidx[rr[t]] : rr[t])) : 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            double s = 0;
-#pragma unroll
-            for (int k = 0; k < K; k++) if ((unsigned)k < len[t]) s += a[t][k] * x[t][k];
-            if (len[t] != 255u) sts64(os + 8u * (unsigned)rr[t], i0[t] + scale * s);
-        }
-    }
-    // long rows: one warp per row
-    const int nl = op.ell_nl;
-    const unsigned lva = op.e_lva, lci = op.e_lci, lrp = op.e_lrp, lrows = op.e_lrows;
-    LCQ_LOOP for (int p = LCQ_WARP; p < nl; p += LCQ_NWARP) {
-        const int r = lds32(lrows + 4u * (unsigned)p);
-        const int k1 = lds32(lrp + 4u * (unsigned)p + 4u);
-        double s0 = 0, s1 = 0;
-        int k = lds32(lrp + 4u * (unsigned)p) + LCQ_LANE;
-        LCQ_LOOP for (; k + LCQ_LANES < k1; k += 2 * LCQ_LANES) {
-            const unsigned c0 = ldsu16(lci + 2u * (unsigned)k), c1 = ldsu16(lci + 2u * (unsigned)(k + LCQ_LANES));
-            const double a0 = lds64(lva + 8u * (unsigned)k), a1 = lds64(lva + 8u * (unsigned)(k + LCQ_LANES));
-            s0 += a0 * lds64(vs + 8u * c0);
-            s1 += a1 * lds64(vs + 8u * c1);
-        }
-        if (k < k1) s0 += lds64(lva + 8u * (unsigned)k) * lds64(vs + 8u * ldsu16(lci + 2u * (unsigned)k));
-        const double s = warp_sum(s0 + s1);
-        if (LCQ_LANE == 0) {
-            const double i0 = has_init ? lds64(is + 8u * (unsigned)(iidx ? iidx[r] : r)) : 0.0;
-            sts64(os + 8u * (unsigned)r, i0 + scale * s);
-        }
-    }
-}
-
-// out[a] = sum_k M[idx[a]][k] v[c] - (sub ? sub[idx[a]] : 0) for a < na; idx, v, sub, out in shared memory
-template <int K>
-LCQ_DEV void ell_mv_rows(const Op& op, unsigned xs, int na, unsigned vs, unsigned ss, bool has_sub, unsigned os)
-{
-    const int rows = op.rows;
-    const unsigned eva = op.e_va, eci = op.e_ci, elen = op.e_len;
-    LCQ_LOOP for (int a0 = LCQ_TID; a0 < na; a0 += 4 * LCQ_NT) {
-        unsigned len[4], c[4][K];
-        double a[4][K], x[4][K], sb[4];
-        int rr[4];
-        bool ok[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const int p = a0 + t * LCQ_NT;
-            ok[t] = p < na;
-            rr[t] = lds32(xs + 4u * (unsigned)(ok[t] ? p : a0));
-        }
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            len[t] = ldsu8(elen + (unsigned)rr[t]);
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                const unsigned e = (unsigned)(k * rows + rr[t]);
-                c[t][k] = ldsu16(eci + 2u * e);
-                a[t][k] = lds64(eva + 8u * e);
-            }
-            sb[t] = has_sub ? lds64(ss + 8u * (unsigned)rr[t]) : 0.0;
-        }
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-#pragma unroll
-            for (int k = 0; k < K; k++) x[t][k] = lds64(vs + 8u * c[t][k]);
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            double s = 0;
-            if (len[t] == 255u) {
-                // a long row in the working set: its thread sums it alone (rare)
-                const int nl = op.ell_nl;
-                LCQ_LOOP for (int p = 0; p < nl; p++) {
-                    if (lds32(op.e_lrows + 4u * (unsigned)p) != rr[t]) continue;
-                    const int k1 = lds32(op.e_lrp + 4u * (unsigned)p + 4u);
-                    LCQ_LOOP for (int k = lds32(op.e_lrp + 4u * (unsigned)p); k < k1; k++)
-                        s += lds64(op.e_lva + 8u * (unsigned)k) * lds64(vs + 8u * ldsu16(op.e_lci + 2u * (unsigned)k));
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < K; k++) if ((unsigned)k < len[t]) s += a[t][k] * x[t][k];
-            }
-            if (ok[t]) sts64(os + 8u * (unsigned)(a0 + t * LCQ_NT), s - sb[t]);
-        }
-    }
-}
-#endif
-
 template <bool VS>
 LCQ_DEVN void op_mv_t(const Op& opr, const double* v, const double* init, double scale, double* out, const int* iidx = nullptr)
 {
@@ -668,18 +538,6 @@ LCQ_DEVN void op_mv_t(const Op& opr, const double* v, const double* init, double
     const bool has_init = init != nullptr;
     if (!has_init) init = v;   // a valid address for the address-space assumption; never read
     if (op.rp) {
-#ifndef LCQP_HOST_EMU
-        if (VS && op.smem == 2) {
-            const unsigned vs = saddr(v), is = saddr(init), os = saddr(out);
-            switch (op.ellK) {
-                case 0: case 1: ell_mv<1>(op, vs, is, has_init, iidx, scale, os); break;
-                case 2: ell_mv<2>(op, vs, is, has_init, iidx, scale, os); break;
-                case 3: ell_mv<3>(op, vs, is, has_init, iidx, scale, os); break;
-                default: ell_mv<4>(op, vs, is, has_init, iidx, scale, os); break;
-            }
-            return;
-        }
-#endif
         if (op.smem == 1) csr_mv<VS, true>(op.rp, op.ci, op.va, op.lrows, op.rows, op.nlong, v, init, has_init, scale, out, iidx);
         else csr_mv<VS, false>(op.rp, op.ci, op.va, op.lrows, op.rows, op.nlong, v, init, has_init, scale, out, iidx);
         return;
@@ -765,18 +623,6 @@ LCQ_DEVN void op_mv_rows(const Op& opr, const int* idx, int na, const double* v,
     const bool has_sub = sub != nullptr;
     if (!has_sub) sub = v;
     if (op.rp) {
-#ifndef LCQP_HOST_EMU
-        if (op.smem == 2) {
-            const unsigned xs = saddr(idx), vs = saddr(v), ss = saddr(sub), os = saddr(out);
-            switch (op.ellK) {
-                case 0: case 1: ell_mv_rows<1>(op, xs, na, vs, ss, has_sub, os); break;
-                case 2: ell_mv_rows<2>(op, xs, na, vs, ss, has_sub, os); break;
-                case 3: ell_mv_rows<3>(op, xs, na, vs, ss, has_sub, os); break;
-                default: ell_mv_rows<4>(op, xs, na, vs, ss, has_sub, os); break;
-            }
-            return;
-        }
-#endif
         if (op.smem == 1) csr_mv_rows<true>(op.rp, op.ci, op.va, idx, na, v, sub, has_sub, out);
         else csr_mv_rows<false>(op.rp, op.ci, op.va, idx, na, v, sub, has_sub, out);
     } else {
@@ -1008,14 +854,9 @@ LCQ_DEVN Op build_op(const double* src, int rows, int cols, int ld, int trans, C
     }
     LCQ_SYNC();
     if (LCQ_TID == 0) {
-        int tot = 0, nl = 0, eK = 0, enl = 0, elnnz = 0;
+        int tot = 0, nl = 0;
         rp[0] = 0;
-        LCQ_LOOP for (int r = 0; r < rows; r++) {
-            const int c = rp[r + 1];
-            nl += (c > kLongRow); tot += c; rp[r + 1] = tot;
-            if (c > kEllMax) { enl++; elnnz += c; } else if (c > eK) eK = c;
-        }
-        sc->ired[4] = eK; sc->ired[5] = enl; sc->ired[6] = elnnz;
+        LCQ_LOOP for (int r = 0; r < rows; r++) { const int c = rp[r + 1]; nl += (c > kLongRow); tot += c; rp[r + 1] = tot; }
         const int io = pool.used[0], dof = pool.used[1];
         const int ci_ints = (tot + 1) / 2;   // 16-bit column indices
         const bool sparse = cols < 65536 && (long long)tot * 4 <= (long long)rows * cols && io + ci_ints + nl <= pool.icap && dof + tot <= pool.dcap;
@@ -1045,7 +886,6 @@ LCQ_DEVN Op build_op(const double* src, int rows, int cols, int ld, int trans, C
     }
     LCQ_SYNC();
     op.rp = rp; op.ci = ci; op.va = va; op.lrows = pool.ibuf + io + (rp[rows] + 1) / 2; op.nlong = nl;
-    op.ellK = sc->ired[4]; op.ell_nl = sc->ired[5]; op.ell_lnnz = sc->ired[6];
     return op;
 }
 
@@ -1395,61 +1235,6 @@ LCQ_DEVN void cache_op(Op& op, unsigned char*& cur, unsigned char* end)
     cur += need;
 }
 
-// ---- ELL form of a cached operator -----------------------------------------------------------------------
-inline LCQ_HD size_t r16(size_t b) { return (b + 15) / 16 * 16; }
-inline LCQ_HD size_t ell_cache_bytes(int rows, int K, int nl, int lnnz)
-{
-    const size_t e = (size_t)rows * (K > 0 ? K : 1);
-    return r16(e * sizeof(double)) + r16((size_t)lnnz * sizeof(double)) + r16(((size_t)nl + 1 + nl) * sizeof(int)) +
-           r16(e * sizeof(unsigned short)) + r16((size_t)lnnz * sizeof(unsigned short)) + r16((size_t)rows);
-}
-LCQ_DEV size_t ell_cache_bytes(const Op& op) { return op.rp ? ell_cache_bytes(op.rows, op.ellK, op.ell_nl, op.ell_lnnz) : 0; }
-
-#ifndef LCQP_HOST_EMU
-// Build the ELL copy of a CSR operator (global memory) in [*cur, end) if it fits (block-cooperative).
-LCQ_DEVN void cache_op_ell(Op& op, unsigned char*& cur, unsigned char* end)
-{
-    if (!op.rp) return;
-    const int rows = op.rows, K = op.ellK > 0 ? op.ellK : 1, nl = op.ell_nl, lnnz = op.ell_lnnz;
-    const size_t need = ell_cache_bytes(rows, op.ellK, nl, lnnz);
-    if (cur + need > end) return;
-    const size_t e = (size_t)rows * K;
-    unsigned char* q = cur;
-    double* va = reinterpret_cast<double*>(q); q += r16(e * sizeof(double));
-    double* lva = reinterpret_cast<double*>(q); q += r16((size_t)lnnz * sizeof(double));
-    int* lrp = reinterpret_cast<int*>(q);
-    int* lrows = lrp + nl + 1; q += r16(((size_t)nl + 1 + nl) * sizeof(int));
-    unsigned short* ci = reinterpret_cast<unsigned short*>(q); q += r16(e * sizeof(unsigned short));
-    unsigned short* lci = reinterpret_cast<unsigned short*>(q); q += r16((size_t)lnnz * sizeof(unsigned short));
-    unsigned char* len = q;
-    LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
-        const int k0 = op.rp[r], c = op.rp[r + 1] - k0;
-        len[r] = (unsigned char)(c > kEllMax ? 255 : c);
-        LCQ_LOOP for (int k = 0; k < K; k++) {
-            const bool in = c <= kEllMax && k < c;
-            va[(size_t)k * rows + r] = in ? op.va[k0 + k] : 0.0;
-            ci[(size_t)k * rows + r] = in ? op.ci[k0 + k] : (unsigned short)0;
-        }
-    }
-    LCQ_SYNC();
-    if (LCQ_TID == 0) {
-        int p = 0, tot = 0;
-        LCQ_LOOP for (int r = 0; r < rows && p < nl; r++)
-            if (len[r] == 255) { lrows[p] = r; lrp[p] = tot; tot += op.rp[r + 1] - op.rp[r]; p++; }
-        lrp[nl] = tot;
-    }
-    LCQ_SYNC();
-    LCQ_LOOP for (int p = 0; p < nl; p++) {
-        const int r = lrows[p], k0 = op.rp[r], c = op.rp[r + 1] - k0, o = lrp[p];
-        LCQ_LOOP for (int k = LCQ_TID; k < c; k += LCQ_NT) { lva[o + k] = op.va[k0 + k]; lci[o + k] = op.ci[k0 + k]; }
-    }
-    op.e_va = saddr(va); op.e_ci = saddr(ci); op.e_len = saddr(len); op.e_lva = saddr(lva); op.e_lci = saddr(lci);
-    op.e_lrp = saddr(lrp); op.e_lrows = saddr(lrows);
-    op.smem = 2;
-    cur += need;
-}
-#endif
-
 // `mt` / `ro` are this CTA's block-shared copies; one thread writes them.  what: bit0 packed SEinv,
 // bit1 the operators of the inner passes, bit2 the operators of the outer loop.
 LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsigned char* base, size_t bytes, int what)
@@ -1483,18 +1268,8 @@ LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsign
         }
     }
     if (what & 2) {
-#ifndef LCQP_HOST_EMU
-        if (!(what & 8)) {
-            cache_op(oA, cur, end); cache_op(oAt, cur, end); cache_op(oAHE, cur, end); cache_op(oAHtE, cur, end);
-            cache_op(oHinv, cur, end); cache_op(oP, cur, end);
-        } else {
-        cache_op_ell(oA, cur, end); cache_op_ell(oAt, cur, end); cache_op_ell(oAHE, cur, end); cache_op_ell(oAHtE, cur, end);
-        cache_op_ell(oHinv, cur, end); cache_op_ell(oP, cur, end);
-        }
-#else
         cache_op(oA, cur, end); cache_op(oAt, cur, end); cache_op(oAHE, cur, end); cache_op(oAHtE, cur, end);
         cache_op(oHinv, cur, end); cache_op(oP, cur, end);
-#endif
     }
     Op rL = ro.L, rR = ro.R, rLt = ro.Lt, rRt = ro.Rt, rQ = ro.Q, rAt = ro.At;
     if (what & 4) {
@@ -1515,13 +1290,8 @@ LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsign
 LCQ_DEV void cache_requirements(Mats& mt, const RawOps& ro)
 {
     mt.cache_bytes_se = (int)(((size_t)mt.mE * (mt.mE + 1) / 2 * sizeof(double) + 15) / 16 * 16);
-#ifndef LCQP_HOST_EMU
-    mt.cache_bytes_hot = (int)(((size_t)mt.mE * sizeof(int) + 15) / 16 * 16 + ell_cache_bytes(mt.oA) + ell_cache_bytes(mt.oAt) + ell_cache_bytes(mt.oAHE) + ell_cache_bytes(mt.oAHtE) +
-                               ell_cache_bytes(mt.oHinv) + ell_cache_bytes(mt.oP));
-#else
     mt.cache_bytes_hot = (int)(((size_t)mt.mE * sizeof(int) + 15) / 16 * 16 + op_cache_bytes(mt.oA) + op_cache_bytes(mt.oAt) + op_cache_bytes(mt.oAHE) + op_cache_bytes(mt.oAHtE) +
                                op_cache_bytes(mt.oHinv) + op_cache_bytes(mt.oP));
-#endif
     mt.cache_bytes_raw = (int)(op_cache_bytes(ro.L) + op_cache_bytes(ro.R) + op_cache_bytes(ro.Lt) + op_cache_bytes(ro.Rt) +
                                op_cache_bytes(ro.Q) + op_cache_bytes(ro.At));
 }
@@ -2451,6 +2221,8 @@ struct SmemPlan {
     int outer_in_smem;
     int tinv_in_smem;
     size_t gl_doubles;   // doubles of global scratch per CTA for what did not fit
+    int ys_global;       // the accepted duals (read by the outer loop only) live in the global scratch
+    int bounds_shared;   // l / ub of all groups alias one copy behind the groups (bounds shared by the batch)
 };
 
 // every vector starts on a 16-byte boundary (vector loads): lengths are rounded up to even
@@ -2472,6 +2244,8 @@ inline LCQ_HD SmemPlan make_plan(const Dims& d, size_t budget, bool tinv_global 
     SmemPlan p;
     size_t b = qp_doubles(d) * sizeof(double) + misc_bytes(d);
     p.gl_doubles = 0;
+    p.ys_global = 0;
+    p.bounds_shared = 0;
     p.tinv_in_smem = !tinv_global && (b + tinv_doubles(d) * sizeof(double) <= budget);
     if (p.tinv_in_smem) b += tinv_doubles(d) * sizeof(double); else p.gl_doubles += tinv_gl_doubles(d);
     p.outer_in_smem = (b + outer_doubles(d) * sizeof(double) <= budget);
@@ -2480,7 +2254,8 @@ inline LCQ_HD SmemPlan make_plan(const Dims& d, size_t budget, bool tinv_global 
     return p;
 }
 
-LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* base, double* gl)
+// shared_bounds: 2 ev(m) doubles shared by the groups of the CTA (plan.bounds_shared), else null
+LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* base, double* gl, double* shared_bounds = nullptr)
 {
     double* q = reinterpret_cast<double*>(base);
     auto take = [&](size_t k) { double* r = q; q += ev(k); return r; };
@@ -2488,12 +2263,14 @@ LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* bas
     const int n = d.n, m = d.m;
     w.q = take(n); w.x = take(n); w.xa = take(n); w.r1 = take(n); w.u = take(n); w.t = take(n); w.dx = take(n);
     w.px = w.t;   // q + P x lives only inside kkt_residual, t only inside kkt_solve / admm_iter
-    w.z = take(m); w.y = take(m); w.l = take(m); w.ub = take(m); w.lam = take(m); w.dlam = take(m); w.r2 = take(m);
+    w.z = take(m); w.y = take(m); w.lam = take(m); w.dlam = take(m); w.r2 = take(m);
+    if (p.bounds_shared && shared_bounds) { w.l = shared_bounds; w.ub = shared_bounds + ev(m); }
+    else { w.l = take(m); w.ub = take(m); }
     w.zx = take(m); w.zp = take(m); w.yf = take(m);
     w.w = w.yf;   // ADMM scratch; yf is scratch of the active-set passes (zeroed before they start)
     w.dI = take(d.cap); w.lI = take(d.cap);
     w.cE = take(d.capE); w.vE = take(d.capE);
-    w.ys = take(m);
+    w.ys = p.ys_global ? takeg(m) : take(m);
     w.Tinv = p.tinv_in_smem ? take(tinv_doubles(d)) : takeg(tinv_gl_doubles(d));
     w.tld = p.tinv_in_smem ? 0 : tinv_ld(d);
     auto tk = [&](size_t k) { return p.outer_in_smem ? take(k) : takeg(k); };
