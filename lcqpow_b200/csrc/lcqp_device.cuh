@@ -481,16 +481,26 @@ LCQ_DEV void csr_mv(const int* __restrict__ rp, const unsigned short* __restrict
         // everything but iidx lives in shared memory: 32-bit shared addresses, LDS/STS (same operation order
         // as the generic loops below, so the results are bit-identical)
         const unsigned rps = saddr(rp), cis = saddr(ci), vas = saddr(va), vs = saddr(v), is = saddr(init), os = saddr(out), lrs = saddr(lrows);
-        LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
-            const int k0 = lds32(rps + 4u * (unsigned)r), k1 = lds32(rps + 4u * (unsigned)r + 4u);
-            if (k1 - k0 > kLongRow) continue;
-            double s = 0;
-            unsigned ca = cis + 2u * (unsigned)k0, xa = vas + 8u * (unsigned)k0;
-            LCQ_LOOP for (int k = k0; k < k1; k++) { s += lds64(xa) * lds64(vs + 8u * ldsu16(ca)); ca += 2u; xa += 8u; }
-            const double i0 = has_init ? lds64(is + 8u * (unsigned)(iidx ? iidx[r] : r)) : 0.0;
-            sts64(os + 8u * (unsigned)r, i0 + scale * s);
+        // two rows of a thread (r and r + NT) advance in lockstep: two independent load -> multiply -> add chains
+        LCQ_LOOP for (int r = LCQ_TID; r < rows; r += 2 * LCQ_NT) {
+            const int rb = r + LCQ_NT;
+            const bool hb = rb < rows;
+            int ka = lds32(rps + 4u * (unsigned)r), ea = lds32(rps + 4u * (unsigned)r + 4u);
+            int kb = hb ? lds32(rps + 4u * (unsigned)rb) : 0, eb = hb ? lds32(rps + 4u * (unsigned)rb + 4u) : 0;
+            const bool sa_ok = ea - ka <= kLongRow, sb_ok = hb && eb - kb <= kLongRow;
+            if (!sa_ok) ea = ka;
+            if (!sb_ok) eb = kb;
+            const double ia = (has_init && sa_ok) ? lds64(is + 8u * (unsigned)(iidx ? iidx[r] : r)) : 0.0;
+            const double ib = (has_init && sb_ok) ? lds64(is + 8u * (unsigned)(iidx ? iidx[rb] : rb)) : 0.0;
+            double sa = 0, sb = 0;
+            LCQ_LOOP while (ka < ea || kb < eb) {
+                if (ka < ea) { sa += lds64(vas + 8u * (unsigned)ka) * lds64(vs + 8u * ldsu16(cis + 2u * (unsigned)ka)); ka++; }
+                if (kb < eb) { sb += lds64(vas + 8u * (unsigned)kb) * lds64(vs + 8u * ldsu16(cis + 2u * (unsigned)kb)); kb++; }
+            }
+            if (sa_ok) sts64(os + 8u * (unsigned)r, ia + scale * sa);
+            if (sb_ok) sts64(os + 8u * (unsigned)rb, ib + scale * sb);
         }
-        LCQ_LOOP for (int a = LCQ_WARP; a < nlong; a += LCQ_NWARP) {
+        LCQ_LOOP for (int a = LCQ_NWARP - 1 - LCQ_WARP; a < nlong; a += LCQ_NWARP) {
             const int r = lds32(lrs + 4u * (unsigned)a);
             const int k1 = lds32(rps + 4u * (unsigned)r + 4u);
             double s0 = 0, s1 = 0;
@@ -518,7 +528,7 @@ LCQ_DEV void csr_mv(const int* __restrict__ rp, const unsigned short* __restrict
         out[r] = LCQ_INIT(r) + scale * s;
     }
     if (LCQ_LANES > 1)
-        LCQ_LOOP for (int a = LCQ_WARP; a < nlong; a += LCQ_NWARP) {
+        LCQ_LOOP for (int a = LCQ_NWARP - 1 - LCQ_WARP; a < nlong; a += LCQ_NWARP) {
             const int r = lrows[a];
             const int k1 = rp[r + 1];
             double s0 = 0, s1 = 0;

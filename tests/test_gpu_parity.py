@@ -79,6 +79,23 @@ def test_osqp_style_dual_layout(golden, example_data):
     assert int(stx["ret"][0]) == 110
 
 
+
+def test_circle_family_trajectories_match_oracle(oracle):
+    """128 seeded instances of the C2 family with perturbStep on (the shipped default): the CUDA path and the
+    oracle must walk the same penalty homotopy -- identical ReturnValue, stationarity type, outer and total
+    iteration counts for every instance -- and agree in x to 1e-8.  (The oracle is pinned against the real
+    reference on this family by tests/test_oracle_parity.py.)  This is the sensitive detector for changes of
+    summation order in the device kernels."""
+    from lcqpow_b200 import problems as P
+    pb = P.circle_batch(128)
+    over = {"stationarityTolerance": 10e-3}
+    x, y, st, _ = _solve_cuda(pb, over, perturb=1)
+    so = oracle.solve_batch(pb, oracle.default_options(perturbStep=1, **over))
+    for f in ("ret", "status", "iterOuter", "iterTotal"):
+        bad = np.nonzero(np.asarray(st[f]) != np.asarray(so.res[f]))[0]
+        assert bad.size == 0, (f, bad.tolist())
+    assert np.abs(x - so.x).max() <= 1e-8 * max(1.0, np.abs(so.x).max())
+
 def test_large_batch_properties():
     """Full-size behaviour through size-independent properties: every solved instance is complementary
     (phi < tol), feasible, and a re-run is bit-identical (deterministic reductions)."""
