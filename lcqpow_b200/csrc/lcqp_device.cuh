@@ -677,7 +677,11 @@ LCQ_DEV void mv_dense(const double* __restrict__ M, int rows, int cols, int ld, 
 }
 
 // ---- packed symmetric matrix (lower triangle, row-major): S(a,b), b <= a, at a(a+1)/2 + b ----------------
-LCQ_DEV size_t pidx(int a, int b) { return a >= b ? (size_t)a * (a + 1) / 2 + b : (size_t)b * (b + 1) / 2 + a; }
+// Every row starts at an even offset (16-byte aligned, for 16-byte shared-memory loads): row a begins at
+// prow(a) = a(a+1)/2 + (a+1)/2, the rows of odd length carry one pad entry.
+inline LCQ_HD size_t prow(int a) { return (size_t)a * (a + 1) / 2 + (size_t)((a + 1) / 2); }
+inline LCQ_HD size_t packed_doubles(int order) { return prow(order); }
+LCQ_DEV size_t pidx(int a, int b) { return a >= b ? prow(a) + b : prow(b) + a; }
 
 // y = sgn * S v for a symmetric matrix S of order nw, scattered to up to three places:
 //     out[a] = y_a;   o2[sidx[a]] = y_a;   o3[sidx[a]] = y_a          (null pointers are skipped)
@@ -780,21 +784,26 @@ LCQ_SYM_INL void sym_apply(const double* __restrict__ S, int ld, int nw, const d
         const unsigned Ss = saddr(S);
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
             double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            unsigned row = Ss + 8u * (unsigned)(a * (a + 1) / 2);
+            unsigned row = Ss + 8u * (unsigned)prow(a);   // 16-byte aligned
             unsigned va = vs;
             int b = 0;
             LCQ_LOOP for (; b + 4 <= a + 1; b += 4) {
-                const double r0 = lds64(row), r1 = lds64(row + 8u), r2 = lds64(row + 16u), r3 = lds64(row + 24u);
-                const double v0 = lds64(va), v1 = lds64(va + 8u), v2 = lds64(va + 16u), v3 = lds64(va + 24u);
+                double r0, r1, r2, r3, v0, v1, v2, v3;
+                lds128(row, r0, r1); lds128(row + 16u, r2, r3);
+                lds128(va, v0, v1); lds128(va + 16u, v2, v3);
                 s0 += r0 * v0; s1 += r1 * v1; s2 += r2 * v2; s3 += r3 * v3;
                 row += 32u; va += 32u;
             }
             LCQ_LOOP for (; b <= a; b++) { s0 += lds64(row) * lds64(va); row += 8u; va += 8u; }
-            unsigned q = Ss + 8u * (unsigned)(b * (b + 1) / 2 + a);   // S(b, a), b = a + 1
-            LCQ_LOOP for (; b + 2 <= nw; b += 2) {
-                s1 += lds64(q) * lds64(va);
-                s2 += lds64(q + 8u * (unsigned)(b + 1)) * lds64(va + 8u);
-                q += 8u * (unsigned)(2 * b + 3); va += 16u;
+            // b = a + 1: the column part, S(b, a) at prow(b) + a; v is read in aligned pairs
+            if ((b & 1) && b < nw) { s3 += lds64(Ss + 8u * (unsigned)(prow(b) + a)) * lds64(va); b++; va += 8u; }
+            unsigned q = Ss + 8u * (unsigned)(prow(b) + a);
+            LCQ_LOOP for (; b + 2 <= nw; b += 2) {     // b even: prow(b+1) - prow(b) = b + 2, prow(b+2) - prow(b) = 2b + 4
+                double v0, v1;
+                lds128(va, v0, v1);
+                s1 += lds64(q) * v0;
+                s2 += lds64(q + 8u * (unsigned)(b + 2)) * v1;
+                q += 8u * (unsigned)(2 * b + 4); va += 16u;
             }
             if (b < nw) s3 += lds64(q) * lds64(va);
             LCQ_EMIT(a, (s0 + s1) + (s2 + s3));
@@ -1255,12 +1264,12 @@ LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsign
     LCQ_SYNC();
     const double* sep = nullptr;
     if (mE > 0 && (what & 1)) {
-        const size_t need = ((size_t)mE * (mE + 1) / 2 * sizeof(double) + 15) / 16 * 16;
+        const size_t need = (packed_doubles(mE) * sizeof(double) + 15) / 16 * 16;
         if (cur + need <= end) {
             double* P = reinterpret_cast<double*>(cur);
             LCQ_LOOP for (int e = LCQ_TID; e < mE * mE; e += LCQ_NT) {
                 const int a = e / mE, b = e - a * mE;
-                if (b <= a) P[(size_t)a * (a + 1) / 2 + b] = mt.SEinv[(size_t)a * d.ldE + b];
+                if (b <= a) P[prow(a) + b] = mt.SEinv[(size_t)a * d.ldE + b];
             }
             sep = P;
             cur += need;
@@ -1299,7 +1308,7 @@ LCQ_DEVN void cache_shared_operators(const Dims& d, Mats& mt, RawOps& ro, unsign
 // bytes the cache would take (thread 0 of the prepare step calls this)
 LCQ_DEV void cache_requirements(Mats& mt, const RawOps& ro)
 {
-    mt.cache_bytes_se = (int)(((size_t)mt.mE * (mt.mE + 1) / 2 * sizeof(double) + 15) / 16 * 16);
+    mt.cache_bytes_se = (int)((packed_doubles(mt.mE) * sizeof(double) + 15) / 16 * 16);
     mt.cache_bytes_hot = (int)(((size_t)mt.mE * sizeof(int) + 15) / 16 * 16 + op_cache_bytes(mt.oA) + op_cache_bytes(mt.oAt) + op_cache_bytes(mt.oAHE) + op_cache_bytes(mt.oAHtE) +
                                op_cache_bytes(mt.oHinv) + op_cache_bytes(mt.oP));
     mt.cache_bytes_raw = (int)(op_cache_bytes(ro.L) + op_cache_bytes(ro.R) + op_cache_bytes(ro.Lt) + op_cache_bytes(ro.Rt) +
@@ -1444,10 +1453,10 @@ LCQ_DEVN int tinv_append(QP& s, int j)
     } else {
         LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
             const double ua = w.lI[a] * ik;
-            double* row = Si + (size_t)a * (a + 1) / 2;
+            double* row = Si + prow(a);
             LCQ_LOOP for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] += ua * w.lI[b];
         }
-        double* row = Si + (size_t)nw * (nw + 1) / 2;
+        double* row = Si + prow(nw);
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) row[a] = -w.lI[a] * ik;
         if (LCQ_TID == 0) { row[nw] = ik; w.idx[nw] = j; }
     }
@@ -1470,7 +1479,7 @@ LCQ_DEVN void tinv_remove(QP& s, int p)
     else
         LCQ_LOOP for (int a = LCQ_WARP; a < nw; a += LCQ_NWARP) {
             const double ca = w.dI[a] * ic;
-            double* row = Si + (size_t)a * (a + 1) / 2;
+            double* row = Si + prow(a);
             LCQ_LOOP for (int b = LCQ_LANE; b <= a; b += LCQ_LANES) row[b] -= ca * w.dI[b];
         }
     LCQ_SYNC();
@@ -2239,7 +2248,7 @@ struct SmemPlan {
 inline LCQ_HD size_t ev(size_t k) { return (k + 1) & ~(size_t)1; }
 inline LCQ_HD size_t qp_doubles(const Dims& d) { return 7ull * ev(d.n) + 10ull * ev(d.m) + 2ull * ev(d.cap) + 2ull * ev(d.capE) + ev(d.m) /*ys*/; }
 inline LCQ_HD size_t outer_doubles(const Dims& d) { return 7ull * ev(d.n) + 2ull * ev(d.nComp); }
-inline LCQ_HD size_t tinv_doubles(const Dims& d) { return ev((size_t)d.cap * (d.cap + 1) / 2); }
+inline LCQ_HD size_t tinv_doubles(const Dims& d) { return ev(packed_doubles(d.cap)); }
 // working-set inverse in global memory: full storage, even leading dimension (16-byte loads of column pairs)
 inline LCQ_HD int tinv_ld(const Dims& d) { return (d.cap + 1) & ~1; }
 inline LCQ_HD size_t tinv_gl_doubles(const Dims& d) { return (size_t)d.cap * tinv_ld(d); }

@@ -6,7 +6,7 @@ top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 src = open('/root/repo/lcqpow_b200/csrc/lcqp_device.cuh').read().split('\n')
 starts = []
 for i, l in enumerate(src, 1):
-    m = re.match(r'^(?:LCQ_DEVN|LCQ_DEV|inline LCQ_HD)\s+[\w:<>\*& ]+?\s+\**(\w+)\(', l)
+    m = re.match(r'^(?:LCQ_DEVN|LCQ_DEV|LCQ_SYM_INL|LCQ_R1_INL|inline LCQ_HD)\s+[\w:<>\*& ]+?\s+\**(\w+)\(', l)
     if m: starts.append((i, m.group(1)))
 def func_of(ln):
     name = '?'
