@@ -133,6 +133,7 @@ LCQ_DEV void ldg128(const double* p, double& x, double& y) { asm volatile("ld.gl
 // volatile: ptxas keeps volatile loads in program order, i.e. a batch of them is ISSUED before the first use (it
 // otherwise sinks each load to its use when the enclosing function is large) -- that is what hides the L2 latency
 LCQ_DEV void ldg128v(const double* p, double& x, double& y) { asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "l"(p)); }
+LCQ_DEV double ldg64v(const double* p) { double v; asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v; }
 LCQ_DEV void lds128v(unsigned a, double& x, double& y) { asm volatile("ld.volatile.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a)); }
 LCQ_DEV void stg64(double* p, double v) { asm volatile("st.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
 LCQ_DEV void stg128(double* p, double x, double y) { asm volatile("st.global.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(x), "d"(y) : "memory"); }
@@ -556,35 +557,70 @@ LCQ_DEVN void op_mv_t(const Op& opr, const double* v, const double* init, double
     if (VS) { LCQ_ASSUME_SHARED(v); LCQ_ASSUME_SHARED(init); LCQ_ASSUME_SHARED(out); }
 #endif
 #define LCQ_INIT(r) (has_init ? init[iidx ? iidx[r] : (r)] : 0.0)
+#ifndef LCQP_HOST_EMU
+    // Dense operators live in global memory (L2-resident).  Eight loads per thread are issued as a batch
+    // (volatile: see ldg128v); the sums run in the same order as the plain loops of the host build.
+    const double* __restrict__ M = op.dense;
     if (!op.trans) {
         const int rows = op.rows, cols = op.cols, ld = op.ld;
-        LCQ_LOOP for (int r0 = LCQ_WARP; r0 < rows; r0 += 4 * LCQ_NWARP) {
-            const int r1 = r0 + LCQ_NWARP, r2 = r0 + 2 * LCQ_NWARP, r3 = r0 + 3 * LCQ_NWARP;
-            const double* a0 = op.dense + (size_t)r0 * ld;
-            const double* a1 = op.dense + (size_t)(r1 < rows ? r1 : r0) * ld;
-            const double* a2 = op.dense + (size_t)(r2 < rows ? r2 : r0) * ld;
-            const double* a3 = op.dense + (size_t)(r3 < rows ? r3 : r0) * ld;
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            LCQ_LOOP for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) {
-                const double vc = v[c];
-                const double m0 = a0[c], m1 = a1[c], m2 = a2[c], m3 = a3[c];
-                s0 += m0 * vc; s1 += m1 * vc; s2 += m2 * vc; s3 += m3 * vc;
+        LCQ_LOOP for (int r0 = LCQ_WARP; r0 < rows; r0 += 8 * LCQ_NWARP) {
+            double sm[8];
+            unsigned off[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int rk = r0 + k * LCQ_NWARP;
+                off[k] = (unsigned)(rk < rows ? rk : r0) * (unsigned)ld;
+                sm[k] = 0;
             }
-            s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+            LCQ_LOOP for (int c = LCQ_LANE; c < cols; c += LCQ_LANES) {
+                double mk[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) mk[k] = ldg64v(M + (off[k] + (unsigned)c));
+                const double vc = v[c];
+#pragma unroll
+                for (int k = 0; k < 8; k++) sm[k] += mk[k] * vc;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) sm[k] = warp_sum(sm[k]);
             if (LCQ_LANE == 0) {
-                out[r0] = LCQ_INIT(r0) + scale * s0;
-                if (r1 < rows) out[r1] = LCQ_INIT(r1) + scale * s1;
-                if (r2 < rows) out[r2] = LCQ_INIT(r2) + scale * s2;
-                if (r3 < rows) out[r3] = LCQ_INIT(r3) + scale * s3;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const int rk = r0 + k * LCQ_NWARP;
+                    if (rk < rows) out[rk] = LCQ_INIT(rk) + scale * sm[k];
+                }
             }
         }
     } else {
-        LCQ_LOOP for (int r = LCQ_TID; r < op.rows; r += LCQ_NT) {
-            double s = 0;
-            LCQ_LOOP for (int c = 0; c < op.cols; c++) s += op.dense[(size_t)c * op.ld + r] * v[c];
-            out[r] = LCQ_INIT(r) + scale * s;
+        const int rows = op.rows, cols = op.cols, ld = op.ld;
+        LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
+            double sacc = 0;
+            int c = 0;
+            LCQ_LOOP for (; c + 8 <= cols; c += 8) {
+                double mk[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) mk[k] = ldg64v(M + ((unsigned)(c + k) * (unsigned)ld + (unsigned)r));
+#pragma unroll
+                for (int k = 0; k < 8; k++) sacc += mk[k] * v[c + k];
+            }
+            LCQ_LOOP for (; c < cols; c++) sacc += ldg64v(M + ((unsigned)c * (unsigned)ld + (unsigned)r)) * v[c];
+            out[r] = LCQ_INIT(r) + scale * sacc;
         }
     }
+#else
+    if (!op.trans) {
+        LCQ_LOOP for (int r = 0; r < op.rows; r++) {
+            double sacc = 0;
+            LCQ_LOOP for (int c = 0; c < op.cols; c++) sacc += op.dense[(size_t)r * op.ld + c] * v[c];
+            out[r] = LCQ_INIT(r) + scale * sacc;
+        }
+    } else {
+        LCQ_LOOP for (int r = 0; r < op.rows; r++) {
+            double sacc = 0;
+            LCQ_LOOP for (int c = 0; c < op.cols; c++) sacc += op.dense[(size_t)c * op.ld + r] * v[c];
+            out[r] = LCQ_INIT(r) + scale * sacc;
+        }
+    }
+#endif
 #undef LCQ_INIT
 }
 
