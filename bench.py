@@ -352,8 +352,18 @@ def main():
         units_per_launch = n_units / world  # KKT solves (ADMM iterations + refined EQP passes) of one launch on one GPU
         flops_per_launch = units_per_launch * 2.0 * N * N
         achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
+        # DRAM traffic of the kernel per launch: bytes per LCQP from the committed ncu --set full capture
+        # (profiles/dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum / instances of that launch)
+        # scaled to the instances of one launch here; null when the summary is absent
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = float(json.load(open(tpath))["dram_bytes_per_lcqp"]) * batch
+            except Exception:
+                traffic = None
         roof = {"bound": "tensor", "achieved": achieved, "peak": bf16_tf, "unit": "TFLOP/s", "frac": achieved / bf16_tf,
-                "traffic": None, "kernel": "lcqp_solve_kernel", "kernel_ms": k_ms, "units_per_launch": units_per_launch,
+                "traffic": traffic, "kernel": "lcqp_solve_kernel", "kernel_ms": k_ms, "units_per_launch": units_per_launch,
                 "flop_per_unit": 2.0 * N * N, "peak_source": f"bf16_tflops_sustained of {peak_src}; arithmetic is fp64 (see DESIGN.md)"}
         # parity spot check inside the bench: instance 0 is the shipped x_ref=(0.5,-0.6)
         ok0 = bool(abs(x[0, 0] - 0.181110968) < 1e-6 and abs(x[0, 1] + 0.983483383) < 1e-6 and st["status"][0] == 4)
