@@ -183,6 +183,7 @@ LCQ_DEV Op dense_op(const double* M, int rows, int cols, int ld, int trans)
 struct Mats {
     double* P;      // n*n   D Q D
     double* A;      // m*n   E Ahat D
+    double* At;     // n*m   its transpose (dense operators read the output index contiguously)
     double* D;      // n
     double* E;      // m
     double* Hinv;   // n*n   (P + delta I)^-1
@@ -590,6 +591,58 @@ LCQ_DEVN void op_mv_t(const Op& opr, const double* v, const double* init, double
                 }
             }
         }
+    } else if (VS && !(op.ld & 1) && !(reinterpret_cast<uintptr_t>(M) & 15) && !(saddr(v) & 15u)) {
+        // out[r] = sum_c M[c*ld + r] v[c], v in shared memory: the scheme of sym_apply's L2 branch -- a pair of
+        // adjacent lanes owns outputs (2p, 2p+1) by 16-byte loads and splits the c range in two halves (the first
+        // of even length), twelve loads in flight per thread, one shuffle joins the halves
+        const int rows = op.rows, cols = op.cols;
+        const unsigned ldu = (unsigned)op.ld, vs = saddr(v);
+        const int npair = (rows + 1) >> 1;
+        int half = (((cols + 1) >> 1) + 1) & ~1;
+        if (half > cols) half = cols;
+        LCQ_LOOP for (int t0 = 0; t0 < 2 * npair; t0 += LCQ_NT) {
+            const int t = t0 + LCQ_TID;
+            const bool act = t < 2 * npair;
+            const int pr = t >> 1, h = t & 1;
+            int c = act ? (h ? half : 0) : 0;
+            const int c1 = act ? (h ? cols : half) : 0;
+            const double* p = M + (size_t)((unsigned)c * ldu + 2u * (unsigned)pr);
+            unsigned va = vs + 8u * (unsigned)c;
+            double x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+            LCQ_LOOP for (; c + 12 <= c1; c += 12) {
+                double m0[12], m1[12];
+#pragma unroll
+                for (int k = 0; k < 12; k++) { ldg128v(p, m0[k], m1[k]); p += ldu; }
+#pragma unroll
+                for (int k = 0; k < 12; k += 2) {
+                    double v0, v1;
+                    lds128v(va + 8u * k, v0, v1);
+                    x0 += m0[k] * v0; y0 += m1[k] * v0;
+                    x1 += m0[k + 1] * v1; y1 += m1[k + 1] * v1;
+                }
+                va += 96u;
+            }
+            LCQ_LOOP for (; c + 2 <= c1; c += 2) {
+                double m00, m10, m01, m11, v0, v1;
+                ldg128v(p, m00, m10); p += ldu;
+                ldg128v(p, m01, m11); p += ldu;
+                lds128(va, v0, v1);
+                va += 16u;
+                x0 += m00 * v0; y0 += m10 * v0;
+                x1 += m01 * v1; y1 += m11 * v1;
+            }
+            if (c < c1) {
+                double m0, m1;
+                ldg128v(p, m0, m1);
+                const double v0 = lds64(va);
+                x0 += m0 * v0; y0 += m1 * v0;
+            }
+            double sa = x0 + x1, sb = y0 + y1;
+            sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+            sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+            const int r = 2 * pr + h;
+            if (act && r < rows) out[r] = LCQ_INIT(r) + scale * (h ? sb : sa);
+        }
     } else {
         const int rows = op.rows, cols = op.cols, ld = op.ld;
         LCQ_LOOP for (int r = LCQ_TID; r < rows; r += LCQ_NT) {
@@ -675,6 +728,27 @@ LCQ_DEVN void op_mv_rows(const Op& opr, const int* idx, int na, const double* v,
 #ifndef LCQP_HOST_EMU
         LCQ_ASSUME_SHARED(idx); LCQ_ASSUME_SHARED(v); LCQ_ASSUME_SHARED(sub); LCQ_ASSUME_SHARED(out);
 #endif
+        if (op.trans) {
+            // M[r][c] = dense[c*ld + r]: one thread per selected row, eight loads in flight
+            LCQ_LOOP for (int a = LCQ_TID; a < na; a += LCQ_NT) {
+                const int r = idx[a];
+                const double* col = op.dense + r;
+                const int cols = op.cols, ld = op.ld;
+                double s = 0;
+                int c = 0;
+#ifndef LCQP_HOST_EMU
+                LCQ_LOOP for (; c + 8 <= cols; c += 8) {
+                    double mk[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) mk[k] = ldg64v(col + (unsigned)(c + k) * (unsigned)ld);
+#pragma unroll
+                    for (int k = 0; k < 8; k++) s += mk[k] * v[c + k];
+                }
+#endif
+                LCQ_LOOP for (; c < cols; c++) s += col[(size_t)c * ld] * v[c];
+                out[a] = s - (has_sub ? sub[r] : 0.0);
+            }
+        } else
         LCQ_LOOP for (int a = LCQ_WARP; a < na; a += LCQ_NWARP) {
             const int r = idx[a];
             const double* row = op.dense + (size_t)r * op.ld;
@@ -993,6 +1067,11 @@ LCQ_DEVN void prepare_scale(const Dims& d, const Inst& in, Mats& mt, double* v1,
         LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) mt.E[i] *= Et[i];
     }
     LCQ_SYNC();
+    LCQ_LOOP for (int e = LCQ_TID; e < m * n; e += LCQ_NT) {
+        const int j = e / m, i = e - j * m;
+        mt.At[e] = mt.A[(size_t)i * n + j];
+    }
+    LCQ_SYNC();
 }
 
 // Bounds of A_full = [A; L; R] (+ box rows) as setConstraints / setComplementarityBounds build them
@@ -1188,11 +1267,13 @@ LCQ_DEVN int prepare_factor(const Dims& d, Mats& mt, const signed char* ctype, c
 LCQ_DEV void mats_dense_ops(const Dims& d, Mats& mt)
 {
     const int n = d.n, m = d.m;
-    mt.oP = dense_op(mt.P, n, n, n, 0);
-    mt.oA = dense_op(mt.A, m, n, n, 0);
+    // every dense operator is applied in the form out[r] = sum_c M[c*ld + r] v[c] (coalesced, no cross-lane
+    // reduction): the symmetric ones as they are (P exactly symmetric, the inverses to rounding), A through At
+    mt.oP = dense_op(mt.P, n, n, n, 1);
+    mt.oA = dense_op(mt.At, m, n, m, 1);
     mt.oAt = dense_op(mt.A, n, m, n, 1);
-    mt.oHinv = dense_op(mt.Hinv, n, n, n, 0);
-    mt.oMinv = dense_op(mt.Minv, n, n, n, 0);
+    mt.oHinv = dense_op(mt.Hinv, n, n, n, 1);
+    mt.oMinv = dense_op(mt.Minv, n, n, n, 1);
 }
 
 // the operators of the static equality block need its order (known after prepare_factor)
@@ -1208,9 +1289,11 @@ LCQ_DEV void mats_dense_ops_post(const Dims& d, Mats& mt)
 LCQ_DEVN void mats_build_ops_pre(const Dims& d, Mats& mt, CsrPool& pool, Scalars* sc)
 {
     const int n = d.n, m = d.m;
-    const Op a = build_op(mt.P, n, n, n, 0, pool, sc);
-    const Op b = build_op(mt.A, m, n, n, 0, pool, sc);
+    Op a = build_op(mt.P, n, n, n, 0, pool, sc);
+    Op b = build_op(mt.A, m, n, n, 0, pool, sc);
     const Op c = build_op(mt.A, n, m, n, 1, pool, sc);
+    if (!a.rp) a = dense_op(mt.P, n, n, n, 1);     // dense fall-back: see mats_dense_ops
+    if (!b.rp) b = dense_op(mt.At, m, n, m, 1);
     if (LCQ_TID == 0) { mt.oP = a; mt.oA = b; mt.oAt = c; }
     LCQ_SYNC();
 }
@@ -1218,10 +1301,12 @@ LCQ_DEVN void mats_build_ops_pre(const Dims& d, Mats& mt, CsrPool& pool, Scalars
 LCQ_DEVN void mats_build_ops_post(const Dims& d, Mats& mt, CsrPool& pool, Scalars* sc)
 {
     const int n = d.n, m = d.m;
-    const Op a = build_op(mt.Hinv, n, n, n, 0, pool, sc);
+    Op a = build_op(mt.Hinv, n, n, n, 0, pool, sc);
     const Op b = build_op(mt.AHE, mt.mE, n, n, 0, pool, sc);
     const Op c = build_op(mt.AHE, n, mt.mE, n, 1, pool, sc);
-    const Op e = build_op(mt.Minv, n, n, n, 0, pool, sc);
+    Op e = build_op(mt.Minv, n, n, n, 0, pool, sc);
+    if (!a.rp) a = dense_op(mt.Hinv, n, n, n, 1);
+    if (!e.rp) e = dense_op(mt.Minv, n, n, n, 1);
     (void)m;
     if (LCQ_TID == 0) { mt.oHinv = a; mt.oAHE = b; mt.oAHtE = c; mt.oMinv = e; }
     LCQ_SYNC();
@@ -2344,7 +2429,7 @@ LCQ_DEV void carve(Work& w, const Dims& d, const SmemPlan& p, unsigned char* bas
 inline LCQ_HD size_t mats_doubles(const Dims& d)
 {
     const size_t n = d.n, m = d.m;
-    return 3 * ev(n * n) + 2 * ev(m * n) + ev(n) + ev(m) + ev(m * m) + ev((size_t)d.ldE * d.ldE) + ev((size_t)d.ldE * n) + ev((m + 1) / 2) /*eidx*/ + ev((m + 7) / 8) /*ctype*/ + 2;
+    return 3 * ev(n * n) + 3 * ev(m * n) + ev(n) + ev(m) + ev(m * m) + ev((size_t)d.ldE * d.ldE) + ev((size_t)d.ldE * n) + ev((m + 1) / 2) /*eidx*/ + ev((m + 7) / 8) /*ctype*/ + 2;
 }
 
 // every block starts on a 16-byte boundary (the store itself comes from cudaMalloc / an even offset)
@@ -2354,6 +2439,7 @@ LCQ_DEV void carve_mats(Mats& mt, double* base, const Dims& d)
     const size_t n = d.n, m = d.m;
     mt.P = base; base += ev(n * n);
     mt.A = base; base += ev(m * n);
+    mt.At = base; base += ev(m * n);
     mt.D = base; base += ev(n);
     mt.E = base; base += ev(m);
     mt.Hinv = base; base += ev(n * n);
