@@ -1,12 +1,18 @@
 // lcqp_device.cuh -- device code of the B200-native batched LCQP solver (sm_100a).
 //
-// One CTA owns one LCQP instance from loadLCQP to the stationarity classification: the whole
-// penalty-homotopy loop of LCQProblem::runSolver (/root/reference/src/LCQProblem.cpp:444-560) and the
-// convex QP under it run inside one persistent kernel; instances are pulled from a global work counter.
-// Per-instance iterates, bounds, working set and the inverse Schur complement of the working set live in
-// shared memory; the operators (matrices) are applied from global memory, where everything that a batch
-// shares (Q, A, L, R and all that is prepared from them) stays L2-resident and -- when it is sparse --
-// is applied in CSR form.
+// One GROUP of threads (128; up to four groups per CTA, each with its own named barrier) owns one LCQP instance
+// from loadLCQP to the stationarity classification: the whole penalty-homotopy loop of LCQProblem::runSolver
+// (/root/reference/src/LCQProblem.cpp:444-560) and the convex QP under it run inside one persistent kernel;
+// groups pull instances from a global work counter.  Per-instance iterates, bounds and working set live in
+// shared memory; the inverse Schur complement of the working set lives there too when it fits, else in a
+// per-group global scratch that stays in L2.  Operators that a batch shares (Q, A, L, R and all that is prepared
+// from them) are applied in CSR form from a shared-memory cache that the groups of a CTA share; per-instance
+// (dense) operators are applied from L2 in column form.
+//
+// The hot loops use explicit address spaces (inline PTX: ld.shared / ld.global with 32-bit shared addresses) and
+// issue their L2 loads as batches (ld.volatile.global: ptxas would otherwise sink each load to its use); the
+// solver state (struct QP) is in shared memory, not in the threads' local memory.  DESIGN.md section 5 has the
+// measurements behind each of these choices.
 //
 // The convex QP  min 1/2 x'Px + q'x  s.t. l <= Ahat x <= u  is solved EXACTLY (the contract of the
 // reference's qpOASES subsolver):
