@@ -140,6 +140,12 @@ __global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_solve_kernel(const __g
         if (g > 0 && threadIdx.x == 0) { mt = mt_s[0]; ro = ro_s[0]; }
         __syncthreads();
     }
+    // bounds shared by the batch: the one copy that the groups alias is written once, here
+    const bool bounds_ready = a.plan.bounds_shared != 0 && mt_s[0].status == 0;
+    if (bounds_ready) {
+        if (g == 0) { const Inst in0 = make_inst(a, 0); set_bounds(a.d, in0, mt.E, wk.l, wk.ub, wk.ctype, wk.sc, true); }
+        __syncthreads();
+    }
     const int nD = a.d.n + a.d.mA;
     const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (1u << LCQP_A);
     const bool raw_all_shared = (a.shared_mask & mat_bits) == mat_bits || (a.d.nC == 0 && (a.shared_mask & mat_bits) == (mat_bits & ~(1u << LCQP_A)));
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_solve_kernel(const __g
         LoopOut out;
         double* xo = a.xout + (size_t)b * a.d.n;
         double* yo = a.yout + (size_t)b * nD;
-        run_instance(s, mt, a.mats_shared != 0, in, ro, a.instance_offset + (unsigned long long)b, xo, yo, out);
+        run_instance(s, mt, a.mats_shared != 0, in, ro, a.instance_offset + (unsigned long long)b, xo, yo, out, bounds_ready);
 #ifdef LCQP_PROFILE
         LCQ_PROF(wk.sc, 13);
         if (threadIdx.x == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_prof[k], (unsigned long long)wk.sc->prof[k]);
@@ -585,7 +591,7 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     a.cache_bytes = 0; a.cache_what = 0; a.cache_offset = 0;
     const SmemPlan pmin = make_plan(d, 0, true);   // the instance's QP vectors only
     // Bounds that the whole batch shares (every bound array shared or absent, and shared scaling) scale to the
-    // same l / ub for every instance: the groups alias ONE copy (each group rewrites it with identical values).
+    // same l / ub for every instance: the groups alias ONE copy (written once per CTA before the instance loop).
     const unsigned bound_bits = (1u << LCQP_LBL) | (1u << LCQP_UBL) | (1u << LCQP_LBR) | (1u << LCQP_UBR) | (1u << LCQP_LBA) | (1u << LCQP_UBA) | (1u << LCQP_LB) | (1u << LCQP_UB);
     bool bounds_shared = can_cache;
     for (int k = 0; k < LCQP_NUM_ARRAYS; k++)

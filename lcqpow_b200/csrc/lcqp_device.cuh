@@ -1083,7 +1083,10 @@ LCQ_DEVN void prepare_scale(const Dims& d, const Inst& in, Mats& mt, double* v1,
 // Bounds of A_full = [A; L; R] (+ box rows) as setConstraints / setComplementarityBounds build them
 // (/root/reference/src/LCQProblem.cpp:584-608, 745-782), scaled by E, with OSQP's row types
 // (auxil.c:76-98).  Returns bit0: some l > u, bit1: a complementarity lower bound is -inf (:747,:767).
-LCQ_DEVN int set_bounds(const Dims& d, const Inst& in, const double* E, double* l, double* u, signed char* ctype, Scalars* sc)
+// store_lu = false: l / u already hold these values (one copy shared by the groups of the CTA, written before the
+// instance loop); only the row types and the flags are produced.
+LCQ_DEVN int set_bounds(const Dims& d, const Inst& in, const double* E, double* l, double* u, signed char* ctype, Scalars* sc,
+                        bool store_lu = true)
 {
     int bad = 0;
     LCQ_LOOP for (int i = LCQ_TID; i < d.m; i += LCQ_NT) {
@@ -1101,11 +1104,11 @@ LCQ_DEVN int set_bounds(const Dims& d, const Inst& in, const double* E, double* 
         if (lo > up) bad |= 1;
         const bool linf = !(lo > -kQPInf), uinf = !(up < kQPInf);
         const double Ei = E[i];
-        l[i] = linf ? -INFINITY : lo * Ei;
-        u[i] = uinf ? INFINITY : up * Ei;
+        const double li = linf ? -INFINITY : lo * Ei, ui = uinf ? INFINITY : up * Ei;
+        if (store_lu) { l[i] = li; u[i] = ui; }
         signed char t = 0;
         if (linf && uinf) t = -1;
-        else if (!linf && !uinf && u[i] - l[i] < kRhoTol) t = 1;
+        else if (!linf && !uinf && ui - li < kRhoTol) t = 1;
         ctype[i] = t;
     }
     (void)sc;
@@ -2465,7 +2468,7 @@ LCQ_DEV void carve_mats(Mats& mt, double* base, const Dims& d)
 // `mats_shared`: mt was prepared by the batch-level prepare step; otherwise this CTA prepares it here.
 // ------------------------------------------------------------------------------------------------
 LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, const RawOps& ro, unsigned long long instance,
-                           double* xo, double* yo, LoopOut& out)
+                           double* xo, double* yo, LoopOut& out, bool bounds_ready = false)
 {
     const Dims& d = *s.d;
     const Work& w = *s.w;
@@ -2486,7 +2489,7 @@ LCQ_DEVN void run_instance(QP& s, Mats& mt, bool mats_shared, const Inst& in, co
             if (LCQ_TID == 0) mats_dense_ops(d, mt);
             LCQ_SYNC();
         }
-        const int bflags = set_bounds(d, in, mt.E, w.l, w.ub, w.ctype, w.sc);
+        const int bflags = set_bounds(d, in, mt.E, w.l, w.ub, w.ctype, w.sc, !bounds_ready);
         if (bflags & 2) { out.ret = RET_INVALID_LOWER_COMP; skip = true; }  // loadLCQP fails (:747,:767)
         const bool infeasible = (bflags & 1) != 0;
         if (!skip && !infeasible) {
