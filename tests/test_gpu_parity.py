@@ -96,6 +96,28 @@ def test_circle_family_trajectories_match_oracle(oracle):
         assert bad.size == 0, (f, bad.tolist())
     assert np.abs(x - so.x).max() <= 1e-8 * max(1.0, np.abs(so.x).max())
 
+
+def test_circle_large_batch_properties():
+    """C2 at a bench-like size (4096 instances, the vectorised generator of bench.py) through size-independent
+    properties: every instance ends SUCCESSFUL_RETURN and S-stationary (as every reference qpOASES run of this
+    family does), satisfies the circle constraints A x = 1 and the complementarity of each pair, instance 0 is
+    the shipped solution (examples/OptimizeOnCircle.cpp: x = (0.1811, -0.9835)), and duplicated instances give
+    bit-identical results wherever they sit in the batch (groups pull instances dynamically)."""
+    from lcqpow_b200 import problems as P
+    pb = P.circle_batch_fast(4096).normalised()
+    g = pb.g.copy(); x0 = pb.x0.copy()
+    g[4095] = g[7]; x0[4095] = x0[7]          # a duplicate far away in the batch
+    import dataclasses
+    pb = dataclasses.replace(pb, g=g, x0=x0)
+    x, y, st, _ = _solve_cuda(pb, {"stationarityTolerance": 10e-3}, perturb=0)
+    assert (st["ret"] == 0).all() and (st["status"] == 4).all()
+    assert abs(x[0, 0] - 0.181110968) < 1e-6 and abs(x[0, 1] + 0.983483383) < 1e-6
+    A = pb.A.reshape(pb.nC, pb.nV)
+    assert np.abs(x @ A.T - 1.0).max() <= 1e-8
+    u, v = x[:, 2::2], x[:, 3::2]
+    assert (u >= -1e-9).all() and (v >= -1e-9).all() and np.abs(u * v).sum(axis=1).max() < 1e-9
+    assert np.array_equal(x[7], x[4095]) and int(st["iterTotal"][7]) == int(st["iterTotal"][4095])
+
 def test_large_batch_properties():
     """Full-size behaviour through size-independent properties: every solved instance is complementary
     (phi < tol), feasible, and a re-run is bit-identical (deterministic reductions)."""
