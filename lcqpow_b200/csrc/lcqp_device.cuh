@@ -154,6 +154,7 @@ constexpr double kMinScaling = 1e-4;     // constants.h:94
 constexpr double kMaxScaling = 1e4;
 constexpr int kScalingIters = 10;        // constants.h:56
 constexpr int kMaxLeyffer = 16;
+constexpr double kFloorTol = 1e-11;       // KKT residual below which refinement is at its round-off floor
 constexpr double kResTol = 1e-9;         // residual of an EQP solve that still counts as solved
 constexpr int kLongRow = 32;             // CSR rows longer than this are reduced by a warp
 
@@ -1830,7 +1831,10 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] -= w.dx[j];
             LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] -= w.dlam[i];
             LCQ_SYNC();
-            kkt_residual(s, W, w.xa, w.lam);
+            // At the round-off floor (both residuals tiny) zx and r1 of the point just tried differ from those of
+            // the restored point by the size of the last correction, far below every tolerance of kkt_check:
+            // they are not recomputed.
+            if (!(best < kFloorTol && rn < kFloorTol)) kkt_residual(s, W, w.xa, w.lam);
             converged = true;
         } else {
             // A correction that barely helps means the remaining residual lies along directions whose
