@@ -15,6 +15,7 @@
 
 #include <chrono>
 #include <cstring>
+#include <vector>
 
 extern "C" {
 #include <osqp.h>
@@ -50,6 +51,35 @@ typedef struct {
     double rhoOpt;
     double seconds;   /* wall time of loadLCQP + (switchToSparseMode) + runSolver */
 } lcqp_ref_result;
+
+/* Debug door for the parity work (tests/ only): qpOASES print level of the next solves (its own
+ * per-iteration table, PL_TABULAR = -1, goes to stdout) and whether the outer loop records its iterates
+ * (Options::setStoreSteps).  The recorded run is read back with lcqpow_ref_last_trace. */
+static int g_qpoases_print_level = 0; /* qpOASES::PL_NONE */
+static int g_store_steps = 0;
+static std::vector<double> g_trace_x, g_trace_alpha, g_trace_stat;
+static std::vector<int> g_trace_sub;
+static int g_trace_nV = 0;
+
+void lcqpow_ref_set_debug(int qpoases_print_level, int store_steps)
+{
+    g_qpoases_print_level = qpoases_print_level;
+    g_store_steps = store_steps;
+}
+
+/* Copies the iterates of the last solve: xsteps[step][nV], sub[step] (qp iterations of that pass),
+ * alpha[step], stat[step].  Returns the number of recorded steps (may exceed cap: only cap are copied). */
+int lcqpow_ref_last_trace(int cap, double* xsteps, int* sub, double* alpha, double* stat)
+{
+    const int ns = (int)g_trace_sub.size();
+    for (int s = 0; s < ns && s < cap; s++) {
+        if (xsteps) std::memcpy(xsteps + (size_t)s * g_trace_nV, &g_trace_x[(size_t)s * g_trace_nV], sizeof(double) * g_trace_nV);
+        if (sub) sub[s] = g_trace_sub[s];
+        if (alpha) alpha[s] = g_trace_alpha[s];
+        if (stat) stat[s] = g_trace_stat[s];
+    }
+    return ns;
+}
 
 void lcqpow_ref_default_options(lcqp_ref_options* o)
 {
@@ -102,6 +132,12 @@ int lcqpow_ref_solve(int nV, int nC, int nComp,
         OSQPSettings* s = options.getOSQPOptions();
         s->adaptive_rho_interval = o->osqp_adaptive_rho_interval;
     }
+    if (g_qpoases_print_level != 0) {
+        qpOASES::Options qo = options.getqpOASESOptions();
+        qo.printLevel = (qpOASES::PrintLevel)g_qpoases_print_level;
+        options.setqpOASESOptions(qo);
+    }
+    if (g_store_steps) options.setStoreSteps(true);
     lcqp.setOptions(options);
 
     ReturnValue rv = lcqp.loadLCQP(Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0);
@@ -132,6 +168,14 @@ int lcqpow_ref_solve(int nV, int nC, int nComp,
     res->qpExitFlag = stats.getQPSolverExitFlag();
     res->rhoOpt = stats.getRhoOpt();
     res->seconds = std::chrono::duration<double>(t1 - t0).count();
+    if (g_store_steps) {
+        g_trace_nV = nV;
+        g_trace_x.clear();
+        for (const std::vector<double>& xs : stats.getxStepsStdVec()) g_trace_x.insert(g_trace_x.end(), xs.begin(), xs.end());
+        g_trace_sub = stats.getSubproblemItersStdVec();
+        g_trace_alpha = stats.getStepLengthStdVec();
+        g_trace_stat = stats.getStatValsStdVec();
+    }
     return res->ret;
 }
 

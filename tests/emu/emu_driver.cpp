@@ -9,7 +9,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../lcqpow_b200/csrc/lcqp_device.cuh"
+#include "../../lcqpow_b200/csrc/lcqp_pas.cuh"
 
 using namespace lcqp;
 
@@ -32,7 +32,7 @@ static size_t field_len(int k, int n, int c, int p)
 static unsigned long long g_instance_offset = 0;
 extern "C" void lcqp_emu_set_instance_offset(unsigned long long off) { g_instance_offset = off; }
 
-extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsigned shared_mask_in,
+static int legacy_solve_batch(int batch, int nV, int nC, int nComp, unsigned shared_mask_in,
                                     const double* Q, const double* g, const double* L, const double* R,
                                     const double* lbL, const double* ubL, const double* lbR, const double* ubR,
                                     const double* A, const double* lbA, const double* ubA,
@@ -122,6 +122,105 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
         st.rhoOpt = out.rhoOpt; st.admmIters = (double)s.n_admm;
         res[b] = st;
         nfail += (out.ret != 0);
+    }
+    return nfail;
+}
+
+// ---- the parametric active-set path (lcqp_pas.cuh), driven the way lcqp_cabi.cu drives it: the equality mask over the
+// batch, batch-level preparation when Q/A/L/R are shared, then pas_run_instance per instance.  Instances whose Hessian is
+// not positive definite (status 1) go to the regularised solver above, as in the product.
+static long long g_last_solves = 0, g_last_changes = 0, g_last_polish = 0;
+extern "C" void lcqp_emu_last_counts(long long* solves, long long* changes, long long* polish)
+{
+    *solves = g_last_solves; *changes = g_last_changes; *polish = g_last_polish;
+}
+
+extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsigned shared_mask_in,
+                                    const double* Q, const double* g, const double* L, const double* R,
+                                    const double* lbL, const double* ubL, const double* lbR, const double* ubR,
+                                    const double* A, const double* lbA, const double* ubA,
+                                    const double* lb, const double* ub, const double* x0, const double* y0,
+                                    const lcqp_cuda_options* o, double* x, double* y, lcqp_cuda_stats* res)
+{
+    using namespace lcqp::pas;
+    if (getenv("LCQP_EMU_LEGACY"))
+        return legacy_solve_batch(batch, nV, nC, nComp, shared_mask_in, Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0, o, x, y, res);
+    const double* base[LCQP_NUM_ARRAYS] = {Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0};
+    const PDims d = make_pdims(nV, nC, nComp, (o->qpSolver != 2) && (lb || ub));
+    Dims dold = make_dims(nV, nC, nComp, d.has_box);
+    const unsigned all_bits = (1u << LCQP_NUM_ARRAYS) - 1u;
+    const unsigned shared_mask = (batch == 1) ? all_bits : shared_mask_in;
+    const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (nC > 0 ? (1u << LCQP_A) : 0u);
+    const bool mats_shared = (shared_mask & mat_bits) == mat_bits;
+    auto inst = [&](int b) {
+        Inst in;
+        const double** p = reinterpret_cast<const double**>(&in);
+        for (int k = 0; k < LCQP_NUM_ARRAYS; k++)
+            p[k] = base[k] ? base[k] + (((shared_mask >> k) & 1u) ? 0 : field_len(k, nV, nC, nComp) * (size_t)b) : nullptr;
+        return in;
+    };
+    Scalars sc;
+    const size_t pool_cap = 4 * ((size_t)d.n * d.n + 3 * (size_t)d.m * d.n) / 4 + 64ull * (d.m + d.n) + 4096;
+    std::vector<int> pool_i(pool_cap);
+    std::vector<double> pool_d(pool_cap);
+    int pool_used[2] = {0, 0};
+    CsrPool pool = {pool_i.data(), pool_d.data(), (int)pool_cap, (int)pool_cap, pool_used};
+    std::vector<double> store(pmats_doubles(d));
+    std::vector<double> v1(d.n + d.m + 2), v2(d.n + d.m + 2);
+    std::vector<signed char> eq(d.m + 16);
+    PMats mt;
+    carve_pmats(mt, store.data(), d);
+    RawOps ro;
+    {
+        const Inst in0 = inst(0);
+        raw_build_ops(dold, in0, ro, shared_mask, pool, &sc);
+        if (mats_shared) {
+            // rows that are equalities (l == u, finite) in every instance
+            for (int r = 0; r < d.m; r++) {
+                int all = 1;
+                for (int b = 0; b < batch && all; b++) { const Inst in = inst(b); double lo, up; row_bounds(d, in, r, lo, up); all = (lo == up && lo > -qINFTY && lo < qINFTY); }
+                eq[r] = (signed char)all;
+            }
+            pas_prepare(d, in0, mt, eq.data(), &sc);
+            if (mt.status == 0) { pmats_dense_ops(d, mt); pmats_build_ops(d, mt, pool, &sc); }
+        }
+    }
+    if (mats_shared && mt.status == 1)
+        return legacy_solve_batch(batch, nV, nC, nComp, shared_mask_in, Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0, o, x, y, res);
+    const int mEc = mats_shared ? mt.mE : (d.m < d.n ? d.m : d.n);
+    const int mIc = mats_shared ? mt.mI : d.m;
+    const int capc = mats_shared ? pas_cap(d, mt.mE, mt.mI) : ((d.n < d.m) ? d.n : d.m);
+    std::vector<double> smem_d(pas_smem_bytes(mIc, capc) / 8 + 8);
+    std::vector<double> gl(pas_gl_doubles(d, mEc, capc) + 8);
+    PWork wk;
+    pas_carve(wk, d, mEc, mIc, capc, reinterpret_cast<unsigned char*>(smem_d.data()), gl.data());
+    PQP s;
+    s.d = &d; s.o = o; s.w = &wk; s.mt = &mt;
+    const int nD = nV + nC + 2 * nComp;
+    int nfail = 0;
+    g_last_solves = g_last_changes = g_last_polish = 0;
+    for (int b = 0; b < batch; b++) {
+        const Inst in = inst(b);
+        s.in = &in;
+        raw_dense_ops(dold, in, ro, shared_mask);
+        LoopOut out;
+        const bool ok = pas_run_instance(s, mt, mats_shared, ro, g_instance_offset + (unsigned long long)b, x + (size_t)b * nV, y + (size_t)b * nD, out, eq.data());
+        if (!ok) {   // semidefinite Hessian of this instance: the regularised solver
+            const unsigned one_all = all_bits;
+            legacy_solve_batch(1, nV, nC, nComp, one_all, in.Q, in.g, in.L, in.R, in.lbL, in.ubL, in.lbR, in.ubR, in.A, in.lbA, in.ubA, in.lb, in.ub, in.x0, in.y0, o,
+                               x + (size_t)b * nV, y + (size_t)b * nD, res + b);
+            nfail += (res[b].ret != 0);
+            continue;
+        }
+        lcqp_cuda_stats st;
+        st.ret = out.ret; st.status = out.status; st.iterTotal = out.iterTotal; st.iterOuter = out.iterOuter;
+        st.subproblemIter = out.subIter; st.qpExitFlag = out.exitFlag;
+        st.nDuals = (o->qpSolver == 2) ? d.mA : nD;
+        st.kktSolves = (int)s.n_solve;
+        st.rhoOpt = out.rhoOpt; st.admmIters = 0.0;
+        res[b] = st;
+        nfail += (out.ret != 0);
+        g_last_solves += s.n_solve; g_last_changes += s.n_change; g_last_polish += s.n_polish;
     }
     return nfail;
 }
