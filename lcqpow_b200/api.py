@@ -230,6 +230,8 @@ class LCQProblemBatch:
         not named in ``shared``.  Host numpy arrays (row-major fp64)."""
         vals = dict(Q=Q, g=g, L=L, R=R, lbL=lbL, ubL=ubL, lbR=lbR, ubR=ubR, A=A, lbA=lbA, ubA=ubA, lb=lb, ub=ub, x0=x0, y0=y0)
         batch = self.capacity if batch is None else batch
+        if batch <= 0 or batch > self.capacity:
+            raise ValueError(f"loadLCQP: batch {batch} outside 1..{self.capacity}")
         mask = 0
         arrs = []
         for k, f in enumerate(FIELDS):
@@ -240,12 +242,23 @@ class LCQProblemBatch:
             a = np.ascontiguousarray(a, dtype=np.float64)
             if f in shared:
                 mask |= 1 << k
+            # the library copies field_len * (1 | batch) doubles from this buffer: a short array would be read
+            # past its end
+            want = self._field_len(f) * (1 if (f in shared or batch == 1) else batch)
+            if a.size != want:
+                raise ValueError(f"loadLCQP: {f} has {a.size} entries, expected {want} "
+                                 f"({'shared' if f in shared else 'batch of ' + str(batch)})")
             arrs.append(a)
         self._keep = arrs
         rc = self.lib.lcqp_cuda_load(self.h, batch, mask, *[_as_ptr(a) for a in arrs])
         if rc == 0:
             self.batch = batch
         return rc
+
+    def _field_len(self, f: str) -> int:
+        n, c, p = self.nV, self.nC, self.nComp
+        return {"Q": n * n, "g": n, "L": p * n, "R": p * n, "lbL": p, "ubL": p, "lbR": p, "ubR": p,
+                "A": c * n, "lbA": c, "ubA": c, "lb": n, "ub": n, "x0": n, "y0": n + c + 2 * p}[f]
 
     def loadBatch(self, pb) -> int:
         """Load an lcqpow_b200.problems.LCQPBatch."""

@@ -9,7 +9,7 @@
 #include <string>
 #include <vector>
 
-#include "lcqp_device.cuh"
+#include "lcqp_pas.cuh"
 
 namespace lcqp {
 
@@ -184,6 +184,149 @@ __global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_solve_kernel(const __g
     }
 }
 
+// =================================================================================================
+// The parametric active-set path (lcqp_pas.cuh)
+// =================================================================================================
+constexpr int kPasGroupsMax = 8;
+
+struct PasArgs {
+    pas::PDims d;
+    lcqp_cuda_options o;
+    const double* arr[LCQP_NUM_ARRAYS];
+    unsigned long long stride[LCQP_NUM_ARRAYS];  // 0 when shared
+    int batch;
+    unsigned shared_mask;
+    int mats_shared;
+    int bounds_vary;             // some bound array has one copy per instance
+    pas::PMats* shared_mats;     // prepared operands of the batch (device struct)
+    RawOps* shared_raw;
+    double* shared_store;
+    signed char* eqmask;         // m: row is an equality in every instance
+    CsrPool pool;
+    int mEc, mIc, capc;          // sizes the per-group buffers were carved for
+    unsigned long long group_smem;    // dynamic shared memory per group
+    double* workspace;
+    unsigned long long ws_stride;     // doubles per group
+    unsigned long long ws_mats;       // doubles of the per-group PMats block (0 when shared)
+    double* xout;
+    double* yout;
+    lcqp_cuda_stats* stats;
+    unsigned int* counter;
+    int* fallback_flag;          // set when an instance's reduced Hessian is not positive definite
+    unsigned long long instance_offset;
+};
+
+__device__ __forceinline__ Inst pas_make_inst(const PasArgs& a, int b)
+{
+    Inst in;
+    const double** p = reinterpret_cast<const double**>(&in);
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) p[k] = a.arr[k] ? a.arr[k] + a.stride[k] * (unsigned long long)b : nullptr;
+    return in;
+}
+
+// eqmask[r] stays 1 only if row r has l = u (finite) in every instance
+__global__ void pas_eqmask_kernel(const __grid_constant__ PasArgs a)
+{
+    const int nb = a.bounds_vary ? a.batch : 1;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const Inst in = pas_make_inst(a, b);
+        for (int r = threadIdx.x; r < a.d.m; r += blockDim.x) {
+            double lo, up;
+            pas::row_bounds(a.d, in, r, lo, up);
+            if (!(lo == up && lo > -pas::qINFTY && lo < pas::qINFTY)) a.eqmask[r] = 0;
+        }
+    }
+}
+
+// Batch-level preparation by one CTA: CSR copies of the shared unscaled matrices (outer loop) and, when Q, L, R
+// and A are all shared, the prepared operands of the subsolver.
+__global__ void __launch_bounds__(kPrepThreads) pas_prepare_kernel(const __grid_constant__ PasArgs a)
+{
+    __shared__ pas::PMats mt;
+    __shared__ RawOps ro;
+    __shared__ Scalars sc;
+    CsrPool pool = a.pool;
+    if (threadIdx.x == 0) { pool.used[0] = 0; pool.used[1] = 0; }
+    __syncthreads();
+    const Inst in = pas_make_inst(a, 0);
+    const Dims dold = make_dims(a.d.n, a.d.nC, a.d.nComp, a.d.has_box);
+    raw_build_ops(dold, in, ro, a.shared_mask, pool, &sc);
+    if (threadIdx.x == 0) *a.shared_raw = ro;
+    if (a.mats_shared) {
+        if (threadIdx.x == 0) pas::carve_pmats(mt, a.shared_store, a.d);
+        __syncthreads();
+        pas::pas_prepare(a.d, in, mt, a.eqmask, &sc);
+        if (mt.status == 0) {
+            if (threadIdx.x == 0) pas::pmats_dense_ops(a.d, mt);
+            __syncthreads();
+            pas::pmats_build_ops(a.d, mt, pool, &sc);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) *a.shared_mats = mt;
+    }
+}
+
+// The solver: persistent CTAs of blockDim.y groups x blockDim.x threads; every group works on one LCQP instance at a
+// time (pulled from a global counter) with its own control flow and its own named barrier.
+__global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_pas_kernel(const __grid_constant__ PasArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ pas::PMats mt_s[kPasGroupsMax];
+    __shared__ RawOps ro_s[kPasGroupsMax];
+    __shared__ pas::PWork wk_s[kPasGroupsMax];
+    __shared__ pas::PQP qp_s[kPasGroupsMax];
+    __shared__ Inst in_s[kPasGroupsMax];
+    __shared__ pas::PDims dm;
+    __shared__ lcqp_cuda_options opt;
+    const int g = threadIdx.y, G = blockDim.y;
+    pas::PMats& mt = mt_s[g];
+    RawOps& ro = ro_s[g];
+    pas::PWork& wk = wk_s[g];
+    pas::PQP& s = qp_s[g];
+    double* ws = a.workspace + a.ws_stride * ((unsigned long long)blockIdx.x * G + g);
+    if (threadIdx.x == 0) {
+        if (g == 0) { dm = a.d; opt = a.o; }
+        s.d = &dm; s.o = &opt; s.w = &wk; s.mt = &mt; s.in = &in_s[g];
+        s.nw = 0; s.n_solve = 0; s.n_change = 0; s.n_polish = 0; s.nwsr = 0;
+        pas::pas_carve(wk, a.d, a.mEc, a.mIc, a.capc, smem + (size_t)g * a.group_smem, ws + a.ws_mats);
+        if (a.mats_shared) mt = *a.shared_mats;
+        else pas::carve_pmats(mt, ws, a.d);
+        ro = *a.shared_raw;
+    }
+    __syncthreads();
+    const int nD = a.d.n + a.d.mA;
+    const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (1u << LCQP_A);
+    const bool raw_all_shared = (a.shared_mask & mat_bits) == mat_bits || (a.d.nC == 0 && (a.shared_mask & mat_bits) == (mat_bits & ~(1u << LCQP_A)));
+    const Dims dold = make_dims(a.d.n, a.d.nC, a.d.nComp, a.d.has_box);
+    signed char* eq_scratch = reinterpret_cast<signed char*>(wk.tm2);   // free until the first QP of an instance
+    for (;;) {
+        LCQ_SYNC();
+        if (threadIdx.x == 0) wk.sc->bidx = (int)atomicAdd(a.counter, 1u);
+        LCQ_SYNC();
+        const int b = wk.sc->bidx;
+        if (b >= a.batch) break;
+        if (threadIdx.x == 0) {
+            in_s[g] = pas_make_inst(a, b);
+            if (!raw_all_shared) raw_dense_ops(dold, in_s[g], ro, a.shared_mask);
+        }
+        LCQ_SYNC();
+        LoopOut out;
+        double* xo = a.xout + (size_t)b * a.d.n;
+        double* yo = a.yout + (size_t)b * nD;
+        const bool ok = pas::pas_run_instance(s, mt, a.mats_shared != 0, ro, a.instance_offset + (unsigned long long)b, xo, yo, out, eq_scratch);
+        if (threadIdx.x == 0) {
+            lcqp_cuda_stats st;
+            st.ret = ok ? out.ret : -1; st.status = out.status; st.iterTotal = out.iterTotal; st.iterOuter = out.iterOuter;
+            st.subproblemIter = out.subIter; st.qpExitFlag = out.exitFlag;
+            st.nDuals = (a.o.qpSolver == 2) ? a.d.mA : nD;
+            st.kktSolves = (int)s.n_solve;
+            st.rhoOpt = out.rhoOpt; st.admmIters = 0.0;
+            a.stats[b] = st;
+            if (!ok) atomicExch(a.fallback_flag, 1);
+        }
+    }
+}
+
 // ---- plugin door: one QP with persistent state ----------------------------------------------------
 struct QPState {
     int nw, have_W, tinv_valid, prepared;
@@ -303,6 +446,19 @@ struct lcqp_cuda_handle_s {
     cudaStream_t last_stream = nullptr;
     unsigned long long instance_offset = 0;
     int last_grid = 0, last_smem = 0, last_mE = 0;
+    // parametric active-set path
+    cudaStream_t load_stream = nullptr;   // copies + preparation of a load (lcqp_cuda_load returns when they are done)
+    pas::PMats* pas_mats = nullptr;       // device header of the prepared operands
+    pas::PMats* pas_host = nullptr;       // pinned read-back (mE, mI, status)
+    double* pas_store = nullptr;
+    size_t pas_store_cap = 0;
+    signed char* eqmask = nullptr;
+    size_t eqmask_cap = 0;
+    int* fallback_flag = nullptr;
+    int* fallback_host = nullptr;         // pinned
+    bool pas_ready = false;               // prepared for the current load
+    bool use_legacy = false;              // reduced Hessian not positive definite: the regularised solver runs
+    int has_box = 0;
     std::string err;
 };
 
@@ -392,6 +548,11 @@ int lcqp_cuda_create(int nV, int nC, int nComp, int batch_capacity, int device, 
               cudaMalloc(&h->shared_raw, sizeof(RawOps)) == cudaSuccess &&
               cudaMalloc(&h->pool_used, 2 * sizeof(int)) == cudaSuccess &&
               cudaMallocHost(&h->host_mats, sizeof(Mats)) == cudaSuccess &&
+              cudaMalloc(&h->pas_mats, sizeof(pas::PMats)) == cudaSuccess &&
+              cudaMallocHost(&h->pas_host, sizeof(pas::PMats)) == cudaSuccess &&
+              cudaMalloc(&h->fallback_flag, sizeof(int)) == cudaSuccess &&
+              cudaMallocHost(&h->fallback_host, sizeof(int)) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&h->load_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess &&
               cudaEventCreate(&h->ev2) == cudaSuccess;
     if (!ok) { cudaGetLastError(); lcqp_cuda_destroy(h); return LCQP_CUDA_OUT_OF_MEMORY; }
@@ -408,11 +569,22 @@ int lcqp_cuda_destroy(lcqp_cuda_handle h)
     cudaFree(h->shared_store); cudaFree(h->shared_mats); cudaFree(h->shared_raw);
     cudaFree(h->pool_i); cudaFree(h->pool_d); cudaFree(h->pool_used); cudaFree(h->workspace);
     if (h->host_mats) cudaFreeHost(h->host_mats);
+    cudaFree(h->pas_mats); cudaFree(h->pas_store); cudaFree(h->eqmask); cudaFree(h->fallback_flag);
+    if (h->pas_host) cudaFreeHost(h->pas_host);
+    if (h->fallback_host) cudaFreeHost(h->fallback_host);
+    if (h->load_stream) cudaStreamDestroy(h->load_stream);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->ev2) cudaEventDestroy(h->ev2);
     delete h;
     return LCQP_CUDA_OK;
+}
+
+// knobs of the regularised solver (semidefinite Hessians): a non-positive interval would spin its ADMM loop forever
+static bool qp_knobs_valid(const lcqp_cuda_options* o)
+{
+    return o->qp_check_interval >= 1 && o->qp_max_iter >= 1 && o->qp_rho > 0 && o->qp_sigma > 0 && o->qp_delta > 0 && o->qp_alpha > 0 &&
+           o->qp_alpha < 2 && o->qp_refine_iter >= 0;
 }
 
 int lcqp_cuda_set_options(lcqp_cuda_handle h, const lcqp_cuda_options* o)
@@ -429,14 +601,20 @@ int lcqp_cuda_set_options(lcqp_cuda_handle h, const lcqp_cuda_options* o)
     if (o->etaDynamicPenalty <= 0 || o->etaDynamicPenalty >= 1) return 119;
     if (o->qpSolver < 0 || o->qpSolver > 2) return 109;
     if (o->nDynamicPenalty > kMaxLeyffer) return LCQP_CUDA_BAD_ARGUMENT;
+    if (!qp_knobs_valid(o)) return LCQP_CUDA_BAD_ARGUMENT;
     h->opts = *o;
     return LCQP_CUDA_OK;
 }
+
+static int pas_prepare_load(lcqp_cuda_handle h);
 
 static int load_common(lcqp_cuda_handle h, int batch, unsigned shared_mask, const double* const* ptr, bool device_ptrs)
 {
     if (!h) return LCQP_CUDA_BAD_HANDLE;
     if (batch <= 0 || batch > h->capacity) return fail(h, LCQP_CUDA_BAD_ARGUMENT, "batch out of range");
+    // a previous run may still be reading the staging buffers
+    if (h->ran && h->last_stream != nullptr) cudaStreamSynchronize(h->last_stream);
+    else if (h->ran) cudaDeviceSynchronize();
     // loadLCQP argument checks (LCQProblem.cpp:87-144, :563-626, LCQProblem.ipp:39-50)
     if (!ptr[LCQP_Q]) return fail(h, LCQP_CUDA_BAD_ARGUMENT, "Q is NULL");
     if (!ptr[LCQP_G]) return 116;                                    // INVALID_OBJECTIVE_LINEAR_TERM
@@ -455,13 +633,22 @@ static int load_common(lcqp_cuda_handle h, int batch, unsigned shared_mask, cons
             if (cudaMalloc(&h->own_in[k], want * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(input)"); }
             h->own_in_cap[k] = want;
         }
-        CK(cudaMemcpyAsync(h->own_in[k], ptr[k], count * sizeof(double), cudaMemcpyHostToDevice, 0), LCQP_CUDA_LAUNCH_FAILED);
+        CK(cudaMemcpyAsync(h->own_in[k], ptr[k], count * sizeof(double), cudaMemcpyHostToDevice, h->load_stream), LCQP_CUDA_LAUNCH_FAILED);
         h->dev_in[k] = h->own_in[k];
     }
     h->batch = batch;
     h->shared_mask = shared_mask;
     h->loaded = true;
     h->ran = false;
+    h->pas_ready = false;
+    // a load is complete when it returns: the copies are done (the caller may reuse its buffers, and any stream may
+    // run the batch) and the batch-level operands are prepared, so that lcqp_cuda_run is one asynchronous launch
+    const int rc = pas_prepare_load(h);
+    if (rc != LCQP_CUDA_OK) return rc;
+    CK(cudaStreamSynchronize(h->load_stream), LCQP_CUDA_LAUNCH_FAILED);
+    h->use_legacy = (h->pas_host->status == 1);
+    if (h->pas_host->status > 1) return fail(h, LCQP_CUDA_LAUNCH_FAILED, "preparation of the shared operands failed");
+    h->pas_ready = true;
     return LCQP_CUDA_OK;
 }
 
@@ -492,13 +679,8 @@ int lcqp_cuda_set_instance_offset(lcqp_cuda_handle h, unsigned long long off)
     return LCQP_CUDA_OK;
 }
 
-int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
+static int run_legacy(lcqp_cuda_handle h, cudaStream_t stream)
 {
-    if (!h) return LCQP_CUDA_BAD_HANDLE;
-    if (!h->loaded) return fail(h, LCQP_CUDA_NOT_LOADED, "run before load");
-    cudaStream_t stream = (cudaStream_t)stream_v;
-    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
-
     KernelArgs a;
     memset(&a, 0, sizeof(a));
     Dims& d = a.d;
@@ -689,6 +871,156 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     return LCQP_CUDA_OK;
 }
 
+// ---- the parametric active-set path -----------------------------------------------------------------------
+static void pas_fill_args(lcqp_cuda_handle h, PasArgs& a)
+{
+    memset(&a, 0, sizeof(a));
+    a.d = pas::make_pdims(h->nV, h->nC, h->nComp, h->has_box);
+    a.o = h->opts;
+    unsigned bound_bits = (1u << LCQP_LBL) | (1u << LCQP_UBL) | (1u << LCQP_LBR) | (1u << LCQP_UBR) | (1u << LCQP_LBA) | (1u << LCQP_UBA) | (1u << LCQP_LB) | (1u << LCQP_UB);
+    const unsigned all_bits = (1u << LCQP_NUM_ARRAYS) - 1u;
+    a.shared_mask = (h->batch == 1) ? all_bits : h->shared_mask;
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) {
+        a.arr[k] = h->dev_in[k];
+        a.stride[k] = ((a.shared_mask >> k) & 1u) ? 0ull : (unsigned long long)field_len(k, h->nV, h->nC, h->nComp);
+        if (((bound_bits >> k) & 1u) && h->dev_in[k] && a.stride[k]) a.bounds_vary = 1;
+    }
+    a.batch = h->batch;
+    const unsigned mat_bits = (1u << LCQP_Q) | (1u << LCQP_L) | (1u << LCQP_R) | (h->nC > 0 ? (1u << LCQP_A) : 0u);
+    a.mats_shared = ((a.shared_mask & mat_bits) == mat_bits);
+    a.shared_mats = h->pas_mats;
+    a.shared_raw = h->shared_raw;
+    a.shared_store = h->pas_store;
+    a.eqmask = h->eqmask;
+    a.pool.ibuf = h->pool_i; a.pool.dbuf = h->pool_d; a.pool.icap = (int)h->pool_cap; a.pool.dcap = (int)h->pool_cap; a.pool.used = h->pool_used;
+    a.xout = h->xout; a.yout = h->yout; a.stats = h->stats; a.counter = h->counter;
+    a.fallback_flag = h->fallback_flag;
+    a.instance_offset = h->instance_offset;
+}
+
+// Batch-level preparation of a load (on the load stream): equality mask over the batch, CSR copies of the shared
+// raw matrices, prepared operands when Q, L, R, A are shared.  The header (mE, mI, status) is read back.
+static int pas_prepare_load(lcqp_cuda_handle h)
+{
+    h->has_box = (h->dev_in[LCQP_LB] || h->dev_in[LCQP_UB]) ? 1 : 0;
+    const pas::PDims d = pas::make_pdims(h->nV, h->nC, h->nComp, h->has_box);
+    const size_t md = pas::pmats_doubles(d);
+    if (md > h->pas_store_cap) {
+        if (h->pas_store) cudaFree(h->pas_store);
+        h->pas_store = nullptr; h->pas_store_cap = 0;
+        if (cudaMalloc(&h->pas_store, md * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(prepared operands)"); }
+        h->pas_store_cap = md;
+    }
+    if ((size_t)d.m + 16 > h->eqmask_cap) {
+        if (h->eqmask) cudaFree(h->eqmask);
+        h->eqmask = nullptr; h->eqmask_cap = 0;
+        if (cudaMalloc(&h->eqmask, (size_t)d.m + 16) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(eqmask)"); }
+        h->eqmask_cap = (size_t)d.m + 16;
+    }
+    const size_t pool_cap = 2 * (size_t)d.n * d.n + 3 * (size_t)d.m * d.n + 64ull * (d.m + d.n) + 4096;
+    if (pool_cap > h->pool_cap) {
+        if (h->pool_i) cudaFree(h->pool_i);
+        if (h->pool_d) cudaFree(h->pool_d);
+        h->pool_i = nullptr; h->pool_d = nullptr; h->pool_cap = 0;
+        if (cudaMalloc(&h->pool_i, pool_cap * sizeof(int)) != cudaSuccess || cudaMalloc(&h->pool_d, pool_cap * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(csr pool)");
+        }
+        h->pool_cap = pool_cap;
+    }
+    PasArgs a;
+    pas_fill_args(h, a);
+    cudaStream_t st = h->load_stream;
+    CK(cudaMemsetAsync(h->eqmask, 1, (size_t)d.m, st), LCQP_CUDA_LAUNCH_FAILED);
+    {
+        int grid = a.bounds_vary ? (h->batch < 4 * h->num_sms ? h->batch : 4 * h->num_sms) : 1;
+        pas_eqmask_kernel<<<grid, 128, 0, st>>>(a);
+        h->launches++;
+        CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
+    }
+    pas_prepare_kernel<<<1, kPrepThreads, 0, st>>>(a);
+    h->launches++;
+    CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
+    memset(h->pas_host, 0, sizeof(pas::PMats));
+    if (a.mats_shared) CK(cudaMemcpyAsync(h->pas_host, h->pas_mats, sizeof(pas::PMats), cudaMemcpyDeviceToHost, st), LCQP_CUDA_LAUNCH_FAILED);
+    return LCQP_CUDA_OK;
+}
+
+static int run_pas(lcqp_cuda_handle h, cudaStream_t stream)
+{
+    PasArgs a;
+    pas_fill_args(h, a);
+    const pas::PDims& d = a.d;
+    if (a.mats_shared) { a.mEc = h->pas_host->mE; a.mIc = h->pas_host->mI; a.capc = pas::pas_cap(d, a.mEc, a.mIc); }
+    else { a.mEc = pas::pas_mEmax(d); a.mIc = d.m; a.capc = d.n < d.m ? d.n : d.m; }
+    h->last_mE = a.mats_shared ? a.mEc : -1;
+    // a CTA is G groups of T threads; every group keeps the row vectors of its instance in shared memory
+    int threads = 128;
+    if (const char* t = getenv("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) threads = v; }
+    int gmax = kMaxCtaThreads / threads;
+    if (gmax > kPasGroupsMax) gmax = kPasGroupsMax;
+    if (const char* t = getenv("LCQP_CUDA_GROUPS")) { const int v = atoi(t); if (v >= 1 && v < gmax) gmax = v; }
+    if (gmax > h->batch) gmax = h->batch;
+    cudaFuncAttributes fattr;
+    CK(cudaFuncGetAttributes(&fattr, lcqp_pas_kernel), LCQP_CUDA_LAUNCH_FAILED);
+    const size_t budget = kSmemMax - fattr.sharedSizeBytes;
+    a.group_smem = (pas::pas_smem_bytes(a.mIc, a.capc) + 15) / 16 * 16;
+    int groups = gmax;
+    while (groups > 1 && (size_t)groups * a.group_smem > budget) groups--;
+    if ((size_t)groups * a.group_smem > budget) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
+    const size_t smem = (size_t)groups * a.group_smem;
+    CK(cudaFuncSetAttribute(lcqp_pas_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_pas_kernel, threads * groups, smem), LCQP_CUDA_LAUNCH_FAILED);
+    if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
+    int grid = per_sm * h->num_sms;
+    if ((long long)grid * groups > h->batch) grid = (h->batch + groups - 1) / groups;
+    a.ws_mats = a.mats_shared ? 0 : pas::pmats_doubles(d);
+    a.ws_stride = a.ws_mats + pas::pas_gl_doubles(d, a.mEc, a.capc) + 16;
+    a.ws_stride = (a.ws_stride + 1) & ~1ull;
+    const size_t ws_total = a.ws_stride * (size_t)grid * groups;
+    if (ws_total > h->workspace_cap) {
+        // (the previous run on another stream may still use the old block: wait for it)
+        if (h->workspace) { cudaDeviceSynchronize(); cudaFree(h->workspace); }
+        h->workspace = nullptr; h->workspace_cap = 0;
+        if (cudaMalloc(&h->workspace, (ws_total ? ws_total : 1) * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(workspace)"); }
+        h->workspace_cap = ws_total;
+    }
+    a.workspace = h->workspace;
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaMemsetAsync(h->fallback_flag, 0, sizeof(int), stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
+    if (getenv("LCQP_CUDA_VERBOSE"))
+        fprintf(stderr, "lcqp_cuda (parametric active set): grid %d x (%d threads x %d groups), %d CTA/SM, smem %zu B = %d x %llu, mE %d mI %d cap %d, scratch %llu doubles/group\n",
+                grid, threads, groups, per_sm, smem, groups, a.group_smem, a.mEc, a.mIc, a.capc, a.ws_stride);
+    lcqp_pas_kernel<<<grid, dim3(threads, groups), smem, stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
+    h->last_stream = stream;
+    h->last_grid = grid * groups;
+    h->last_smem = (int)smem;
+    h->ran = true;
+    if (!a.mats_shared) {
+        // per-instance matrices: an instance with a semidefinite reduced Hessian sends the batch to the regularised solver
+        CK(cudaMemcpyAsync(h->fallback_host, h->fallback_flag, sizeof(int), cudaMemcpyDeviceToHost, stream), LCQP_CUDA_LAUNCH_FAILED);
+        CK(cudaStreamSynchronize(stream), LCQP_CUDA_LAUNCH_FAILED);
+        if (*h->fallback_host) { h->use_legacy = true; return run_legacy(h, stream); }
+    }
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!h->loaded) return fail(h, LCQP_CUDA_NOT_LOADED, "run before load");
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+    if (h->use_legacy || !h->pas_ready || getenv("LCQP_CUDA_LEGACY")) return run_legacy(h, stream);
+    return run_pas(h, stream);
+}
+
 int lcqp_cuda_synchronize(lcqp_cuda_handle h)
 {
     if (!h) return LCQP_CUDA_BAD_HANDLE;
@@ -842,6 +1174,7 @@ int lcqp_cuda_qp_set_options(lcqp_cuda_qp q, const lcqp_cuda_options* o)
 {
     if (!q) return LCQP_CUDA_BAD_HANDLE;
     if (!o) return LCQP_CUDA_BAD_ARGUMENT;
+    if (!qp_knobs_valid(o)) return LCQP_CUDA_BAD_ARGUMENT;
     q->opts = *o;
     return LCQP_CUDA_OK;
 }

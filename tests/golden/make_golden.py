@@ -22,6 +22,17 @@ REF_DATA = "/root/reference/examples/example_data"
 STEMS = ("Q", "g", "L", "R", "lbL", "ubL", "lbR", "ubR", "A", "lbA", "ubA", "lb", "ub", "x0")
 
 
+def family_cases(data):
+    """name -> (LCQPBatch, option overrides, reference subsolver).  Also imported by tests/conftest.py."""
+    return {
+        "circle_bench": (P.circle_batch_fast(256), {"stationarityTolerance": 10e-3}, pyref.QPOASES_SPARSE),
+        "dense_bench": (P.dense_random_batch(256), {}, pyref.QPOASES_DENSE),
+        "circle_N20": (P.circle_batch(16, N=20), {"stationarityTolerance": 10e-3}, pyref.QPOASES_DENSE),
+        "dense_n32": (P.dense_random_batch(32, n=32, nComp=16, nC=8), {}, pyref.QPOASES_DENSE),
+        "example_data_family": (P.example_data_batch(data, 17), {}, pyref.QPOASES_DENSE),
+    }
+
+
 def main():
     ref = pyref.RefLib()
     # 1) the shipped input fixture (input data only)
@@ -56,6 +67,20 @@ def main():
             out[f"{name}/{tag}/rhoOpt"] = s.res["rhoOpt"]
             print(name, tag, "ret", s.res["ret"].tolist(), "k", s.res["iterOuter"].tolist(), "i", s.res["iterTotal"].tolist())
     np.savez_compressed(os.path.join(HERE, "reference_outputs.npz"), **out)
+
+    # 2) the families the bench and the verdict of round 1 use: 256 instances each, qpOASES runs of the reference
+    #    (QPOASES_SPARSE for the circle family -- three times faster than QPOASES_DENSE, same trajectories)
+    fam = {}
+    for name, (pb, over, flavour) in family_cases(data).items():
+        s = ref.solve_batch(pb, ref.default_options(qpSolver=flavour, perturbStep=0, **over))
+        fam[f"{name}/x"] = s.x
+        fam[f"{name}/y"] = s.y.astype(np.float32)   # duals: signs / classification only
+        for f in ("ret", "status", "iterTotal", "iterOuter", "subproblemIter", "qpExitFlag"):
+            fam[f"{name}/{f}"] = s.res[f].astype(np.int32)
+        fam[f"{name}/rhoOpt"] = s.res["rhoOpt"]
+        print(name, "ret", np.unique(s.res["ret"], return_counts=True), "status", np.unique(s.res["status"], return_counts=True),
+              "k mean", s.res["iterOuter"].mean(), "i mean", s.res["iterTotal"].mean(), "sub mean", s.res["subproblemIter"].mean())
+    np.savez_compressed(os.path.join(HERE, "reference_families.npz"), **fam)
 
 
 if __name__ == "__main__":
