@@ -310,10 +310,17 @@ __global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_pas_kernel(const __gri
             if (!raw_all_shared) raw_dense_ops(dold, in_s[g], ro, a.shared_mask);
         }
         LCQ_SYNC();
+#ifdef LCQP_PROFILE
+        if (threadIdx.x == 0) { for (int k = 0; k < 16; k++) wk.sc->prof[k] = 0; wk.sc->prof_last = clock64(); wk.sc->prof_cur = 11; }
+#endif
         LoopOut out;
         double* xo = a.xout + (size_t)b * a.d.n;
         double* yo = a.yout + (size_t)b * nD;
         const bool ok = pas::pas_run_instance(s, mt, a.mats_shared != 0, ro, a.instance_offset + (unsigned long long)b, xo, yo, out, eq_scratch);
+#ifdef LCQP_PROFILE
+        LCQ_PROF(wk.sc, 13);
+        if (threadIdx.x == 0) for (int k = 0; k < 16; k++) atomicAdd(&g_prof[k], (unsigned long long)wk.sc->prof[k]);
+#endif
         if (threadIdx.x == 0) {
             lcqp_cuda_stats st;
             st.ret = ok ? out.ret : -1; st.status = out.status; st.iterTotal = out.iterTotal; st.iterOuter = out.iterOuter;
@@ -964,7 +971,7 @@ static int run_pas(lcqp_cuda_handle h, cudaStream_t stream)
     cudaFuncAttributes fattr;
     CK(cudaFuncGetAttributes(&fattr, lcqp_pas_kernel), LCQP_CUDA_LAUNCH_FAILED);
     const size_t budget = kSmemMax - fattr.sharedSizeBytes;
-    a.group_smem = (pas::pas_smem_bytes(a.mIc, a.capc) + 15) / 16 * 16;
+    a.group_smem = (pas::pas_smem_bytes(d, a.mEc, a.mIc, a.capc) + 15) / 16 * 16;
     int groups = gmax;
     while (groups > 1 && (size_t)groups * a.group_smem > budget) groups--;
     if ((size_t)groups * a.group_smem > budget) return fail(h, LCQP_CUDA_TOO_LARGE, "instance does not fit the shared-memory budget");
@@ -998,6 +1005,20 @@ static int run_pas(lcqp_cuda_handle h, cudaStream_t stream)
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
+#ifdef LCQP_PROFILE
+    if (getenv("LCQP_CUDA_VERBOSE")) {
+        cudaStreamSynchronize(stream);
+        unsigned long long pr[16];
+        cudaMemcpyFromSymbol(pr, g_prof, sizeof(pr));
+        unsigned long long z[16] = {};
+        cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+        double tot = 0;
+        for (int k = 0; k < 16; k++) tot += (double)pr[k];
+        static const char* nm[16] = {"dy = Sinv rhs", "dz = Tt[:,W] dy", "ratio tests", "step + hom.len", "ws remove", "ws add", "drift", "ramping", "dc / target", "finish: rebase", "finish: polish", "outer loop", "init (aux QP)", "store stats", "hotstart misc", "-"};
+        fprintf(stderr, "lcqp_cuda profile (group cycles per LCQP, %% of total):\n");
+        for (int k = 0; k < 16; k++) fprintf(stderr, "   %-16s %12.0f  %5.1f%%\n", nm[k], (double)pr[k] / h->batch, 100.0 * pr[k] / (tot > 0 ? tot : 1));
+    }
+#endif
     h->last_stream = stream;
     h->last_grid = grid * groups;
     h->last_smem = (int)smem;

@@ -62,21 +62,32 @@ enum { QP_OK = 0, QP_INFEASIBLE_BOUNDS = 31, QP_INFEASIBLE = 37, QP_UNBOUNDED = 
 // Prepared operands.  rows: m = nC + 2 nComp (+ n box rows); E = eliminated equality rows, I = the others.
 // ------------------------------------------------------------------------------------------------
 struct PMats {
+    // work arrays of the preparation (row-major, natural leading dimensions)
     double* P;       // n*n      Z (Z'QZ)^-1 Z'
     double* N;       // n*mE     (I - P Q) N0
     double* N0;      // n*mE     A_E'(A_E A_E')^-1
     double* Gt;      // mI*n     A_I P
-    double* Tt;      // mI*ldI   Gt A_I'   (exactly symmetric, ldI even)
     double* K;       // mI*mE    A_I N
     double* Af;      // m*n      A_full (dense copy; rows of box constraints are unit rows)
     double* scr;     // preparation scratch (pmats_scratch_doubles)
+    // what the solver reads: every operator stored so that consecutive threads read consecutive addresses
+    // (out[r] = sum_c X[c*ld + r] v[c], ld even), see op_mv_t<true> in lcqp_device.cuh
+    double* Tt;      // mI*ldI   Gt A_I'   (exactly symmetric)
+    double* Pp;      // n*ldn    P (symmetric)
+    double* GtT;     // n*ldI    Gt'
+    double* KT;      // mE*ldI   K'
+    double* NT;      // mE*ldn   N'
+    double* N0p;     // n*ldE    N0
+    double* Afp;     // m*ldn    A_full
+    double* AfT;     // n*ldm    A_full'
+    int ldn, ldm, ldE;
     int* Eidx;       // mE  full row index of eliminated row e
     int* Iidx;       // mI  full row index of remaining row i
     int* pos;        // m   position of full row r in its list (E or I)
     signed char* isE;  // m
     int mE, mI, ldI;
     int status;      // 0 ok, 1 reduced Hessian not positive definite (take the regularised solver), 2 other failure
-    Op oP, oA, oAt, oGt, oN, oN0t;   // n x n, m x n, n x m, mI x n, n x mE, mE x n
+    Op oP, oA, oAt, oGt, oK, oN, oN0t;   // n x n, m x n, n x m, mI x n, mI x mE, n x mE, mE x n
 };
 
 struct PDims {
@@ -101,7 +112,9 @@ inline LCQ_HD size_t pmats_scratch_doubles(const PDims& d)
 inline LCQ_HD size_t pmats_doubles(const PDims& d)
 {
     const size_t n = d.n, m = d.m, e = pas_mEmax(d);
-    return pev(n * n) + 2 * pev(n * e) + 2 * pev(m * n) + pev(m * (m + 1)) + pev(m * e) + 2 * pev((m + 1) / 2) + pev(m) + pev((m + 7) / 8) + pmats_scratch_doubles(d) + 8;
+    const size_t work = pev(n * n) + 2 * pev(n * e) + 2 * pev(m * n) + pev(m * e);
+    const size_t fin = pev(m * (m + 1)) + pev(n * (n + 1)) + pev(n * (m + 1)) + pev(e * (m + 1)) + pev(e * (n + 1)) + pev(n * (e + 1)) + pev(m * (n + 1)) + pev(n * (m + 1));
+    return work + fin + 2 * pev((m + 1) / 2) + pev(m) + pev((m + 7) / 8) + pmats_scratch_doubles(d) + 8;
 }
 
 LCQ_DEV void carve_pmats(PMats& mt, double* base, const PDims& d)
@@ -112,8 +125,16 @@ LCQ_DEV void carve_pmats(PMats& mt, double* base, const PDims& d)
     mt.N0 = base; base += pev(n * e);
     mt.Gt = base; base += pev(m * n);
     mt.Af = base; base += pev(m * n);
-    mt.Tt = base; base += pev(m * (m + 1));
     mt.K = base; base += pev(m * e);
+    mt.Tt = base; base += pev(m * (m + 1));
+    mt.Pp = base; base += pev(n * (n + 1));
+    mt.GtT = base; base += pev(n * (m + 1));
+    mt.KT = base; base += pev(e * (m + 1));
+    mt.NT = base; base += pev(e * (n + 1));
+    mt.N0p = base; base += pev(n * (e + 1));
+    mt.Afp = base; base += pev(m * (n + 1));
+    mt.AfT = base; base += pev(n * (m + 1));
+    mt.ldn = (int)pev(n); mt.ldm = (int)pev(m); mt.ldE = 2;
     mt.Eidx = reinterpret_cast<int*>(base); base += pev((m + 1) / 2);
     mt.Iidx = reinterpret_cast<int*>(base); base += pev((m + 1) / 2);
     mt.pos = reinterpret_cast<int*>(base); base += pev(m);   // (m ints fit in m doubles)
@@ -375,26 +396,38 @@ LCQ_DEVN void pas_prepare(const PDims& d, const Inst& in, PMats& mt, const signe
         mt.K[e] = acc;
     }
     LCQ_SYNC();
+    // the solver's copies
+    const int ldn = mt.ldn, ldm = mt.ldm;
+    const int ldE = (int)pev(mE > 0 ? mE : 1);
+    if (LCQ_TID == 0) mt.ldE = ldE;
+    LCQ_LOOP for (int e = LCQ_TID; e < n * n; e += LCQ_NT) { const int i = e / n, j = e - i * n; mt.Pp[(size_t)i * ldn + j] = mt.P[e]; }
+    LCQ_LOOP for (int e = LCQ_TID; e < mI * n; e += LCQ_NT) { const int i = e / n, j = e - i * n; mt.GtT[(size_t)j * ldI + i] = mt.Gt[e]; }
+    LCQ_LOOP for (int e = LCQ_TID; e < mI * mE; e += LCQ_NT) { const int i = e / mE, a = e - i * mE; mt.KT[(size_t)a * ldI + i] = mt.K[e]; }
+    LCQ_LOOP for (int e = LCQ_TID; e < n * mE; e += LCQ_NT) { const int j = e / mE, a = e - j * mE; mt.NT[(size_t)a * ldn + j] = mt.N[e]; mt.N0p[(size_t)j * ldE + a] = mt.N0[e]; }
+    LCQ_LOOP for (int e = LCQ_TID; e < m * n; e += LCQ_NT) { const int r = e / n, j = e - r * n; mt.Afp[(size_t)r * ldn + j] = mt.Af[e]; mt.AfT[(size_t)j * ldm + r] = mt.Af[e]; }
+    LCQ_SYNC();
 }
 
-// dense operator descriptors (one thread)
+// dense operator descriptors (one thread): all in the transposed ("column") form
 LCQ_DEV void pmats_dense_ops(const PDims& d, PMats& mt)
 {
-    mt.oP = dense_op(mt.P, d.n, d.n, d.n, 0);
-    mt.oA = dense_op(mt.Af, d.m, d.n, d.n, 0);
-    mt.oAt = dense_op(mt.Af, d.n, d.m, d.n, 1);
-    mt.oGt = dense_op(mt.Gt, mt.mI, d.n, d.n, 0);
-    mt.oN = dense_op(mt.N, d.n, mt.mE, mt.mE > 0 ? mt.mE : 1, 0);
-    mt.oN0t = dense_op(mt.N0, mt.mE, d.n, mt.mE > 0 ? mt.mE : 1, 1);
+    const int e1 = mt.mE > 0 ? mt.mE : 1;
+    mt.oP = dense_op(mt.Pp, d.n, d.n, mt.ldn, 1);
+    mt.oA = dense_op(mt.AfT, d.m, d.n, mt.ldm, 1);
+    mt.oAt = dense_op(mt.Afp, d.n, d.m, mt.ldn, 1);
+    mt.oGt = dense_op(mt.GtT, mt.mI, d.n, mt.ldI, 1);
+    mt.oK = dense_op(mt.KT, mt.mI, e1, mt.ldI, 1);
+    mt.oN = dense_op(mt.NT, d.n, e1, mt.ldn, 1);
+    mt.oN0t = dense_op(mt.N0p, e1, d.n, mt.ldE, 1);
 }
 
 // CSR copies where sparse (batch-shared operands only)
 LCQ_DEVN void pmats_build_ops(const PDims& d, PMats& mt, CsrPool& pool, Scalars* sc)
 {
-    const Op a = build_op(mt.P, d.n, d.n, d.n, 0, pool, sc);
-    const Op b = build_op(mt.Af, d.m, d.n, d.n, 0, pool, sc);
-    const Op c = build_op(mt.Af, d.n, d.m, d.n, 1, pool, sc);
-    const Op e = build_op(mt.Gt, mt.mI, d.n, d.n, 0, pool, sc);
+    const Op a = build_op(mt.Pp, d.n, d.n, mt.ldn, 1, pool, sc);
+    const Op b = build_op(mt.AfT, d.m, d.n, mt.ldm, 1, pool, sc);
+    const Op c = build_op(mt.Afp, d.n, d.m, mt.ldn, 1, pool, sc);
+    const Op e = build_op(mt.GtT, mt.mI, d.n, mt.ldI, 1, pool, sc);
     if (LCQ_TID == 0) { mt.oP = a; mt.oA = b; mt.oAt = c; mt.oGt = e; }
     LCQ_SYNC();
 }
@@ -406,16 +439,19 @@ struct PWork {
     // shared memory: vectors over the remaining rows (mI) and the working set (cap)
     double *y, *z, *l, *u, *c, *dz, *dc, *lf, *uf, *yb;    // mI
     double *va, *vb;                                       // cap
+    double *xq, *tn, *sv;                                  // n   (xq: the QP's primal iterate; tn, sv: operator inputs)
+    double *tm1, *tm2;                                     // m   (operator inputs / outputs in full row order)
+    double *tE1, *tE2, *bEn;                               // mE  (bEn: the true bounds of the eliminated rows)
     int* widx;                                             // cap: rows (I numbering) of the working set
     int* stamp;                                            // mI: position in its index list (insertion order)
     signed char* st;                                       // mI: ST_*
     Scalars* sc;
     // global scratch
     double* Sinv; int ld;                                  // cap x ld, full storage, exactly symmetric
-    double *xq, *gq, *gk, *dg0, *xk, *pk, *gt, *gphi, *stat, *tn;   // n
+    double *gq, *gk, *dg0, *xk, *pk, *gt, *gphi, *stat, *tq;   // n
     double *Lx, *Rx;                                       // nComp
-    double *tm1, *tm2, *ys;                                // m   (ys: duals of the last QP, full row order)
-    double *bE, *bEb, *yE, *tE1, *tE2;                     // mE  (bE: current equality bounds, bEb: at the last rebase, yE: duals)
+    double *ys;                                            // m   duals of the last QP, full row order
+    double *bE, *bEb, *yE;                                 // mE  (bE: current equality bounds, bEb: at the last rebase, yE: duals)
 };
 
 struct PQP {
@@ -425,6 +461,7 @@ struct PQP {
     const Inst* in;
     PWork* w;
     int nw, cap;
+    int e_moving;        // the bounds of the eliminated rows are still on their way (initial homotopy only)
     int stamp_next, rampOffset;
     double phi, len0;
     int nwsr;            // working-set changes of the current QP
@@ -441,14 +478,17 @@ inline LCQ_HD int pas_cap(const PDims& d, int mE, int mI)
     return c;
 }
 inline LCQ_HD int pas_ld(int cap) { return (cap + 1) & ~1; }
-inline LCQ_HD size_t pas_smem_doubles(int mI, int cap) { return 10 * pev(mI) + 2 * pev(cap); }
-inline LCQ_HD size_t pas_smem_bytes(int mI, int cap)
+inline LCQ_HD size_t pas_smem_doubles(const PDims& d, int mE, int mI, int cap)
 {
-    return pas_smem_doubles(mI, cap) * sizeof(double) + (size_t)pev(cap) * sizeof(int) + (size_t)pev(mI) * sizeof(int) + ((size_t)(mI + 15) / 16) * 16 + sizeof(Scalars) + 64;
+    return 10 * pev(mI) + 2 * pev(cap) + 3 * pev(d.n) + 2 * pev(d.m) + 3 * pev(mE > 0 ? mE : 1);
+}
+inline LCQ_HD size_t pas_smem_bytes(const PDims& d, int mE, int mI, int cap)
+{
+    return pas_smem_doubles(d, mE, mI, cap) * sizeof(double) + (size_t)pev(cap) * sizeof(int) + (size_t)pev(mI) * sizeof(int) + ((size_t)(mI + 15) / 16) * 16 + sizeof(Scalars) + 64;
 }
 inline LCQ_HD size_t pas_gl_doubles(const PDims& d, int mE, int cap)
 {
-    return (size_t)cap * pas_ld(cap) + 10 * pev(d.n) + 2 * pev(d.nComp) + 3 * pev(d.m) + 5 * pev(mE > 0 ? mE : 1);
+    return (size_t)cap * pas_ld(cap) + 9 * pev(d.n) + 2 * pev(d.nComp) + pev(d.m) + 3 * pev(mE > 0 ? mE : 1);
 }
 
 LCQ_DEV void pas_carve(PWork& w, const PDims& d, int mE, int mI, int cap, unsigned char* smem, double* gl)
@@ -458,6 +498,12 @@ LCQ_DEV void pas_carve(PWork& w, const PDims& d, int mE, int mI, int cap, unsign
     w.y = take(mI); w.z = take(mI); w.l = take(mI); w.u = take(mI); w.c = take(mI); w.dz = take(mI); w.dc = take(mI);
     w.lf = take(mI); w.uf = take(mI); w.yb = take(mI);
     w.va = take(cap); w.vb = take(cap);
+    w.xq = take(d.n); w.tn = take(d.n); w.sv = take(d.n);
+    w.tm1 = take(d.m); w.tm2 = take(d.m);
+    {
+        const int e1 = mE > 0 ? mE : 1;
+        w.tE1 = take(e1); w.tE2 = take(e1); w.bEn = take(e1);
+    }
     w.widx = reinterpret_cast<int*>(q);
     w.stamp = w.widx + pev(cap);
     w.st = reinterpret_cast<signed char*>(w.stamp + pev(mI));
@@ -467,12 +513,12 @@ LCQ_DEV void pas_carve(PWork& w, const PDims& d, int mE, int mI, int cap, unsign
     auto tg = [&](size_t k) { double* r = gl; gl += pev(k); return r; };
     w.ld = pas_ld(cap);
     w.Sinv = tg((size_t)cap * w.ld);
-    w.xq = tg(d.n); w.gq = tg(d.n); w.gk = tg(d.n); w.dg0 = tg(d.n); w.xk = tg(d.n); w.pk = tg(d.n); w.gt = tg(d.n);
-    w.gphi = tg(d.n); w.stat = tg(d.n); w.tn = tg(d.n);
+    w.gq = tg(d.n); w.gk = tg(d.n); w.dg0 = tg(d.n); w.xk = tg(d.n); w.pk = tg(d.n); w.gt = tg(d.n);
+    w.gphi = tg(d.n); w.stat = tg(d.n); w.tq = tg(d.n);
     w.Lx = tg(d.nComp); w.Rx = tg(d.nComp);
-    w.tm1 = tg(d.m); w.tm2 = tg(d.m); w.ys = tg(d.m);
+    w.ys = tg(d.m);
     const int e = mE > 0 ? mE : 1;
-    w.bE = tg(e); w.bEb = tg(e); w.yE = tg(e); w.tE1 = tg(e); w.tE2 = tg(e);
+    w.bE = tg(e); w.bEb = tg(e); w.yE = tg(e);
 }
 
 // ---- small block-wide helpers ----------------------------------------------------------------------
@@ -615,42 +661,88 @@ LCQ_DEVN void pas_remove(PQP& s, int p)
     LCQ_SYNC();
 }
 
-// out (mI) = Tt[:, W] v   (v over the working set; reads rows W of the symmetric Tt: coalesced)
+// out (mI) = Tt[:, W] v - sub   (v over the working set; reads rows W of the symmetric Tt).  v, out, sub in shared
+// memory.  A pair of adjacent lanes owns two adjacent columns (one 16-byte load per row) and splits the rows of the
+// working set in two halves; twelve loads are in flight per thread; one shuffle joins the halves.
 LCQ_DEVN void tt_cols_apply(const PQP& s, const double* v, double* out, const double* sub)
 {
     const PWork& w = *s.w;
     const int mI = s.mt->mI, ldI = s.mt->ldI, nw = s.nw;
     const double* Tt = s.mt->Tt;
-    LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) {
-        double a0 = 0, a1 = 0;
-        int a = 0;
-        LCQ_LOOP for (; a + 2 <= nw; a += 2) {
-            a0 += Tt[(size_t)w.widx[a] * ldI + i] * v[a];
-            a1 += Tt[(size_t)w.widx[a + 1] * ldI + i] * v[a + 1];
+#ifndef LCQP_HOST_EMU
+    const int npair = (mI + 1) >> 1;
+    const int half = (nw + 1) >> 1;
+    LCQ_LOOP for (int t0 = 0; t0 < 2 * npair; t0 += LCQ_NT) {
+        const int t = t0 + LCQ_TID;
+        const bool act = t < 2 * npair;
+        const int c = t >> 1, h = t & 1;
+        int b = act ? (h ? half : 0) : 0;
+        const int b1 = act ? (h ? nw : half) : 0;
+        double x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+        LCQ_LOOP for (; b + 12 <= b1; b += 12) {
+            double m0[12], m1[12];
+#pragma unroll
+            for (int k = 0; k < 12; k++) ldg128v(Tt + ((unsigned)w.widx[b + k] * (unsigned)ldI + 2u * (unsigned)c), m0[k], m1[k]);
+#pragma unroll
+            for (int k = 0; k < 12; k += 2) {
+                const double v0 = v[b + k], v1 = v[b + k + 1];
+                x0 += m0[k] * v0; y0 += m1[k] * v0;
+                x1 += m0[k + 1] * v1; y1 += m1[k + 1] * v1;
+            }
         }
-        if (a < nw) a0 += Tt[(size_t)w.widx[a] * ldI + i] * v[a];
-        out[i] = (a0 + a1) - (sub ? sub[i] : 0.0);
+        LCQ_LOOP for (; b + 4 <= b1; b += 4) {
+            double m0[4], m1[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) ldg128v(Tt + ((unsigned)w.widx[b + k] * (unsigned)ldI + 2u * (unsigned)c), m0[k], m1[k]);
+#pragma unroll
+            for (int k = 0; k < 4; k += 2) {
+                const double v0 = v[b + k], v1 = v[b + k + 1];
+                x0 += m0[k] * v0; y0 += m1[k] * v0;
+                x1 += m0[k + 1] * v1; y1 += m1[k + 1] * v1;
+            }
+        }
+        LCQ_LOOP for (; b < b1; b++) {
+            double m0, m1;
+            ldg128(Tt + ((unsigned)w.widx[b] * (unsigned)ldI + 2u * (unsigned)c), m0, m1);
+            const double v0 = v[b];
+            x0 += m0 * v0; y0 += m1 * v0;
+        }
+        double sa = x0 + x1, sb = y0 + y1;
+        sa += __shfl_xor_sync(0xffffffffu, sa, 1);
+        sb += __shfl_xor_sync(0xffffffffu, sb, 1);
+        const int i = 2 * c + h;
+        if (act && i < mI) out[i] = (h ? sb : sa) - (sub ? sub[i] : 0.0);
     }
+#else
+    LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) {
+        // (same association as the device loop: two halves of the working set, each split over two accumulators)
+        const int half = (nw + 1) >> 1;
+        double hsum[2];
+        for (int h = 0; h < 2; h++) {
+            int b = h ? half : 0;
+            const int b1 = h ? nw : half;
+            double x0 = 0, x1 = 0;
+            for (; b + 2 <= b1; b += 2) {
+                x0 += Tt[(size_t)w.widx[b] * ldI + i] * v[b];
+                x1 += Tt[(size_t)w.widx[b + 1] * ldI + i] * v[b + 1];
+            }
+            if (b < b1) x0 += Tt[(size_t)w.widx[b] * ldI + i] * v[b];
+            hsum[h] = x0 + x1;
+        }
+        out[i] = (hsum[0] + hsum[1]) - (sub ? sub[i] : 0.0);
+    }
+#endif
     LCQ_SYNC();
 }
 
 // c-space image of a gradient change v (n) and an equality-bound change dbE (mE, may be null):  out = Gt v - K dbE
+// (v, dbE, out in shared memory)
 LCQ_DEVN void c_image(const PQP& s, const double* v, const double* dbE, double* out)
 {
-    const PWork& w = *s.w;
     const PMats& mt = *s.mt;
-    const int mI = mt.mI, mE = mt.mE;
-    op_mv(mt.oGt, v, nullptr, 1.0, w.tm1);
+    op_mv_s(mt.oGt, v, nullptr, 1.0, out);
     LCQ_SYNC();
-    LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) {
-        double acc = 0;
-        if (dbE) {
-            const double* k = mt.K + (size_t)i * mE;
-            LCQ_LOOP for (int e = 0; e < mE; e++) acc += k[e] * dbE[e];
-        }
-        out[i] = w.tm1[i] - acc;
-    }
-    LCQ_SYNC();
+    if (dbE && mt.mE > 0) { op_mv_s(mt.oK, dbE, out, -1.0, out); LCQ_SYNC(); }
 }
 
 // xq += P (A_I' dyI - dgrad) + N dbE;  dyI: full-order vector in tm2 (zero on the eliminated rows), dgrad (n) and
@@ -659,12 +751,12 @@ LCQ_DEVN void x_update(const PQP& s, const double* dgrad, const double* dbE)
 {
     const PWork& w = *s.w;
     const int n = s.d->n;
-    op_mv(s.mt->oAt, w.tm2, nullptr, 1.0, w.tn);
+    op_mv_s(s.mt->oAt, w.tm2, nullptr, 1.0, w.tn);
     LCQ_SYNC();
     if (dgrad) { LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.tn[j] -= dgrad[j]; LCQ_SYNC(); }
-    op_mv(s.mt->oP, w.tn, w.xq, 1.0, w.xq);
+    op_mv_s(s.mt->oP, w.tn, w.xq, 1.0, w.xq);
     LCQ_SYNC();
-    if (dbE && s.mt->mE > 0) { op_mv(s.mt->oN, dbE, w.xq, 1.0, w.xq); LCQ_SYNC(); }
+    if (dbE && s.mt->mE > 0) { op_mv_s(s.mt->oN, dbE, w.xq, 1.0, w.xq); LCQ_SYNC(); }
 }
 
 // Bring xq, gq and the base duals / equality bounds to the current point of the homotopy: g = g_new - phi dg0.
@@ -678,7 +770,7 @@ LCQ_DEVN void rebase(PQP& s)
     LCQ_LOOP for (int r = LCQ_TID; r < m; r += LCQ_NT) { const int p = mt.pos[r]; w.tm2[r] = mt.isE[r] ? 0.0 : (w.y[p] - w.yb[p]); }
     LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) w.tE1[e] = w.bE[e] - w.bEb[e];
     LCQ_SYNC();
-    x_update(s, w.stat, w.tE1);
+    x_update(s, w.stat, s.e_moving ? w.tE1 : nullptr);
     LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) { w.gq[j] += w.stat[j]; w.dg0[j] *= s.phi; }
     LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) w.bEb[e] = w.bE[e];
     LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) w.yb[i] = w.y[i];
@@ -716,10 +808,10 @@ LCQ_DEVN void dc_from_target(PQP& s)
 {
     const PWork& w = *s.w;
     const PMats& mt = *s.mt;
-    LCQ_LOOP for (int j = LCQ_TID; j < s.d->n; j += LCQ_NT) w.stat[j] = s.phi * w.dg0[j];
-    LCQ_LOOP for (int e = LCQ_TID; e < mt.mE; e += LCQ_NT) { double lo, up; row_bounds(*s.d, *s.in, mt.Eidx[e], lo, up); w.tE2[e] = lo - w.bE[e]; }
+    LCQ_LOOP for (int j = LCQ_TID; j < s.d->n; j += LCQ_NT) w.sv[j] = s.phi * w.dg0[j];
+    LCQ_LOOP for (int e = LCQ_TID; e < mt.mE; e += LCQ_NT) w.tE2[e] = w.bEn[e] - w.bE[e];
     LCQ_SYNC();
-    c_image(s, w.stat, mt.mE > 0 ? w.tE2 : nullptr, w.dc);
+    c_image(s, w.sv, s.e_moving ? w.tE2 : nullptr, w.dc);
 }
 
 // performRamping (QProblem.cpp:5416-5492)
@@ -745,7 +837,7 @@ LCQ_DEVN void ramping(PQP& s)
     // A_I'(y - yb) (x and the equality multipliers stay)
     LCQ_LOOP for (int r = LCQ_TID; r < m; r += LCQ_NT) { const int p = mt.pos[r]; w.tm2[r] = mt.isE[r] ? 0.0 : (w.y[p] - w.yb[p]); }
     LCQ_SYNC();
-    op_mv(mt.oAt, w.tm2, w.gq, 1.0, w.gq);
+    op_mv_s(mt.oAt, w.tm2, w.gq, 1.0, w.gq);
     LCQ_SYNC();
     LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) w.yb[i] = w.y[i];
     LCQ_SYNC();
@@ -830,9 +922,11 @@ LCQ_DEVN int pas_homotopy(PQP& s)
     bool dc_dirty = true;
     double tau = 0.0;
     LCQ_LOOP for (int it = 0; it < max_iter; it++) {
+        LCQ_PROF(w.sc, 8);
         if (dc_dirty) { dc_from_target(s); dc_dirty = false; }
         else { const double f = 1.0 - tau; LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) w.dc[i] *= f; LCQ_SYNC(); }
         const int nw = s.nw;
+        LCQ_PROF(w.sc, 0);
         // step direction: dy_W = Sinv (db_W + dc_W), dz = Tt[:,W] dy_W - dc
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
             const int i = w.widx[a];
@@ -845,7 +939,9 @@ LCQ_DEVN int pas_homotopy(PQP& s)
             LCQ_SYNC();
             if (LCQ_TID == 0) s.n_solve++;
         }
+        LCQ_PROF(w.sc, 1);
         tt_cols_apply(s, w.vb, w.dz, w.dc);
+        LCQ_PROF(w.sc, 2);
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
             const int i = w.widx[a];
             w.dz[i] = (w.st[i] == ST_LOWER) ? (w.lf[i] - w.l[i]) : (w.uf[i] - w.u[i]);
@@ -893,6 +989,7 @@ LCQ_DEVN int pas_homotopy(PQP& s)
         tau = (code >= 0) ? tmin : 1.0;
         if (!(tau > 1e-25)) tau = 0.0;   // ZERO (QProblem.cpp:5212)
         // step
+        LCQ_PROF(w.sc, 3);
         double hl = 0;
         if (tau > 0.0) {
             LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.y[w.widx[a]] += tau * w.va[a];
@@ -902,7 +999,7 @@ LCQ_DEVN int pas_homotopy(PQP& s)
                 w.l[i] += tau * (w.lf[i] - w.l[i]);
                 w.u[i] += tau * (w.uf[i] - w.u[i]);
             }
-            LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) { double lo, up; row_bounds(*s.d, *s.in, mt.Eidx[e], lo, up); w.bE[e] += tau * (lo - w.bE[e]); }
+            if (s.e_moving) LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) w.bE[e] += tau * (w.bEn[e] - w.bE[e]);
             LCQ_SYNC();
             if (LCQ_TID == 0) s.phi *= (1.0 - tau);
             LCQ_SYNC();
@@ -912,9 +1009,9 @@ LCQ_DEVN int pas_homotopy(PQP& s)
             hl = fmax(hl, fabs(w.lf[i] - w.l[i]) / fmax(fabs(w.lf[i]), 1.0));
             hl = fmax(hl, fabs(w.uf[i] - w.u[i]) / fmax(fabs(w.uf[i]), 1.0));
         }
-        LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) { double lo, up; row_bounds(*s.d, *s.in, mt.Eidx[e], lo, up); hl = fmax(hl, fabs(lo - w.bE[e]) / fmax(fabs(lo), 1.0)); }
+        if (s.e_moving) LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) hl = fmax(hl, fabs(w.bEn[e] - w.bE[e]) / fmax(fabs(w.bEn[e]), 1.0));
         hl = fmax(block_max(hl, w.sc), s.phi * s.len0);
-        if (hl <= kTermTol) return QP_OK;
+        if (hl <= kTermTol) { LCQ_PROF(w.sc, 14); return QP_OK; }
         if (LCQ_TID == 0) s.nwsr++;
         LCQ_SYNC();
         // change the working set (QProblem.cpp:5284-5365)
@@ -922,19 +1019,21 @@ LCQ_DEVN int pas_homotopy(PQP& s)
         if (code >= 0) {
             const int row = code / 3, kind = code - 3 * row;
             if (kind == 0) {
+                LCQ_PROF(w.sc, 4);
                 int p = -1;
                 LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) if (w.widx[a] == row) p = a;
                 double dummy;
                 p = block_argmin2(p >= 0 ? 0.0 : INFINITY, 0, p, &dummy, nullptr, w.sc);
                 pas_remove(s, p);
             } else {
+                LCQ_PROF(w.sc, 5);
                 const int rc = add_with_li(s, row, kind == 1 ? ST_LOWER : ST_UPPER);
                 if (rc) return rc;
             }
             ramp = (tau <= qEPS);
         }
-        if (ramp) { ramping(s); dc_dirty = true; }
-        else drift(s);
+        if (ramp) { LCQ_PROF(w.sc, 7); ramping(s); dc_dirty = true; }
+        else { LCQ_PROF(w.sc, 6); drift(s); }
     }
     return QP_MAXITER;
 }
@@ -946,9 +1045,13 @@ LCQ_DEVN void pas_finish(PQP& s, const RawOps& ro)
     const PWork& w = *s.w;
     const PMats& mt = *s.mt;
     const int n = s.d->n, m = s.d->m, mI = mt.mI, mE = mt.mE;
+    LCQ_PROF(w.sc, 9);
+    // the eliminated rows finish their way here (the homotopy stops within the termination tolerance of the target)
+    if (s.e_moving) { LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) w.bE[e] = w.bEn[e]; LCQ_SYNC(); }
     rebase(s);
+    LCQ_PROF(w.sc, 10);
     LCQ_LOOP for (int pass = 0; pass <= kPolishMax; pass++) {
-        op_mv(mt.oA, w.xq, nullptr, 1.0, w.tm1);   // A_full xq
+        op_mv_s(mt.oA, w.xq, nullptr, 1.0, w.tm1);   // A_full xq
         LCQ_SYNC();
         const int nw = s.nw;
         double rn = 0;
@@ -962,20 +1065,19 @@ LCQ_DEVN void pas_finish(PQP& s, const RawOps& ro)
         rn = block_max(rn, w.sc);
         if (rn <= kPolishTol || pass == kPolishMax) break;
         if (LCQ_TID == 0) s.n_polish++;
-        // dy_W = Sinv (r2W - K[W] r2E) ; dx = P A_W' dy_W + N r2E
-        LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
-            const double* k = mt.K + (size_t)w.widx[a] * mE;
-            double acc = 0;
-            LCQ_LOOP for (int e = 0; e < mE; e++) acc += k[e] * w.tE2[e];
-            w.va[a] -= acc;
+        // dy_W = Sinv (r2W - K[W] r2E) ; dx = P A_W' dy_W + N r2E        (dz is free here: K r2E)
+        if (mE > 0) {
+            op_mv_s(mt.oK, w.tE2, nullptr, 1.0, w.dz);
+            LCQ_SYNC();
+            LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.va[a] -= w.dz[w.widx[a]];
+            LCQ_SYNC();
         }
-        LCQ_SYNC();
         if (nw > 0) { sym_apply(w.Sinv, w.ld, nw, w.va, 1.0, w.vb, nullptr, nullptr, nullptr); LCQ_SYNC(); }
         LCQ_LOOP for (int r = LCQ_TID; r < m; r += LCQ_NT) w.tm2[r] = 0.0;
         LCQ_SYNC();
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) { const int i = w.widx[a]; w.tm2[mt.Iidx[i]] = w.vb[a]; w.y[i] += w.vb[a]; }
         LCQ_SYNC();
-        x_update(s, nullptr, w.tE2);
+        x_update(s, nullptr, mE > 0 ? w.tE2 : nullptr);
     }
     // z = (A_full xq)_I (tm1 holds A_full xq of the accepted point), c consistent with it; duals in full row order.
     // The polish moves multipliers by round-off: their signs are re-established as the drift correction of every
@@ -994,15 +1096,18 @@ LCQ_DEVN void pas_finish(PQP& s, const RawOps& ro)
         LCQ_SYNC();
         op_mv(ro.Q, w.xq, w.gq, 1.0, w.tn);
         LCQ_SYNC();
-        op_mv(mt.oAt, w.tm2, w.tn, -1.0, w.tn);
+        op_mv_s(mt.oAt, w.tm2, w.tn, -1.0, w.tn);
         LCQ_SYNC();
-        op_mv(mt.oN0t, w.tn, nullptr, 1.0, w.yE);
+        op_mv_s(mt.oN0t, w.tn, nullptr, 1.0, w.yE);
         LCQ_SYNC();
     }
     LCQ_LOOP for (int r = LCQ_TID; r < m; r += LCQ_NT) w.ys[r] = mt.isE[r] ? w.yE[mt.pos[r]] : w.y[mt.pos[r]];
     LCQ_SYNC();
     (void)n;
     c_from_state(s);
+    if (LCQ_TID == 0) s.e_moving = 0;   // the eliminated rows sit on their true bounds from here on
+    LCQ_SYNC();
+    LCQ_PROF(w.sc, 11);
 }
 
 // QProblem::hotstart (QProblem.cpp:446-640): far bounds around the homotopy loop.  gk holds the new gradient.
@@ -1011,6 +1116,7 @@ LCQ_DEVN int pas_hotstart(PQP& s, const RawOps& ro)
     const PWork& w = *s.w;
     const PMats& mt = *s.mt;
     const int m = s.d->m, mI = mt.mI;
+    LCQ_PROF(w.sc, 14);
     // areBoundsConsistent (:2647-2662) and the largest finite bound (:528-540)
     int bad = 0;
     double far = kFar0;
@@ -1021,6 +1127,7 @@ LCQ_DEVN int pas_hotstart(PQP& s, const RawOps& ro)
         if (up < qINFTY && up > far) far = up;
         if (lo > -qINFTY && lo < -far) far = -lo;
     }
+    LCQ_LOOP for (int e = LCQ_TID; e < mt.mE; e += LCQ_NT) { double lo, up; row_bounds(*s.d, *s.in, mt.Eidx[e], lo, up); w.bEn[e] = lo; }
     bad = block_or(bad, w.sc);
     if (bad) return QP_INFEASIBLE_BOUNDS;
     far = block_max(far, w.sc);
@@ -1064,10 +1171,11 @@ LCQ_DEVN int pas_init(PQP& s, const RawOps& ro, const double* x0, const double* 
     const PDims& d = *s.d;
     const int n = d.n, m = d.m, mI = mt.mI, mE = mt.mE;
     const bool have_y = (y0A != nullptr);
-    if (LCQ_TID == 0) { s.nw = 0; s.stamp_next = mI; s.rampOffset = 0; s.phi = 1.0; s.len0 = 0.0; s.nwsr = 0; }
+    LCQ_PROF(w.sc, 12);
+    if (LCQ_TID == 0) { s.nw = 0; s.stamp_next = mI; s.rampOffset = 0; s.phi = 1.0; s.len0 = 0.0; s.nwsr = 0; s.e_moving = 1; }
     LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xq[j] = x0 ? x0[j] : 0.0;
     LCQ_SYNC();
-    op_mv(mt.oA, w.xq, nullptr, 1.0, w.tm1);   // A_full x0
+    op_mv_s(mt.oA, w.xq, nullptr, 1.0, w.tm1);   // A_full x0
     LCQ_SYNC();
     // full-order duals of the guess in tm2
     LCQ_LOOP for (int r = LCQ_TID; r < m; r += LCQ_NT) w.tm2[r] = !have_y ? 0.0 : (r < d.mA ? y0A[r] : (y0box ? y0box[r - d.mA] : 0.0));
@@ -1112,7 +1220,7 @@ LCQ_DEVN int pas_init(PQP& s, const RawOps& ro, const double* x0, const double* 
     LCQ_SYNC();
     // setupAuxiliaryQPgradient (:2602-2641): gq = -H x0 + A_full' y  -- H x0 through the raw Q operator is the caller's
     // (gq arrives holding -Q x0); add A_full' y
-    op_mv(mt.oAt, w.tm2, w.gq, 1.0, w.gq);
+    op_mv_s(mt.oAt, w.tm2, w.gq, 1.0, w.gq);
     LCQ_SYNC();
     set_target(s);
     ramping(s);
@@ -1126,11 +1234,11 @@ LCQ_DEVN int pas_init(PQP& s, const RawOps& ro, const double* x0, const double* 
 // out = Q v + rho (L'(R v) + R'(L v)) + add ; leaves Lx = L v, Rx = R v
 LCQ_DEVN void pqk_apply(const RawOps& ro, double rho, const double* v, const double* add, double* out, const PWork& w)
 {
-    op_mv(ro.Q, v, add, 1.0, w.tn);
+    op_mv(ro.Q, v, add, 1.0, w.tq);
     op_mv(ro.L, v, nullptr, 1.0, w.Lx);
     op_mv(ro.R, v, nullptr, 1.0, w.Rx);
     LCQ_SYNC();
-    op_mv(ro.Lt, w.Rx, w.tn, rho, out);
+    op_mv(ro.Lt, w.Rx, w.tq, rho, out);
     LCQ_SYNC();
     op_mv(ro.Rt, w.Lx, out, rho, out);
     LCQ_SYNC();

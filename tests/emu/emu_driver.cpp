@@ -190,7 +190,7 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
     const int mEc = mats_shared ? mt.mE : (d.m < d.n ? d.m : d.n);
     const int mIc = mats_shared ? mt.mI : d.m;
     const int capc = mats_shared ? pas_cap(d, mt.mE, mt.mI) : ((d.n < d.m) ? d.n : d.m);
-    std::vector<double> smem_d(pas_smem_bytes(mIc, capc) / 8 + 8);
+    std::vector<double> smem_d(pas_smem_bytes(d, mEc, mIc, capc) / 8 + 8);
     std::vector<double> gl(pas_gl_doubles(d, mEc, capc) + 8);
     PWork wk;
     pas_carve(wk, d, mEc, mIc, capc, reinterpret_cast<unsigned char*>(smem_d.data()), gl.data());
