@@ -188,6 +188,10 @@ __global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_solve_kernel(const __g
 // The parametric active-set path (lcqp_pas.cuh)
 // =================================================================================================
 constexpr int kPasGroupsMax = 8;
+#ifndef LCQP_PAS_CTA_THREADS
+#define LCQP_PAS_CTA_THREADS 512
+#endif
+constexpr int kPasCtaThreads = LCQP_PAS_CTA_THREADS;   // threads of a solver CTA (the register budget per thread follows)
 
 struct PasArgs {
     pas::PDims d;
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(kPrepThreads) pas_prepare_kernel(const __grid_
 
 // The solver: persistent CTAs of blockDim.y groups x blockDim.x threads; every group works on one LCQP instance at a
 // time (pulled from a global counter) with its own control flow and its own named barrier.
-__global__ void __launch_bounds__(kMaxCtaThreads, 1) lcqp_pas_kernel(const __grid_constant__ PasArgs a)
+__global__ void __launch_bounds__(kPasCtaThreads, 1) lcqp_pas_kernel(const __grid_constant__ PasArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ pas::PMats mt_s[kPasGroupsMax];
@@ -964,7 +968,7 @@ static int run_pas(lcqp_cuda_handle h, cudaStream_t stream)
     // a CTA is G groups of T threads; every group keeps the row vectors of its instance in shared memory
     int threads = 128;
     if (const char* t = getenv("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) threads = v; }
-    int gmax = kMaxCtaThreads / threads;
+    int gmax = kPasCtaThreads / threads;
     if (gmax > kPasGroupsMax) gmax = kPasGroupsMax;
     if (const char* t = getenv("LCQP_CUDA_GROUPS")) { const int v = atoi(t); if (v >= 1 && v < gmax) gmax = v; }
     if (gmax > h->batch) gmax = h->batch;

@@ -522,6 +522,19 @@ LCQ_DEV void pas_carve(PWork& w, const PDims& d, int mE, int mI, int cap, unsign
 }
 
 // ---- small block-wide helpers ----------------------------------------------------------------------
+// two block-wide maxima with one pair of barriers
+LCQ_DEV void block_max2(double& a, double& b, Scalars* sc)
+{
+    a = warp_max(a);
+    b = warp_max(b);
+    LCQ_SYNC();
+    if (LCQ_LANE == 0) { sc->red[LCQ_WARP] = a; sc->red[32 + LCQ_WARP] = b; }
+    LCQ_SYNC();
+    double x = sc->red[0], y = sc->red[32];
+    LCQ_LOOP for (int k = 1; k < LCQ_NWARP; k++) { x = fmax(x, sc->red[k]); y = fmax(y, sc->red[32 + k]); }
+    a = x; b = y;
+}
+
 // lexicographic argmin over (value, rank): smallest value, ties -> smallest rank; idx < 0: no candidate
 LCQ_DEV bool lex2_better(double a, int ra, int ia, double b, int rb, int ib)
 {
@@ -615,6 +628,7 @@ LCQ_DEVN void pas_append(PQP& s, int k, int status, double p)
     if (nw > 0) rank1_update_full(w.Sinv, ld, nw, w.vb, ip);
     double* row = w.Sinv + (size_t)nw * ld;
     LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) { const double v = -w.vb[a] * ip; row[a] = v; w.Sinv[(size_t)a * ld + nw] = v; }
+    LCQ_SYNC();   // every thread has read s.nw
     if (LCQ_TID == 0) {
         row[nw] = ip;
         w.widx[nw] = k;
@@ -664,7 +678,7 @@ LCQ_DEVN void pas_remove(PQP& s, int p)
 // out (mI) = Tt[:, W] v - sub   (v over the working set; reads rows W of the symmetric Tt).  v, out, sub in shared
 // memory.  A pair of adjacent lanes owns two adjacent columns (one 16-byte load per row) and splits the rows of the
 // working set in two halves; twelve loads are in flight per thread; one shuffle joins the halves.
-LCQ_DEVN void tt_cols_apply(const PQP& s, const double* v, double* out, const double* sub)
+LCQ_DEVN void tt_cols_apply(const PQP& s, const double* v, double* out, const double* sub, bool skip_active = false)
 {
     const PWork& w = *s.w;
     const int mI = s.mt->mI, ldI = s.mt->ldI, nw = s.nw;
@@ -674,8 +688,10 @@ LCQ_DEVN void tt_cols_apply(const PQP& s, const double* v, double* out, const do
     const int half = (nw + 1) >> 1;
     LCQ_LOOP for (int t0 = 0; t0 < 2 * npair; t0 += LCQ_NT) {
         const int t = t0 + LCQ_TID;
-        const bool act = t < 2 * npair;
+        bool act = t < 2 * npair;
         const int c = t >> 1, h = t & 1;
+        // (both lanes of a pair take the same decision: the shuffle below stays convergent)
+        if (act && skip_active && w.st[2 * c] != ST_INACTIVE && (2 * c + 1 >= mI || w.st[2 * c + 1] != ST_INACTIVE)) act = false;
         int b = act ? (h ? half : 0) : 0;
         const int b1 = act ? (h ? nw : half) : 0;
         double x0 = 0, x1 = 0, y0 = 0, y1 = 0;
@@ -940,7 +956,7 @@ LCQ_DEVN int pas_homotopy(PQP& s)
             if (LCQ_TID == 0) s.n_solve++;
         }
         LCQ_PROF(w.sc, 1);
-        tt_cols_apply(s, w.vb, w.dz, w.dc);
+        tt_cols_apply(s, w.vb, w.dz, w.dc, true);
         LCQ_PROF(w.sc, 2);
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) {
             const int i = w.widx[a];
@@ -991,26 +1007,27 @@ LCQ_DEVN int pas_homotopy(PQP& s)
         // step
         LCQ_PROF(w.sc, 3);
         double hl = 0;
-        if (tau > 0.0) {
-            LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.y[w.widx[a]] += tau * w.va[a];
-            LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) {
+        // step, and the remaining relative homotopy length (QProblem.cpp:5372-5410) in the same sweep
+        if (tau > 0.0) LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.y[w.widx[a]] += tau * w.va[a];
+        LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) {
+            const double lfi = w.lf[i], ufi = w.uf[i];
+            double li = w.l[i], ui = w.u[i];
+            if (tau > 0.0) {
                 w.z[i] += tau * w.dz[i];
                 w.c[i] += tau * w.dc[i];
-                w.l[i] += tau * (w.lf[i] - w.l[i]);
-                w.u[i] += tau * (w.uf[i] - w.u[i]);
+                li += tau * (lfi - li); ui += tau * (ufi - ui);
+                w.l[i] = li; w.u[i] = ui;
             }
-            if (s.e_moving) LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) w.bE[e] += tau * (w.bEn[e] - w.bE[e]);
-            LCQ_SYNC();
-            if (LCQ_TID == 0) s.phi *= (1.0 - tau);
-            LCQ_SYNC();
+            hl = fmax(hl, fmax(fabs(lfi - li) / fmax(fabs(lfi), 1.0), fabs(ufi - ui) / fmax(fabs(ufi), 1.0)));
         }
-        // remaining relative homotopy length (QProblem.cpp:5372-5410)
-        LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) {
-            hl = fmax(hl, fabs(w.lf[i] - w.l[i]) / fmax(fabs(w.lf[i]), 1.0));
-            hl = fmax(hl, fabs(w.uf[i] - w.u[i]) / fmax(fabs(w.uf[i]), 1.0));
+        if (s.e_moving) LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) {
+            double be = w.bE[e];
+            if (tau > 0.0) { be += tau * (w.bEn[e] - be); w.bE[e] = be; }
+            hl = fmax(hl, fabs(w.bEn[e] - be) / fmax(fabs(w.bEn[e]), 1.0));
         }
-        if (s.e_moving) LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) hl = fmax(hl, fabs(w.bEn[e] - w.bE[e]) / fmax(fabs(w.bEn[e]), 1.0));
-        hl = fmax(block_max(hl, w.sc), s.phi * s.len0);
+        if (LCQ_TID == 0 && tau > 0.0) s.phi *= (1.0 - tau);
+        hl = block_max(hl, w.sc);
+        hl = fmax(hl, s.phi * s.len0);
         if (hl <= kTermTol) { LCQ_PROF(w.sc, 14); return QP_OK; }
         if (LCQ_TID == 0) s.nwsr++;
         LCQ_SYNC();
@@ -1062,11 +1079,14 @@ LCQ_DEVN void pas_finish(PQP& s, const RawOps& ro)
             w.va[a] = r;
             rn = fmax(rn, fabs(r));
         }
-        rn = block_max(rn, w.sc);
+        double rnE = 0;
+        LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) rnE = fmax(rnE, fabs(w.tE2[e]));
+        block_max2(rn, rnE, w.sc);
         if (rn <= kPolishTol || pass == kPolishMax) break;
         if (LCQ_TID == 0) s.n_polish++;
+        const bool eq_part = (mE > 0) && (rnE > 0.01 * kPolishTol);
         // dy_W = Sinv (r2W - K[W] r2E) ; dx = P A_W' dy_W + N r2E        (dz is free here: K r2E)
-        if (mE > 0) {
+        if (eq_part) {
             op_mv_s(mt.oK, w.tE2, nullptr, 1.0, w.dz);
             LCQ_SYNC();
             LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.va[a] -= w.dz[w.widx[a]];
@@ -1077,7 +1097,7 @@ LCQ_DEVN void pas_finish(PQP& s, const RawOps& ro)
         LCQ_SYNC();
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) { const int i = w.widx[a]; w.tm2[mt.Iidx[i]] = w.vb[a]; w.y[i] += w.vb[a]; }
         LCQ_SYNC();
-        x_update(s, nullptr, mE > 0 ? w.tE2 : nullptr);
+        x_update(s, nullptr, eq_part ? w.tE2 : nullptr);
     }
     // z = (A_full xq)_I (tm1 holds A_full xq of the accepted point), c consistent with it; duals in full row order.
     // The polish moves multipliers by round-off: their signs are re-established as the drift correction of every
