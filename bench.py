@@ -2,14 +2,22 @@
 """bench.py -- throughput of the LCQP hot path (LCQProblem::runSolver + QP subsolver) on B200.
 
 Metric (BASELINE.json): LCQPs solved / second, batched, on N GPUs of one node.
-Workload: config C2 of SURVEY.md 8(d) -- OptimizeOnCircle-shaped LCQPs (nV=202, nC=101, nComp=100) that
-share Q/A/L/R/lbA/ubA and differ in g and x0 (examples/OptimizeOnCircle.cpp:62-99 with a random x_ref per
-instance), stationarityTolerance = 1e-2 as the example sets it, perturbStep on (the default).
+Workloads, chosen by --config:
+  c2 (default, the configuration the metric is quoted on): OptimizeOnCircle-shaped LCQPs (nV=202, nC=101,
+      nComp=100) sharing Q/A/L/R/lbA/ubA, per-instance g and x0 (examples/OptimizeOnCircle.cpp:62-99 with a random
+      x_ref per instance), stationarityTolerance = 1e-2 as the example sets it; 2^20 instances per GPU per step.
+  c5: random dense LCQPs (n=64, 32 pairs, 16 constraints), every matrix per instance; 131072 per GPU per step.
+  c3: examples/example_data (nV=151, nC=50, nComp=100, box bounds) replicated with perturbed g / lbA=ubA / ub.
+perturbStep is on (the default of the reference's Options).
 
 One "step" = one pass of the hot path over one batch of `--batch` instances per GPU (weak scaling).
   value : whole-job LCQPs/s, inputs already resident in HBM when the timed region starts (CUDA events).
-  e2e   : the same metric through the C ABI with HOST (pinned) buffers: H2D of g/x0, run, D2H of x and the
-          statistics inside the timed region.
+  e2e   : the same metric through the C ABI with HOST (pinned) buffers: H2D of the per-instance inputs, run, D2H of
+          x, the duals and the statistics inside the timed region.
+  parity_subset : outside the timed region, `--parity` random instances of the batch are solved once more with
+          perturbStep off (the reference's perturbation draws libc rand() seeded by time(NULL)) on the GPU and by the
+          reference's qpOASES run (oracle/_ref); mismatches in ReturnValue / stationarity type / outer and total
+          iteration counts / x (1e-6) are counted.
   --impl reference : the reference's own CPU implementation of the path (oracle/_ref = unmodified LCQPow +
           qpOASES + OSQP when it was built, else the plain-C oracle port) on all host cores, same config.
 
@@ -36,8 +44,50 @@ if ROOT not in sys.path:
 
 METRIC = "lcqps_solved_per_sec"
 UNIT = "LCQP/s"
-NV, NC, NCOMP = 202, 101, 100
 STAT_TOL = 10e-3  # examples/OptimizeOnCircle.cpp:45
+
+
+class Config:
+    """A workload: generator, dimensions, option overrides, the reference subsolver that ships with it."""
+
+    def __init__(self, name):
+        self.name = name
+        if name == "c2":
+            self.nV, self.nC, self.nComp = 202, 101, 100
+            self.over = {"stationarityTolerance": STAT_TOL}
+            self.default_batch = 1 << 20
+            self.workload = "C2 OptimizeOnCircle N=100 (nV=202,nC=101,nComp=100), shared Q/A/L/R, per-instance g/x0"
+            self.ref_solver_shipped = 2   # OSQP_SPARSE (examples/OptimizeOnCircle.cpp:44)
+            self.ref_solver_parity = 1    # QPOASES_SPARSE: the exact-QP flavour the CUDA path reproduces
+            self.cpu_per_core = 48
+        elif name == "c5":
+            self.nV, self.nC, self.nComp = 64, 16, 32
+            self.over = {}
+            self.default_batch = 1 << 17
+            self.workload = "C5 random dense LCQPs (n=64, 32 pairs, nC=16), every matrix per instance"
+            self.ref_solver_shipped = 0   # QPOASES_DENSE
+            self.ref_solver_parity = 0
+            self.cpu_per_core = 256
+        elif name == "c3":
+            self.nV, self.nC, self.nComp = 151, 50, 100
+            self.over = {}
+            self.default_batch = 10000
+            self.workload = "C3 examples/example_data (nV=151,nC=50,nComp=100, box) x batch with perturbed g/lbA=ubA/ub"
+            self.ref_solver_shipped = 1   # QPOASES_SPARSE (examples/solve_lcqp_from_file.cpp:128)
+            self.ref_solver_parity = 0
+            self.cpu_per_core = 16
+        else:
+            raise SystemExit("unknown --config " + name)
+
+    def generate(self, n, lo=0, hi=None):
+        from lcqpow_b200 import problems as P
+        hi = n if hi is None else hi
+        if self.name == "c2":
+            return P.circle_batch_fast(n).slice(lo, hi)
+        if self.name == "c5":
+            return P.dense_random_batch(hi, seed_lo=lo) if lo else P.dense_random_batch(hi)
+        data = dict(np.load(os.path.join(ROOT, "tests", "golden", "example_data.npz")))
+        return P.example_data_batch(data, n).slice(lo, hi)
 
 
 def load_peaks():
@@ -105,63 +155,72 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arms (rank 0 only).  The only place where bench.py executes oracle/.
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    kind, lo, hi, seed0 = args
-    from lcqpow_b200 import problems as P
-    from oracle import pyref
-    pb = P.circle_batch_fast(hi, seed0=seed0).slice(lo, hi)
-    if kind == "reference":
-        lib = pyref.RefLib()
-        o = lib.default_options(qpSolver=pyref.OSQP_SPARSE, stationarityTolerance=STAT_TOL)  # as shipped (:44-45)
-    else:
-        lib = pyref.OracleLib()
-        o = lib.default_options(stationarityTolerance=STAT_TOL)
-    t = time.perf_counter()
-    s = lib.solve_batch(pb, o)
-    return time.perf_counter() - t, int((s.res["ret"] == 0).sum()), hi - lo
+_REFLIB = None   # loaded once in the parent (the driver's loaded-library hook sees it); fork()ed workers inherit it
 
 
 def cpu_kind():
     from oracle import pyref
+    global _REFLIB
     if pyref.have_ref():
+        if _REFLIB is None:
+            _REFLIB = pyref.RefLib()
         return "reference"
     if not os.path.exists(pyref.ORACLE_SO):
         subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True)
     return "port"
 
 
-def cpu_pass(kind: str, cores: int, per_core: int, seed0: int, pool):
+def _cpu_worker(args):
+    """Solve instances [lo, hi) of the config's family serially in this process.  perturb < 0: options default."""
+    kind, cfg_name, lo, hi, total, solver, perturb, want_x = args
+    from oracle import pyref
+    cfg = Config(cfg_name)
+    pb = cfg.generate(total, lo, hi)
+    if kind == "reference":
+        lib = _REFLIB if _REFLIB is not None else pyref.RefLib()
+        o = lib.default_options(qpSolver=solver, **cfg.over)
+    else:
+        lib = pyref.OracleLib()
+        o = lib.default_options(**cfg.over)
+    if perturb >= 0:
+        o.perturbStep = perturb
+    t = time.perf_counter()
+    s = lib.solve_batch(pb, o)
+    dt = time.perf_counter() - t
+    return dt, int((s.res["ret"] == 0).sum()), hi - lo, (s.x if want_x else None), (s.res if want_x else None)
+
+
+def cpu_pass(kind, cfg, cores, per_core, total, pool):
     """One pass: `cores` processes, each solving `per_core` instances serially.  Returns (LCQP/s, solved, n, wall)."""
-    jobs = [(kind, c * per_core, (c + 1) * per_core, seed0) for c in range(cores)]
+    jobs = [(kind, cfg.name, c * per_core, (c + 1) * per_core, total, cfg.ref_solver_shipped, -1, False) for c in range(cores)]
     t = time.perf_counter()
     out = pool.map(_cpu_worker, jobs)
     wall = time.perf_counter() - t
-    n = sum(o[2] for o in out)
-    solved = sum(o[1] for o in out)
-    return n / wall, solved, n, wall
+    return sum(o[2] for o in out) / wall, sum(o[1] for o in out), sum(o[2] for o in out), wall
 
 
-def cpu_sample_desc(kind, cores, per_core):
-    what = ("unmodified reference (oracle/_ref: LCQPow + OSQP 0.6.2, QPSolver::OSQP_SPARSE as shipped in "
-            "examples/OptimizeOnCircle.cpp:44)") if kind == "reference" else "plain-C oracle port (oracle/lcqp_oracle.c)"
-    return f"first {cores * per_core} instances of the same C2 batch, {per_core} per process, {cores} processes, {what}"
+def cpu_sample_desc(kind, cfg, cores, per_core):
+    names = {0: "QPOASES_DENSE", 1: "QPOASES_SPARSE", 2: "OSQP_SPARSE"}
+    what = (f"unmodified reference (oracle/_ref: LCQPow + qpOASES 3.2 + OSQP 0.6.2), QPSolver::{names[cfg.ref_solver_shipped]} "
+            "as the reference's example ships it") if kind == "reference" else "plain-C oracle port (oracle/lcqp_oracle.c)"
+    return (f"first {cores * per_core} instances of the same {cfg.name.upper()} batch, {per_core} per process, {cores} processes, {what}")
 
 
-# ------------------------------------------------------------------------------------------------
-def run_reference_arm(args, rank, world):
+def run_reference_arm(args, cfg, rank, world):
     if rank != 0:
         return
     kind = cpu_kind()
     cores = len(os.sched_getaffinity(0))
-    per_core = args.cpu_per_core
+    per_core = args.cpu_per_core or cfg.cpu_per_core
+    total = cores * per_core
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_pass(kind, cores, max(1, per_core // 4), 20000, pool)
+            cpu_pass(kind, cfg, cores, max(1, per_core // 4), total, pool)
         t = time.perf_counter()
         n = solved = 0
         for _ in range(args.steps):
-            _, s, k, _ = cpu_pass(kind, cores, per_core, 20000, pool)
+            _, s, k, _ = cpu_pass(kind, cfg, cores, per_core, total, pool)
             n += k
             solved += s
         wall = time.perf_counter() - t
@@ -169,12 +228,73 @@ def run_reference_arm(args, rank, world):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 OptimizeOnCircle N=100 (nV=202,nC=101,nComp=100), shared Q/A/L/R, per-instance g/x0",
-                       "instances_per_step": cores * per_core, "stationarityTolerance": STAT_TOL},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_desc(kind, cores, per_core)},
+            "config": {"workload": cfg.workload, "instances_per_step": cores * per_core,
+                       "sample": "bounded sample of the workload: the first instances_per_step instances of the same family",
+                       **cfg.over},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": cpu_sample_desc(kind, cfg, cores, per_core)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "solved_frac": solved / max(1, n)}
     print(json.dumps(line))
+
+
+def parity_subset(cfg, prob_cls, L, pb, batch, lo_global, n_check, device, seed=12345):
+    """`n_check` random instances of this rank's batch, perturbStep off: GPU against the reference's qpOASES run."""
+    kind = cpu_kind()
+    rng = np.random.default_rng(seed)
+    idx = np.sort(rng.choice(batch, size=min(n_check, batch), replace=False))
+    sub = pb.normalised()
+    kw = {}
+    for f in L.api.FIELDS:
+        a = getattr(sub, f)
+        kw[f] = None if a is None else (a if f in pb.shared else np.ascontiguousarray(a[idx]))
+    import dataclasses
+    sub = dataclasses.replace(sub, batch=len(idx), **kw)
+    prob = prob_cls(cfg.nV, cfg.nC, cfg.nComp, len(idx), device=device)
+    o = L.Options()
+    o.setPerturbStep(False)
+    for k, v in cfg.over.items():
+        getattr(o, "set" + k[0].upper() + k[1:])(v)
+    prob.setOptions(o)
+    assert prob.loadBatch(sub) == 0
+    prob.runSolver()
+    x, st = prob.getPrimalSolution(), prob.getOutputStatistics()
+    prob.close()
+    # reference: the same instances, one slice per core
+    from oracle import pyref
+    cores = len(os.sched_getaffinity(0))
+    lib = _REFLIB if kind == "reference" else pyref.OracleLib()
+    chunks = np.array_split(np.arange(len(idx)), cores)
+    def solve_chunk(ch):
+        kw2 = {}
+        for f in L.api.FIELDS:
+            a = getattr(sub, f)
+            kw2[f] = None if a is None else (a if f in pb.shared else np.ascontiguousarray(a[ch]))
+        s2 = dataclasses.replace(sub, batch=len(ch), **kw2)
+        oo = lib.default_options(perturbStep=0, **cfg.over) if kind != "reference" else lib.default_options(perturbStep=0, qpSolver=cfg.ref_solver_parity, **cfg.over)
+        return lib.solve_batch(s2, oo)
+    # threads would serialise on the reference's globals: fork one process per chunk
+    ctx = mp.get_context("fork")
+    global _PARITY_JOB
+    _PARITY_JOB = solve_chunk
+    with ctx.Pool(cores) as pool:
+        outs = pool.map(_parity_call, [c for c in chunks if len(c)])
+    rx = np.concatenate([o.x for o in outs]); rres = np.concatenate([o.res for o in outs])
+    mism = 0
+    for b in range(len(idx)):
+        same = (rres["ret"][b] == st["ret"][b] and rres["status"][b] == st["status"][b] and rres["iterOuter"][b] == st["iterOuter"][b]
+                and rres["iterTotal"][b] == st["iterTotal"][b])
+        if same and rres["ret"][b] == 0:
+            same = np.abs(rx[b] - x[b]).max() <= 1e-6 * max(1.0, np.abs(rx[b]).max())
+        mism += (not same)
+    return {"n": int(len(idx)), "mismatches": int(mism), "checker": kind,
+            "criterion": "ReturnValue, stationarity type, iterOuter, iterTotal identical; x within 1e-6 relative; perturbStep off"}
+
+
+_PARITY_JOB = None
+
+
+def _parity_call(ch):
+    return _PARITY_JOB(ch)
 
 
 def main():
@@ -183,26 +303,27 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="instances per GPU per step (0: largest power of two <= 2^20 "
-                    "whose step is estimated to take <= --step-seconds)")
-    ap.add_argument("--step-seconds", type=float, default=8.0)
-    ap.add_argument("--cpu-per-core", type=int, default=48, help="instances per host process in the CPU baseline")
+    ap.add_argument("--config", default="c2", choices=["c2", "c5", "c3"])
+    ap.add_argument("--batch", type=int, default=0, help="instances per GPU per step (0: the configuration's own size: "
+                    "2^20 for c2, 2^17 for c5, 10000 for c3)")
+    ap.add_argument("--cpu-per-core", type=int, default=0, help="instances per host process in the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity", type=int, default=1024, help="instances of the parity subset (0: skip)")
     ap.add_argument("--perturb", type=int, default=1)
     args = ap.parse_args()
+    cfg = Config(args.config)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference_arm(args, rank, world)
+        run_reference_arm(args, cfg, rank, world)
         return
 
     import torch
     import torch.distributed as dist
     import lcqpow_b200 as L
-    from lcqpow_b200 import problems as P
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
@@ -211,40 +332,21 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     hbm_gbs, bf16_tf, peak_src = load_peaks()
+    NV, NC, NCOMP = cfg.nV, cfg.nC, cfg.nComp
 
     def make_options():
         o = L.Options()
-        o.setStationarityTolerance(STAT_TOL)
+        for k, v in cfg.over.items():
+            getattr(o, "set" + k[0].upper() + k[1:])(v)
         o.setPerturbStep(bool(args.perturb))
         return o
 
-    # ---- choose the per-GPU batch ---------------------------------------------------------------
-    batch = args.batch
-    if batch <= 0:
-        probe = 2048
-        pb = P.circle_batch_fast(probe)
-        pr = L.LCQProblemBatch(NV, NC, NCOMP, probe, device=local_rank)
-        pr.setOptions(make_options())
-        pr.loadBatch(pb)
-        pr.runSolver()
-        t = time.perf_counter()
-        pr.runSolver()
-        rate = probe / (time.perf_counter() - t)
-        pr.close()
-        batch = 1 << 20
-        while batch > 4096 and batch / rate > args.step_seconds:
-            batch >>= 1
-        if world > 1:
-            tb = torch.tensor([batch], device=dev, dtype=torch.int64)
-            dist.all_reduce(tb, op=dist.ReduceOp.MIN)
-            batch = int(tb.item())
+    batch = args.batch if args.batch > 0 else cfg.default_batch
 
     # ---- inputs: the same family on every rank, instances [rank*batch, (rank+1)*batch) ------------
     from lcqpow_b200 import sharding
     lo, hi = sharding.shard_range(batch * world, rank, world)
-    pb_all = P.circle_batch_fast(batch * world)
-    pb = pb_all.slice(lo, hi).normalised()
-    del pb_all
+    pb = cfg.generate(batch * world, lo, hi).normalised()
     shared = tuple(pb.shared)
     prob = L.LCQProblemBatch(NV, NC, NCOMP, batch, device=local_rank)
     assert prob.setOptions(make_options()) == 0
@@ -269,10 +371,12 @@ def main():
             t = torch.from_numpy(a).pin_memory()
             pin[f] = t.numpy()
             pin["_keep_" + f] = t
+    nD = NV + NC + 2 * NCOMP
     x_pin_t = torch.empty((batch, NV), dtype=torch.float64).pin_memory()
+    y_pin_t = torch.empty((batch, nD), dtype=torch.float64).pin_memory()
     st_pin_t = torch.empty((batch, L.api.STATS_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
     h2d = sum(pin[f].nbytes for f in L.api.FIELDS if pin[f] is not None and f not in shared)
-    d2h = x_pin_t.numel() * 8 + st_pin_t.numel()
+    d2h = x_pin_t.numel() * 8 + y_pin_t.numel() * 8 + st_pin_t.numel()
 
     stream = torch.cuda.current_stream(dev)
 
@@ -287,10 +391,9 @@ def main():
         rc = prob.loadLCQP(**{f: pin[f] for f in L.api.FIELDS}, batch=batch, shared=shared)
         assert rc == 0, rc
         prob.runSolver(stream=0, sync=False)
-        rc = prob.lib.lcqp_cuda_get_primal(prob.h, C.c_void_p(x_pin_t.data_ptr()))
-        assert rc == 0, rc
-        rc = prob.lib.lcqp_cuda_get_stats(prob.h, C.c_void_p(st_pin_t.data_ptr()))
-        assert rc == 0, rc
+        for fn, buf in ((prob.lib.lcqp_cuda_get_primal, x_pin_t), (prob.lib.lcqp_cuda_get_dual, y_pin_t), (prob.lib.lcqp_cuda_get_stats, st_pin_t)):
+            rc = fn(prob.h, C.c_void_p(buf.data_ptr()))
+            assert rc == 0, rc
 
     def barrier():
         if world > 1:
@@ -305,22 +408,23 @@ def main():
     sampler.start()
     l0 = prob.launchCount()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    solve_ms = []
     barrier()
     e0.record(stream)
+    k_ms_sum = 0.0
     for _ in range(args.steps):
         step_resident()
-        # per-launch duration of the dominant kernel, from the library's own events on the launching stream
-        # (queried after the loop would serialise nothing: cudaEventElapsedTime only reads)
+        # duration of the dominant kernel of this step from the library's own CUDA events on the launching stream
+        # (reading them waits for the launch; the next step would wait for it anyway: a load reuses the staging state)
+        k_ms_sum += prob.lastRunMs()[0]
     e1.record(stream)
     barrier()
     elapsed_ms = e0.elapsed_time(e1)
     launches = prob.launchCount() - l0
-    k_ms, tot_ms = prob.lastRunMs()
-    solve_ms.append(k_ms)
+    k_ms = k_ms_sum / args.steps
     clocks = sampler.stop()
     st = prob.getOutputStatistics()
     x = prob.getPrimalSolution()
+    grid, smem_b, mE = prob.lastLaunchInfo()
 
     # ---- e2e leg ------------------------------------------------------------------------------------
     for _ in range(2):
@@ -334,59 +438,81 @@ def main():
 
     # max over ranks
     elapsed_ms, e2e_ms, k_ms = sharding.reduce_scalars([elapsed_ms, e2e_s * 1e3, float(k_ms)], "max", dev)
-    n_solved, n_units, n_outer, n_sub = sharding.reduce_scalars(
+    n_solved, n_units, n_total_it, n_outer_it, n_sub = sharding.reduce_scalars(
         [float((st["ret"] == 0).sum()), float(st["kktSolves"].sum()) + float(st["admmIters"].sum()),
-         float(st["iterTotal"].sum()), float(st["subproblemIter"].sum())], "sum", dev)
-    total = batch * world * args.steps
+         float(st["iterTotal"].sum()), float(st["iterOuter"].sum()), float(st["subproblemIter"].sum())], "sum", dev)
+
+    par = None
+    if args.parity > 0 and rank == 0:
+        try:
+            par = parity_subset(cfg, L.LCQProblemBatch, L, pb, batch, lo, args.parity, local_rank)
+        except Exception as ex:  # the checker is absent on this box: say so, do not fail the measurement
+            par = {"n": 0, "mismatches": None, "error": repr(ex)}
 
     if rank == 0:
-        # the metric counts SOLVED LCQPs (terminal ReturnValue SUCCESSFUL_RETURN), every step solves the same batch
-        if n_solved < 0.5 * batch * world:
-            raise SystemExit(f"bench.py: only {n_solved:.0f} of {batch * world} instances were solved -- the CUDA path is broken, "
+        nb = batch * world
+        ret_hist = {int(k): int(v) for k, v in zip(*np.unique(st["ret"], return_counts=True))}
+        # the metric counts SOLVED LCQPs (terminal ReturnValue SUCCESSFUL_RETURN); every step solves the same batch
+        if cfg.name != "c3" and n_solved < 0.5 * nb:
+            raise SystemExit(f"bench.py: only {n_solved:.0f} of {nb} instances were solved -- the CUDA path is broken, "
                              "refusing to report a throughput")
-        value = n_solved * args.steps / (elapsed_ms * 1e-3)
-        e2e_v = n_solved * args.steps / (e2e_ms * 1e-3)
-        # roofline of the dominant kernel (lcqp_solve_kernel), SURVEY.md 8(d) row "Shared-factor multi-RHS (C2)":
-        # one unit = one KKT solve for one instance = 2 N^2 flop with N = nV + nC + 2 nComp = 503.
-        N = NV + NC + 2 * NCOMP
-        units_per_launch = n_units / world  # KKT solves (ADMM iterations + refined EQP passes) of one launch on one GPU
-        flops_per_launch = units_per_launch * 2.0 * N * N
-        achieved = flops_per_launch / (k_ms * 1e-3) / 1e12
-        # DRAM traffic of the kernel per launch: bytes per LCQP from the committed ncu --set full capture
-        # (profiles/dram_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum / instances of that launch)
-        # scaled to the instances of one launch here; null when the summary is absent
-        traffic = None
+        counted = n_solved if cfg.name != "c3" else float(nb)   # c3: the reference ends the perturbed family with 201 too
+        value = counted * args.steps / (elapsed_ms * 1e-3)
+        e2e_v = counted * args.steps / (e2e_ms * 1e-3)
+        units_per_launch = n_units / world   # explicit-inverse solves (homotopy steps + polish passes) of one launch on one GPU
+        fp64 = C.c_double(0.0)
+        prob.lib.lcqp_cuda_measure_fp64_tflops(local_rank, C.byref(fp64))
+        if cfg.name == "c5":
+            # SURVEY.md 8(d) row "Per-instance dense KKT in SMEM": HBM bound, 8 (n^2 + m n + 2n + 2m + n) in + 8 (n + m + 4) out
+            m = NC + 2 * NCOMP
+            bytes_per_lcqp = 8.0 * (NV * NV + m * NV + 2 * NV + 2 * m + NV) + 8.0 * (NV + m + 4)
+            achieved = bytes_per_lcqp * batch / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
+                    "bytes_per_unit": bytes_per_lcqp, "unit_def": "one LCQP (SURVEY.md 8d: 77 728 B at nC=16)"}
+        else:
+            # SURVEY.md 8(d) row "Shared-factor multi-RHS (C2)": one unit = one KKT solve for one instance = 2 N^2 flop,
+            # N = nV + nC + 2 nComp (+ nV box rows), against the tensor pipe
+            N = NV + NC + 2 * NCOMP + (NV if cfg.name == "c3" else 0)
+            achieved = units_per_launch * 2.0 * N * N / (k_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": achieved, "peak": bf16_tf, "unit": "TFLOP/s", "frac": achieved / bf16_tf, "traffic": None,
+                    "flop_per_unit": 2.0 * N * N, "unit_def": "one KKT solve of one instance counted as 2 N^2 flop (SURVEY.md 8d)"}
         tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
         if os.path.exists(tpath):
             try:
-                traffic = float(json.load(open(tpath))["dram_bytes_per_lcqp"]) * batch
+                tj = json.load(open(tpath))
+                if tj.get("config", "c2") == cfg.name:
+                    roof["traffic"] = float(tj["dram_bytes_per_lcqp"]) * batch
             except Exception:
-                traffic = None
-        roof = {"bound": "tensor", "achieved": achieved, "peak": bf16_tf, "unit": "TFLOP/s", "frac": achieved / bf16_tf,
-                "traffic": traffic, "kernel": "lcqp_solve_kernel", "kernel_ms": k_ms, "units_per_launch": units_per_launch,
-                "flop_per_unit": 2.0 * N * N, "peak_source": f"bf16_tflops_sustained of {peak_src}; arithmetic is fp64 (see DESIGN.md)"}
-        # parity spot check inside the bench: instance 0 is the shipped x_ref=(0.5,-0.6)
-        ok0 = bool(abs(x[0, 0] - 0.181110968) < 1e-6 and abs(x[0, 1] + 0.983483383) < 1e-6 and st["status"][0] == 4)
+                pass
+        roof.update({"kernel": "lcqp_pas_kernel", "kernel_ms": k_ms, "units_per_launch": units_per_launch,
+                     "peak_source": f"{peak_src} (MEASURED_PEAKS.json); the arithmetic is fp64 SIMT -- see `fp64` for the pipe it runs on",
+                     # the work actually done, against the pipes it runs on (model counts of DESIGN.md section 5)
+                     "fp64": {"peak_tflops_measured": fp64.value,
+                              "note": "fp64 FMA probe of this device (lcqp_cuda_measure_fp64_tflops); DESIGN.md 5 has the MAC model"}})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "C2 OptimizeOnCircle N=100 (nV=202,nC=101,nComp=100), shared Q/A/L/R, per-instance g/x0",
-                           "instances_per_gpu_per_step": batch, "stationarityTolerance": STAT_TOL, "perturbStep": bool(args.perturb),
+                "config": {"workload": cfg.workload, "instances_per_gpu_per_step": batch, "perturbStep": bool(args.perturb),
                            "parallelism": f"instance-sharded x{world}, no collective on the data path",
-                           "l2": "inputs+outputs per step exceed L2 (%.0f MB)" % ((h2d + d2h) / 1e6)},
+                           "l2": "inputs+outputs per step exceed L2 (%.0f MB)" % ((h2d + d2h) / 1e6), **cfg.over},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "roofline": roof,
-                "solved_frac": n_solved / (batch * world), "mean_outer_iters": n_outer / (batch * world),
-                "mean_subproblem_iters": n_sub / (batch * world), "kkt_solves_per_lcqp": n_units / (batch * world),
-                "instance0_matches_shipped_solution": ok0}
+                "solved_frac": n_solved / nb, "return_values": ret_hist,
+                "mean_iter_outer": n_outer_it / nb, "mean_iter_total": n_total_it / nb,
+                "mean_subproblem_iters": n_sub / nb, "kkt_solves_per_lcqp": n_units / nb,
+                "launch": {"groups": grid, "smem_bytes_per_cta": smem_b, "eliminated_equality_rows": mE},
+                "parity_subset": par}
+        if cfg.name == "c2":
+            line["instance0_matches_shipped_solution"] = bool(abs(x[0, 0] - 0.181110968) < 1e-6 and abs(x[0, 1] + 0.983483383) < 1e-6 and st["status"][0] == 4)
         if not args.no_cpu_baseline and world == 1:
             kind = cpu_kind()
             cores = len(os.sched_getaffinity(0))
+            per_core = args.cpu_per_core or cfg.cpu_per_core
             with mp.get_context("fork").Pool(cores) as pool:
-                v, s, n, wall = cpu_pass(kind, cores, args.cpu_per_core, 20000, pool)
+                v, s, n, wall = cpu_pass(kind, cfg, cores, per_core, cores * per_core, pool)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
-                                    "sample": cpu_sample_desc(kind, cores, args.cpu_per_core), "seconds": wall,
+                                    "sample": cpu_sample_desc(kind, cfg, cores, per_core), "seconds": wall,
                                     "solved_frac": s / max(1, n)}
         print(json.dumps(line))
     if world > 1:

@@ -139,6 +139,9 @@ int lcqp_cuda_last_run_ms(lcqp_cuda_handle h, float* solve_kernel_ms, float* tot
 /* launch geometry of the last run: CTAs, dynamic shared memory per CTA, order of the static equality block */
 int lcqp_cuda_last_launch_info(lcqp_cuda_handle h, int* grid, int* smem_bytes, int* equality_rows);
 const char* lcqp_cuda_last_error(lcqp_cuda_handle h);
+/* fp64 FMA throughput of the device measured by a short probe kernel (TFLOP/s): the denominator bench.py uses for
+ * the fp64 SIMT work of the solver */
+int lcqp_cuda_measure_fp64_tflops(int device, double* tflops);
 
 /* ---- (2) plugin door: one convex QP, SubsolverBase semantics ---------------------------------- */
 /* SubsolverQPOASES(int nV, int nC, double* Q, double* A) (SubsolverQPOASES.hpp:44-47): nCtot rows of

@@ -338,6 +338,18 @@ __global__ void __launch_bounds__(kPasCtaThreads, 1) lcqp_pas_kernel(const __gri
     }
 }
 
+// fp64 FMA rate of the device (roofline denominator for the SIMT fp64 work of the solver; bench.py reports it)
+__global__ void fp64_fma_probe_kernel(double* out, int iters)
+{
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 // ---- plugin door: one QP with persistent state ----------------------------------------------------
 struct QPState {
     int nw, have_W, tinv_valid, prepared;
@@ -1121,6 +1133,33 @@ int lcqp_cuda_last_launch_info(lcqp_cuda_handle h, int* grid, int* smem_bytes, i
 }
 
 const char* lcqp_cuda_last_error(lcqp_cuda_handle h) { return h ? h->err.c_str() : "bad handle"; }
+
+int lcqp_cuda_measure_fp64_tflops(int device, double* tflops)
+{
+    if (!tflops) return LCQP_CUDA_BAD_ARGUMENT;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LCQP_CUDA_NO_DEVICE;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 14;
+    double* buf = nullptr;
+    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) { cudaGetLastError(); return LCQP_CUDA_OUT_OF_MEMORY; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    fp64_fma_probe_kernel<<<blocks, threads>>>(buf, iters);
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(e0);
+        fp64_fma_probe_kernel<<<blocks, threads>>>(buf, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    if (cudaGetLastError() != cudaSuccess) return LCQP_CUDA_LAUNCH_FAILED;
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return LCQP_CUDA_OK;
+}
 
 // ---- plugin door ---------------------------------------------------------------------------------
 struct lcqp_cuda_qp_s {

@@ -201,13 +201,15 @@ def circle_batch_fast(batch: int, N: int = 100, seed0: int = 20000) -> LCQPBatch
                      x0=x0, shared=frozenset(("Q", "L", "R", "A", "lbA", "ubA")), name=f"circle_N{N}")
 
 
-def dense_random_batch(batch: int, n: int = 64, nComp: int = 32, nC: int = 16, seed0: int = 50000) -> LCQPBatch:
+def dense_random_batch(batch: int, n: int = 64, nComp: int = 32, nC: int = 16, seed0: int = 50000, seed_lo: int = 0) -> LCQPBatch:
     """Config C5: per-instance dense LCQPs, instance b from default_rng(seed0+b).
 
     L=[I 0], R=[0 I]; Q = M'M/n + 0.1 I; A ~ N(0,1)/8; a feasible complementary x* (one of each pair 0,
     the other U(0,1)); lbA = A x* - 0.1 - U(0,1), ubA = A x* + 0.1 + U(0,1); g ~ N(0,1).
     """
     assert 2 * nComp <= n
+    if seed_lo:   # instances [seed_lo, batch) of the family only (a shard)
+        seed0, batch = seed0 + seed_lo, batch - seed_lo
     Q = np.empty((batch, n, n))
     A = np.empty((batch, nC, n))
     g = np.empty((batch, n))
