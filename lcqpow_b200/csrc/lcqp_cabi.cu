@@ -432,6 +432,104 @@ __global__ void __launch_bounds__(kThreads) qp_plugin_kernel(const __grid_consta
     }
 }
 
+// ---- plugin door on the parametric active-set solver: one QP, state kept in device memory between the calls ----
+struct PasQPState {
+    int nw, cap, e_moving, stamp_next, rampOffset, prepared;
+    int iterations, flag;
+    double phi, len0;
+};
+
+struct PasQPArgs {
+    pas::PDims d;
+    lcqp_cuda_options o;
+    Inst in;                 // Q, A (nC = nCtot rows), g, lbA, ubA, lb, ub, x0, y0 (device staging)
+    int mEc, mIc, capc;
+    double* mats_store;
+    pas::PMats* mats;        // persistent header of the prepared operands
+    double* gl;              // persistent global scratch (working-set inverse, gradients, duals)
+    unsigned char* saved_smem;
+    unsigned long long smem_bytes;
+    PasQPState* state;
+    double* xout;            // n
+    double* yout;            // n + mA
+    int initial;
+};
+
+__global__ void __launch_bounds__(kThreads) pas_plugin_kernel(const __grid_constant__ PasQPArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ pas::PMats mt;
+    __shared__ pas::PWork wk;
+    __shared__ pas::PQP s;
+    __shared__ pas::PDims dm;
+    __shared__ lcqp_cuda_options opt;
+    __shared__ Inst in;
+    __shared__ RawOps ro;
+    if (threadIdx.x == 0) {
+        dm = a.d; opt = a.o; in = a.in;
+        pas::pas_carve(wk, a.d, a.mEc, a.mIc, a.capc, smem, a.gl);
+        s.d = &dm; s.o = &opt; s.w = &wk; s.mt = &mt; s.in = &in;
+        s.n_solve = 0; s.n_change = 0; s.n_polish = 0; s.nwsr = 0;
+        ro.Q = dense_op(a.in.Q, a.d.n, a.d.n, a.d.n, 0);
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) wk.sc->wph[threadIdx.x] = 0;
+    int flag = 0;
+    if (a.initial) {
+        if (threadIdx.x == 0) pas::carve_pmats(mt, a.mats_store, a.d);
+        __syncthreads();
+        signed char* eq = reinterpret_cast<signed char*>(wk.tm2);
+        for (int r = threadIdx.x; r < a.d.m; r += blockDim.x) { double lo, up; pas::row_bounds(a.d, in, r, lo, up); eq[r] = (lo == up && lo > -pas::qINFTY && lo < pas::qINFTY) ? 1 : 0; }
+        __syncthreads();
+        pas::pas_prepare(a.d, in, mt, eq, wk.sc);
+        if (threadIdx.x == 0 && mt.status == 0) pas::pmats_dense_ops(a.d, mt);
+        __syncthreads();
+        if (mt.status != 0) flag = pas::QP_SETUP;
+        if (threadIdx.x == 0) { s.cap = pas::pas_cap(a.d, mt.mE, mt.mI); s.nw = 0; }
+        __syncthreads();
+    } else {
+        for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
+            reinterpret_cast<double*>(smem)[k] = reinterpret_cast<const double*>(a.saved_smem)[k];
+        if (threadIdx.x == 0) {
+            mt = *a.mats;
+            s.nw = a.state->nw; s.cap = a.state->cap; s.e_moving = a.state->e_moving; s.stamp_next = a.state->stamp_next;
+            s.rampOffset = a.state->rampOffset; s.phi = a.state->phi; s.len0 = a.state->len0;
+        }
+        __syncthreads();
+    }
+    if (flag == 0) {
+        for (int j = threadIdx.x; j < a.d.n; j += blockDim.x) wk.gk[j] = in.g[j];
+        __syncthreads();
+        if (a.initial) {
+            for (int j = threadIdx.x; j < a.d.n; j += blockDim.x) wk.xk[j] = in.x0 ? in.x0[j] : 0.0;
+            __syncthreads();
+            op_mv(ro.Q, wk.xk, nullptr, -1.0, wk.gq);
+            __syncthreads();
+            const double* y0A = in.y0 ? in.y0 + a.d.n : nullptr;
+            const double* y0box = (in.y0 && a.d.has_box) ? in.y0 : nullptr;
+            flag = pas::pas_init(s, ro, wk.xk, y0A, y0box);
+        } else {
+            flag = pas::pas_hotstart(s, ro);
+        }
+    }
+    if (flag == 0) {
+        for (int j = threadIdx.x; j < a.d.n; j += blockDim.x) {
+            a.xout[j] = wk.xq[j];
+            a.yout[j] = a.d.has_box ? wk.ys[a.d.mA + j] : 0.0;
+        }
+        for (int i = threadIdx.x; i < a.d.mA; i += blockDim.x) a.yout[a.d.n + i] = wk.ys[i];
+    }
+    __syncthreads();
+    for (size_t k = threadIdx.x; k < a.smem_bytes / 8; k += blockDim.x)
+        reinterpret_cast<double*>(a.saved_smem)[k] = reinterpret_cast<const double*>(smem)[k];
+    if (threadIdx.x == 0) {
+        *a.mats = mt;
+        a.state->nw = s.nw; a.state->cap = s.cap; a.state->e_moving = s.e_moving; a.state->stamp_next = s.stamp_next;
+        a.state->rampOffset = s.rampOffset; a.state->phi = s.phi; a.state->len0 = s.len0;
+        a.state->iterations = s.nwsr; a.state->flag = flag; a.state->prepared = 1 + mt.status;
+    }
+}
+
 }  // namespace lcqp
 
 // =================================================================================================
@@ -1177,7 +1275,24 @@ struct lcqp_cuda_qp_s {
     int has_box = 0;
     bool initialised = false;
     long long launches = 0;
+    // parametric active-set solver (the default); the regularised solver above takes over for semidefinite Hessians
+    double* pas_store = nullptr;
+    pas::PMats* pas_mats = nullptr;
+    double* pas_gl = nullptr;
+    unsigned char* pas_saved = nullptr;
+    PasQPState* pas_state = nullptr;
+    bool use_legacy = false;
+    bool pas_has[4] = {false, false, false, false};   // lbA, ubA, lb, ub were given at the initial solve
+    std::vector<char> eq_rows;   // rows that were equalities (l == u) at the initial solve: eliminated for good
 };
+
+static pas::PDims pas_qp_dims(int nV, int nCtot, int has_box)
+{
+    pas::PDims d = pas::make_pdims(nV, 0, 0, has_box);
+    d.nC = nCtot; d.mA = nCtot;
+    d.m = d.mA + (has_box ? nV : 0);
+    return d;
+}
 
 static Dims qp_dims(int nV, int nCtot, int has_box)
 {
@@ -1216,6 +1331,16 @@ int lcqp_cuda_qp_create(int nV, int nCtot, const double* Q, const double* A, int
               cudaMalloc(&q->saved, plan.bytes + 64) == cudaSuccess &&
               cudaMalloc(&q->state, sizeof(QPState)) == cudaSuccess &&
               cudaMalloc(&q->xout, n * 8) == cudaSuccess && cudaMalloc(&q->yout, (n + mA) * 8) == cudaSuccess;
+    {
+        const pas::PDims pd = pas_qp_dims(nV, nCtot, 1);
+        const int mEc = pas::pas_mEmax(pd), capc = pd.n < pd.m ? pd.n : pd.m;
+        ok = ok && cudaMalloc(&q->pas_store, pas::pmats_doubles(pd) * 8) == cudaSuccess &&
+             cudaMalloc(&q->pas_mats, sizeof(pas::PMats)) == cudaSuccess &&
+             cudaMalloc(&q->pas_gl, (pas::pas_gl_doubles(pd, mEc, capc) + 16) * 8) == cudaSuccess &&
+             cudaMalloc(&q->pas_saved, pas::pas_smem_bytes(pd, mEc, pd.m, capc) + 64) == cudaSuccess &&
+             cudaMalloc(&q->pas_state, sizeof(PasQPState)) == cudaSuccess;
+        if (ok) ok = cudaMemset(q->pas_state, 0, sizeof(PasQPState)) == cudaSuccess;
+    }
     if (ok) ok = cudaMemcpy(q->Q, Q, n * n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     if (ok && mA) ok = cudaMemcpy(q->A, A, mA * n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     if (ok) ok = cudaMemset(q->state, 0, sizeof(QPState)) == cudaSuccess;
@@ -1230,6 +1355,7 @@ int lcqp_cuda_qp_destroy(lcqp_cuda_qp q)
     cudaSetDevice(q->device);
     cudaFree(q->Q); cudaFree(q->A); cudaFree(q->stage); cudaFree(q->mats_store); cudaFree(q->mats); cudaFree(q->gl);
     cudaFree(q->saved); cudaFree(q->state); cudaFree(q->xout); cudaFree(q->yout);
+    cudaFree(q->pas_store); cudaFree(q->pas_mats); cudaFree(q->pas_gl); cudaFree(q->pas_saved); cudaFree(q->pas_state);
     delete q;
     return LCQP_CUDA_OK;
 }
@@ -1267,8 +1393,57 @@ int lcqp_cuda_qp_solve(lcqp_cuda_qp q, int initialSolve, int* iterations, int* e
     double* d_y0 = st;
     bool ok = cudaMemcpy(d_g, g, n * 8, cudaMemcpyHostToDevice) == cudaSuccess;
     auto up = [&](double* dst, const double* src, size_t cnt) { if (src && cnt) ok = ok && cudaMemcpy(dst, src, cnt * 8, cudaMemcpyHostToDevice) == cudaSuccess; };
-    if (initialSolve) { up(d_lbA, lbA, mA); up(d_ubA, ubA, mA); up(d_lb, lb, n); up(d_ub, ub, n); up(d_x0, x0, n); up(d_y0, y0, n + mA); }
+    if (initialSolve) {
+        up(d_lbA, lbA, mA); up(d_ubA, ubA, mA); up(d_lb, lb, n); up(d_ub, ub, n); up(d_x0, x0, n); up(d_y0, y0, n + mA);
+        q->use_legacy = false;
+        q->eq_rows.assign(mA + n, 0);
+        for (size_t i = 0; i < mA; i++) q->eq_rows[i] = (lbA && ubA && lbA[i] == ubA[i] && lbA[i] > -1e20 && lbA[i] < 1e20);
+        for (size_t j = 0; j < n; j++) q->eq_rows[mA + j] = (lb && ub && lb[j] == ub[j] && lb[j] > -1e20 && lb[j] < 1e20);
+    } else if (!q->use_legacy) {
+        // SubsolverQPOASES forwards the bounds of every call to qp.hotstart (SubsolverQPOASES.cpp:156-158): a hot start
+        // follows the homotopy to the new bounds as well.  The rows eliminated at the initial solve (l == u) must stay
+        // equalities; a NULL pointer keeps the bounds of the previous call.
+        for (size_t i = 0; i < mA && lbA && ubA; i++) if (q->eq_rows[i] && lbA[i] != ubA[i]) return LCQP_CUDA_BAD_ARGUMENT;
+        for (size_t j = 0; j < n && lb && ub && q->has_box; j++) if (q->eq_rows[mA + j] && lb[j] != ub[j]) return LCQP_CUDA_BAD_ARGUMENT;
+        up(d_lbA, lbA, mA); up(d_ubA, ubA, mA);
+        if (q->has_box) { up(d_lb, lb, n); up(d_ub, ub, n); }
+    }
     if (!ok) { cudaGetLastError(); return LCQP_CUDA_LAUNCH_FAILED; }
+    if (!q->use_legacy) {
+        PasQPArgs pa;
+        memset(&pa, 0, sizeof(pa));
+        pa.d = pas_qp_dims(q->nV, q->nCtot, q->has_box);
+        pa.o = q->opts;
+        pa.in.Q = q->Q; pa.in.A = q->A; pa.in.g = d_g;
+        // the staging copies of the bounds persist between the calls (a pointer that was NULL at the initial solve stays absent)
+        static_assert(sizeof(bool) == 1, "");
+        if (initialSolve) { q->initialised = false; }
+        pa.in.lbA = (initialSolve ? lbA != nullptr : q->pas_has[0]) ? d_lbA : nullptr;
+        pa.in.ubA = (initialSolve ? ubA != nullptr : q->pas_has[1]) ? d_ubA : nullptr;
+        pa.in.lb = (initialSolve ? lb != nullptr : q->pas_has[2]) ? d_lb : nullptr;
+        pa.in.ub = (initialSolve ? ub != nullptr : q->pas_has[3]) ? d_ub : nullptr;
+        if (initialSolve) { q->pas_has[0] = lbA != nullptr; q->pas_has[1] = ubA != nullptr; q->pas_has[2] = lb != nullptr; q->pas_has[3] = ub != nullptr; }
+        pa.in.x0 = (initialSolve && x0) ? d_x0 : nullptr;
+        pa.in.y0 = (initialSolve && y0) ? d_y0 : nullptr;
+        pa.mEc = pas::pas_mEmax(pa.d); pa.mIc = pa.d.m; pa.capc = pa.d.n < pa.d.m ? pa.d.n : pa.d.m;
+        pa.mats_store = q->pas_store; pa.mats = q->pas_mats; pa.gl = q->pas_gl; pa.saved_smem = q->pas_saved;
+        pa.smem_bytes = (pas::pas_smem_bytes(pa.d, pa.mEc, pa.mIc, pa.capc) + 7) / 8 * 8;
+        pa.state = q->pas_state; pa.xout = q->xout; pa.yout = q->yout; pa.initial = initialSolve ? 1 : 0;
+        if (pa.smem_bytes > kSmemMax) return LCQP_CUDA_TOO_LARGE;
+        if (cudaFuncSetAttribute(pas_plugin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pa.smem_bytes) != cudaSuccess) { cudaGetLastError(); return LCQP_CUDA_LAUNCH_FAILED; }
+        pas_plugin_kernel<<<1, kThreads, pa.smem_bytes>>>(pa);
+        q->launches++;
+        if (cudaGetLastError() != cudaSuccess) return LCQP_CUDA_LAUNCH_FAILED;
+        PasQPState hs;
+        if (cudaMemcpy(&hs, q->pas_state, sizeof(hs), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return LCQP_CUDA_LAUNCH_FAILED; }
+        if (!(initialSolve && hs.prepared == 2)) {   // prepared == 1 + status; status 1: semidefinite Hessian -> the regularised solver
+            q->initialised = true;
+            *iterations = hs.iterations;
+            *exit_flag = hs.flag;
+            return hs.flag == 0 ? 0 : 203;  // SUBPROBLEM_SOLVER_ERROR (SubsolverQPOASES.cpp:165-166)
+        }
+        q->use_legacy = true;
+    }
     memset(&a.in, 0, sizeof(a.in));
     a.in.Q = q->Q; a.in.A = q->A; a.in.g = d_g;
     // the QP's bounds are those given at the initial solve (LCQPow never changes them between calls)
@@ -1287,6 +1462,7 @@ int lcqp_cuda_qp_solve(lcqp_cuda_qp q, int initialSolve, int* iterations, int* e
     if (cudaFuncSetAttribute(qp_plugin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes) != cudaSuccess) { cudaGetLastError(); return LCQP_CUDA_LAUNCH_FAILED; }
     qp_plugin_kernel<<<1, kThreads, a.smem_bytes>>>(a);
     q->launches++;
+    if (cudaGetLastError() != cudaSuccess) return LCQP_CUDA_LAUNCH_FAILED;
     QPState hs;
     if (cudaMemcpy(&hs, q->state, sizeof(hs), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return LCQP_CUDA_LAUNCH_FAILED; }
     q->initialised = true;

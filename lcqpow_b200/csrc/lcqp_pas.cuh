@@ -243,8 +243,13 @@ LCQ_DEVN void pas_prepare(const PDims& d, const Inst& in, PMats& mt, const signe
     // Everything up to P is computed in the scaled variables x = D xs, D = diag(1/sqrt(Q_jj)): a Hessian whose
     // curvatures differ by many orders of magnitude (the reference's examples regularise with 5e-12) is badly scaled,
     // not ill-conditioned -- in the scaled variables Z'QZ is inverted to full relative accuracy in every block.
+    // (curvatures below kPDTol of the largest count as zero: such a Hessian is semidefinite for this solver -- qpOASES
+    //  treats them by its zero-curvature exchanges, QProblem.cpp:4278-4511, which the regularised solver stands in for)
     int badd = 0;
-    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) { const double q = in.Q[(size_t)j * n + j]; if (!(q > 0.0)) badd = 1; ds[j] = (q > 0.0) ? 1.0 / sqrt(q) : 1.0; }
+    double qmax = 0;
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) qmax = fmax(qmax, in.Q[(size_t)j * n + j]);
+    qmax = block_max(qmax, sc);
+    LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) { const double q = in.Q[(size_t)j * n + j]; if (!(q > kPDTol * qmax)) badd = 1; ds[j] = (q > 0.0) ? 1.0 / sqrt(q) : 1.0; }
     if (block_or(badd, sc)) { if (LCQ_TID == 0) mt.status = 1; LCQ_SYNC(); return; }
     LCQ_LOOP for (int e = LCQ_TID; e < n * n; e += LCQ_NT) { const int i = e / n, j = e - i * n; Hs[e] = 0.5 * (in.Q[e] + in.Q[(size_t)j * n + i]) * ds[i] * ds[j]; }
     LCQ_LOOP for (int e = LCQ_TID; e < m * n; e += LCQ_NT) { const int r = e / n; mt.Af[e] = afull_at(d, in, r, e - r * n); }

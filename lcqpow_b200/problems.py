@@ -128,6 +128,15 @@ def infeasible_qp() -> LCQPBatch:
                    A=[1, 0], lbA=[0], ubA=[-1])
 
 
+def stationarity_fixture(kind: str) -> LCQPBatch:
+    """Two variables pinned to the bi-active point x = (0, 0) by 0 <= x1 <= 0 _|_ 0 <= x2 <= 0, so that the multipliers
+    of the pair are y = g and the classifier of /root/reference/src/LCQProblem.cpp:1412-1453 sees every sign pattern:
+    S (y >= 0), M (one zero, one negative), C (both negative), W (opposite signs)."""
+    g = {"S": [1.0, 1.0], "M": [0.0, -1.0], "C": [-1.0, -1.0], "W": [1.0, -1.0]}[kind]
+    return _single("stationarity_" + kind, 2, 0, 1, Q=[2, 0, 0, 2], g=g, L=[1, 0], R=[0, 1],
+                   lbL=[0], ubL=[0], lbR=[0], ubR=[0], x0=[0, 0])
+
+
 def circle_shared(N: int = 100):
     """Shared operands of examples/OptimizeOnCircle.cpp:62-99."""
     nV, nC, nComp = 2 + 2 * N, N + 1, N

@@ -59,21 +59,72 @@ def golden_cases(example_data):
         "circle": (P.circle_batch(8), {"stationarityTolerance": 10e-3}),
         "dense": (P.dense_random_batch(16), {}),
         "example_data": (P.example_data_batch(example_data, 1), {}),
+        "stationarity_S": (P.stationarity_fixture("S"), {}),
+        "stationarity_M": (P.stationarity_fixture("M"), {}),
+        "stationarity_C": (P.stationarity_fixture("C"), {}),
+        "stationarity_W": (P.stationarity_fixture("W"), {}),
     }
 
 
-# instances on which the exact-QP trajectory is known to differ from the reference's qpOASES run
-# (see DESIGN.md "Parity"): circle instance 7 reaches another local solution one penalty step earlier.
-KNOWN_TRAJECTORY_DIFFS = {("circle", 7)}
+def family_cases(example_data):
+    """name -> (LCQPBatch, option overrides): the families of tests/golden/reference_families.npz."""
+    from lcqpow_b200 import problems as P
+    return {
+        "circle_bench": (P.circle_batch_fast(256), {"stationarityTolerance": 10e-3}),
+        "dense_bench": (P.dense_random_batch(256), {}),
+        "circle_N20": (P.circle_batch(16, N=20), {"stationarityTolerance": 10e-3}),
+        "dense_n32": (P.dense_random_batch(32, n=32, nComp=16, nC=8), {}),
+        "example_data_family": (P.example_data_batch(example_data, 17), {}),
+    }
+
+
+@pytest.fixture(scope="session")
+def families():
+    return dict(np.load(os.path.join(GOLDEN, "reference_families.npz")))
+
+
+# Fixtures whose outcome WITHOUT perturbStep is decided by round-off in the reference itself, with the evidence:
+#  * warm_up / warm_up_noguess / warm_up_w_A / warm_up_shifted are exactly symmetric in (x1, x2): without the perturbation the reference
+#    stays on the symmetric saddle path to (3.7e-7, 3.7e-7) only as long as its arithmetic keeps x1 == x2 bit for bit
+#    (SURVEY.md section 4: "perturbation is what breaks the tie"); its own test runs them WITH perturbStep and accepts
+#    either solution of the orbit (test/RunUnitTests.cpp:537-546).  They are compared that way here as well
+#    (check_symmetric_saddle).
+#  * golden circle instance 7 passes through a QP (outer iterate 15) in which two multipliers theta_90, theta_91 have
+#    linearised costs rho*lambda_k that are both zero up to round-off (x_k sits on a vertex of the polygon), so the
+#    split between them is decided by the 5e-12 regularisation against 1e-17-sized noise: the reference lands on
+#    0.5 +- 1e-7, any other arithmetic on 0.5 +- another 1e-7, and the homotopy amplifies that (k = 10 vs 9).  About
+#    0.5 % of the circle family does this; all 256 instances of the committed bench family do not.
+SYMMETRIC_SADDLE = {"warm_up", "warm_up_noguess", "warm_up_w_A", "warm_up_shifted"}
+ROUNDOFF_DECIDED = {("circle", 7)}
+
+
+def check_symmetric_saddle(name, x, stats, golden):
+    """Without perturbStep a symmetric fixture either follows the reference's saddle path or leaves it for one of the
+    two solutions of the orbit -- both end S-stationary."""
+    g = {k.split("/", 2)[2]: v for k, v in golden.items() if k.startswith(name + "/qpoases/")}
+    assert int(stats["ret"][0]) == 0 and int(stats["status"][0]) == 4, name
+    on_saddle = np.abs(x[0] - g["x"][0]).max() <= 1e-6
+    if on_saddle:
+        # (the saddle path ends when rho C p_k drops below the tolerance at rho ~ 5e6: the pass in which that happens
+        #  moves by one or two with the last bits of x; the number of penalty updates does not)
+        assert int(stats["iterOuter"][0]) == int(g["iterOuter"][0])
+        assert abs(int(stats["iterTotal"][0]) - int(g["iterTotal"][0])) <= 2
+    else:
+        orbit = {"warm_up": [(1, 0), (0, 1)], "warm_up_noguess": [(1, 0), (0, 1)], "warm_up_w_A": [(1, 0), (0, 0.5)],
+                 "warm_up_shifted": [(1, 2), (2, 1)]}[name]
+        assert any(np.abs(x[0] - np.array(o)).max() <= 1e-6 for o in orbit), (name, x[0])
 
 
 def check_against_golden(name, sol_x, sol_y, stats, golden, rtol=1e-6, check_duals=True):
     """Parity bar of BASELINE.json: same ReturnValue, stationarity type, outer-iteration count, iterTotal and
     rhoOpt as the reference's qpOASES run; x within 1e-6 relative."""
+    if name in SYMMETRIC_SADDLE:
+        return check_symmetric_saddle(name, sol_x, stats, golden)
     g = {k.split("/", 2)[2]: v for k, v in golden.items() if k.startswith(name + "/qpoases/")}
     nb = len(g["ret"])
     for b in range(nb):
-        if (name, b) in KNOWN_TRAJECTORY_DIFFS:
+        if (name, b) in ROUNDOFF_DECIDED:
+            assert int(stats["ret"][b]) == 0 and int(stats["status"][b]) == 4, (name, b)
             continue
         tag = f"{name}[{b}]"
         assert int(stats["ret"][b]) == int(g["ret"][b]), tag
@@ -90,3 +141,18 @@ def check_against_golden(name, sol_x, sol_y, stats, golden, rtol=1e-6, check_dua
             nd = int(g["nDuals"][b])
             yscale = max(1.0, float(np.abs(g["y"][b][:nd]).max()))
             assert np.abs(sol_y[b][:nd] - g["y"][b][:nd]).max() <= 1e-5 * yscale, tag
+
+
+def check_family(name, x, stats, families, rtol=1e-6, subset=None):
+    """Every instance of a committed family against the reference's qpOASES run: ReturnValue, stationarity type,
+    outer and total iteration counts identical, x within 1e-6 relative.  No allowances."""
+    idx = range(len(families[name + "/ret"])) if subset is None else subset
+    bad = []
+    for k, b in enumerate(idx):
+        ok = all(int(stats[f][k]) == int(families[f"{name}/{f}"][b]) for f in ("ret", "status", "iterOuter", "iterTotal"))
+        if ok and int(families[name + "/ret"][b]) == 0:
+            gx = families[name + "/x"][b]
+            ok = np.abs(x[k] - gx).max() <= rtol * max(1.0, float(np.abs(gx).max()))
+        if not ok:
+            bad.append(int(b))
+    assert not bad, (name, bad)

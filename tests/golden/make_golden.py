@@ -50,6 +50,10 @@ def main():
         "circle": (P.circle_batch(8), {"stationarityTolerance": 10e-3}),      # examples/OptimizeOnCircle.cpp:45
         "dense": (P.dense_random_batch(16), {}),
         "example_data": (P.example_data_batch(data, 1), {}),
+        "stationarity_S": (P.stationarity_fixture("S"), {}),
+        "stationarity_M": (P.stationarity_fixture("M"), {}),
+        "stationarity_C": (P.stationarity_fixture("C"), {}),
+        "stationarity_W": (P.stationarity_fixture("W"), {}),
     }
     out = {}
     for name, (pb, over) in cases.items():

@@ -1,20 +1,28 @@
 """Parity tests proper (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI
-(include/lcqp_cuda.h) via lcqpow_b200.api; the checker is the committed golden output of the real reference
-(tests/golden/reference_outputs.npz) and the plain-C oracle."""
+(include/lcqp_cuda.h) via lcqpow_b200.api; the checker is the committed output of the UNMODIFIED reference
+(tests/golden/reference_outputs.npz, reference_families.npz) and, for seeded runs with perturbStep, the numpy oracle."""
+import dataclasses
+
 import numpy as np
 import pytest
 
-from conftest import check_against_golden, golden_cases
+from conftest import check_against_golden, check_family, family_cases, golden_cases
 
 pytestmark = pytest.mark.gpu
 
+GOLDEN_NAMES = ["warm_up", "warm_up_noguess", "warm_up_w_A", "warm_up_binary", "warm_up_shifted", "infeasible_qp",
+                "max_penalty", "circle", "dense", "example_data", "stationarity_S", "stationarity_M", "stationarity_C",
+                "stationarity_W"]
 
-def _solve_cuda(pb, over, perturb=0, qp_solver=0):
+
+def _solve_cuda(pb, over, perturb=0, qp_solver=0, seed=None):
     import lcqpow_b200 as L
     prob = L.LCQProblemBatch(pb.nV, pb.nC, pb.nComp, pb.batch)
     o = L.Options()
     o.setPerturbStep(bool(perturb))
     o.setQPSolver(qp_solver)
+    if seed is not None:
+        o.setPerturbSeed(seed)
     for k, v in over.items():
         assert getattr(o, "set" + k[0].upper() + k[1:])(v) == 0
     assert prob.setOptions(o) == 0
@@ -23,78 +31,128 @@ def _solve_cuda(pb, over, perturb=0, qp_solver=0):
     return prob.getPrimalSolution(), prob.getDualSolution(), prob.getOutputStatistics(), prob
 
 
-@pytest.mark.parametrize("name", ["warm_up", "warm_up_noguess", "warm_up_w_A", "warm_up_binary", "warm_up_shifted",
-                                  "infeasible_qp", "max_penalty", "circle", "dense", "example_data"])
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
 def test_cuda_matches_reference_golden(name, golden, example_data):
     pb, over = golden_cases(example_data)[name]
     x, y, st, _ = _solve_cuda(pb, over)
     check_against_golden(name, x, y, st, golden)
 
 
-@pytest.mark.parametrize("name", ["warm_up", "warm_up_binary", "circle", "dense", "example_data"])
-def test_cuda_matches_oracle(name, oracle, example_data):
-    pb, over = golden_cases(example_data)[name]
+@pytest.mark.parametrize("name", ["circle_bench", "dense_bench", "circle_N20", "dense_n32"])
+def test_cuda_matches_reference_families(name, families, example_data):
+    """256 bench-family circle instances, 256 dense instances (and two smaller families): every instance ends with
+    the reference's ReturnValue, stationarity type, outer and total iteration counts and its x to 1e-6."""
+    pb, over = family_cases(example_data)[name]
     x, y, st, _ = _solve_cuda(pb, over)
-    so = oracle.solve_batch(pb, oracle.default_options(perturbStep=0, **over))
-    for b in range(pb.batch):
-        for f in ("ret", "status", "iterOuter", "iterTotal"):
-            assert int(st[f][b]) == int(so.res[f][b]), (name, b, f)
-        assert np.abs(x[b] - so.x[b]).max() <= 1e-8 * max(1.0, np.abs(so.x[b]).max()), (name, b)
+    check_family(name, x, st, families)
+
+
+def test_cuda_counts_the_references_working_set_changes(families, example_data):
+    pb, over = family_cases(example_data)["dense_bench"]
+    x, y, st, _ = _solve_cuda(pb, over)
+    assert np.array_equal(st["subproblemIter"], families["dense_bench/subproblemIter"])
+
+
+def test_cuda_example_data_family(families, example_data):
+    """Semidefinite Hessian (101 curvatures of 4.4e-16): the regularised solver takes the batch.  The shipped instance
+    matches the reference; the perturbed instances end in a terminal failure as in the reference (201 there, 203 here:
+    DESIGN.md, known gap)."""
+    pb, over = family_cases(example_data)["example_data_family"]
+    x, y, st, _ = _solve_cuda(pb.slice(0, 5), over)
+    check_family("example_data_family", x[:1], {k: st[k][:1] for k in ("ret", "status", "iterOuter", "iterTotal")}, families, subset=[0])
+    assert (st["ret"][1:] != 0).all()
+
+
+def test_stationarity_classification_covers_every_type(golden, example_data):
+    """W / C / M / S (LCQProblem.cpp:1412-1453): the four sign patterns of the pair's multipliers, duals included."""
+    want = {"S": 4, "M": 3, "C": 2, "W": 1}
+    for k, code in want.items():
+        pb, over = golden_cases(example_data)["stationarity_" + k]
+        x, y, st, _ = _solve_cuda(pb, over)
+        assert int(st["status"][0]) == code == int(golden[f"stationarity_{k}/qpoases/status"][0])
+        assert np.abs(y[0] - golden[f"stationarity_{k}/qpoases/y"][0]).max() <= 1e-12
 
 
 def test_warm_up_with_perturbation_orbit():
     """test/RunUnitTests.cpp:505-551: with perturbStep (default) the solution is (1,0) or (0,1) and
     2x_i - 2 - y_i - y_{2+i} = 0; k = 15 in every reference run."""
-    import lcqpow_b200 as L
     from lcqpow_b200 import problems as P
     pb = P.warm_up(False)
+    seen = set()
     for seed in range(1, 21):
-        prob = L.LCQProblemBatch(2, 0, 1, 1)
-        o = L.Options()
-        o.setPerturbSeed(seed)
-        prob.setOptions(o)
-        assert prob.loadBatch(pb) == 0
-        prob.runSolver()
-        st = prob.getOutputStatistics()[0]
-        x = prob.getPrimalSolution()[0]
-        y = prob.getDualSolution()[0]
-        tol = o.getStationarityTolerance()
+        x, y, st, _ = _solve_cuda(pb, {}, perturb=1, seed=seed)
+        x, y, st = x[0], y[0], st[0]
+        tol = 1e6 * 2.221e-16
         assert int(st["ret"]) == 0 and int(st["status"]) == 4
-        assert (abs(x[0] - 1) <= tol and abs(x[1]) <= tol) or (abs(x[1] - 1) <= tol and abs(x[0]) <= tol)
+        a = abs(x[0] - 1) <= tol and abs(x[1]) <= tol
+        b = abs(x[1] - 1) <= tol and abs(x[0]) <= tol
+        assert a or b
+        seen.add(a)
         assert abs(2 * x[0] - 2 - y[0] - y[2]) <= tol and abs(2 * x[1] - 2 - y[1] - y[3]) <= tol
-        assert int(st["iterOuter"]) in (15, 16)
+        assert int(st["iterOuter"]) == 15 and 29 <= int(st["iterTotal"]) <= 31    # SURVEY.md section 4
+    assert seen == {True, False}
 
 
-def test_osqp_style_dual_layout(golden, example_data):
-    """qpSolver = OSQP_SPARSE: nDuals = nC + 2 nComp, no box duals (LCQProblem.cpp:934-935); box bounds are
-    rejected with INVALID_OSQP_BOX_CONSTRAINTS (:955-957)."""
-    pb, over = golden_cases(example_data)["dense"]
-    x, y, st, prob = _solve_cuda(pb, over, qp_solver=2)
-    assert prob.getNumberOfDuals() == pb.nC + 2 * pb.nComp
-    x0, y0, st0, _ = _solve_cuda(pb, over, qp_solver=0)
-    assert np.array_equal(st["iterTotal"], st0["iterTotal"])
-    assert np.abs(y[:, : pb.nC + 2 * pb.nComp] - y0[:, pb.nV:]).max() <= 1e-9
+def test_perturbed_runs_match_numpy_oracle():
+    """perturbStep on (the shipped default): the CUDA path and the numpy oracle share the counter-based perturbation
+    generator, so they must walk the same homotopy instance by instance."""
+    from lcqpow_b200 import problems as P
+    from oracle import pas_oracle
+    for pb, over in ((P.circle_batch(6, seed0=23000), {"stationarityTolerance": 10e-3}), (P.dense_random_batch(16, seed0=52000), {})):
+        x, y, st, _ = _solve_cuda(pb, over, perturb=1)
+        so = pas_oracle.solve_batch(pb, perturb=1, **over)
+        for f in ("ret", "status", "iterOuter", "iterTotal"):
+            assert np.array_equal(np.asarray(st[f]), so[f]), (pb.name, f)
+        assert np.abs(x - so["x"]).max() <= 1e-8 * max(1.0, np.abs(so["x"]).max())
+
+
+def test_osqp_flavour_results(golden, example_data):
+    """qpSolver = OSQP_SPARSE.  Layout and conventions of the reference's OSQP adapter: nDuals = nC + 2 nComp, no box
+    duals (LCQProblem.cpp:934-935), duals with qpOASES' sign (SubsolverOSQP.cpp:196-199 negates OSQP's), box bounds
+    rejected with INVALID_OSQP_BOX_CONSTRAINTS (:955-957).  Results against the reference's own OSQP runs
+    (tests/golden '*/osqp/*', adaptive_rho_interval fixed to 25): same ReturnValue and stationarity type, x within the
+    accuracy of the OSQP run itself.  The number of outer iterations is NOT compared on the circle family: OSQP hands
+    LCQPow eps = 1e-3 iterates whenever its polish fails, which changes k (10 vs 8 on the shipped instance, SURVEY.md
+    section 4); this path returns the exact QP optimum in both layouts."""
+    for name in ("warm_up_binary", "dense", "circle"):
+        pb, over = golden_cases(example_data)[name]
+        x, y, st, prob = _solve_cuda(pb, over, qp_solver=2)
+        nd = pb.nC + 2 * pb.nComp
+        assert prob.getNumberOfDuals() == nd
+        g = {k.split("/", 2)[2]: v for k, v in golden.items() if k.startswith(name + "/osqp/")}
+        for b in range(pb.batch):
+            assert int(st["ret"][b]) == int(g["ret"][b]) == 0 and int(st["status"][b]) == int(g["status"][b]), (name, b)
+            if name != "circle":
+                assert int(st["iterOuter"][b]) == int(g["iterOuter"][b]), (name, b)
+                assert np.abs(x[b] - g["x"][b]).max() <= 1e-5 * max(1.0, np.abs(g["x"][b]).max()), (name, b)
+        if name == "circle":
+            assert np.abs(x[0, :2] - g["x"][0][:2]).max() <= 1e-6          # the shipped instance: (0.1811, -0.9835)
+        x0, y0, st0, _ = _solve_cuda(pb, over, qp_solver=0)
+        assert np.array_equal(st["iterTotal"], st0["iterTotal"])
+        assert np.abs(y[:, :nd] - y0[:, pb.nV:]).max() <= 1e-9
     pbx, overx = golden_cases(example_data)["example_data"]
     _, _, stx, _ = _solve_cuda(pbx, overx, qp_solver=2)
     assert int(stx["ret"][0]) == 110
 
 
-
-def test_circle_family_trajectories_match_oracle(oracle):
-    """128 seeded instances of the C2 family with perturbStep on (the shipped default): the CUDA path and the
-    oracle must walk the same penalty homotopy -- identical ReturnValue, stationarity type, outer and total
-    iteration counts for every instance -- and agree in x to 1e-8.  (The oracle is pinned against the real
-    reference on this family by tests/test_oracle_parity.py.)  This is the sensitive detector for changes of
-    summation order in the device kernels."""
+def test_mixed_row_types_in_one_batch():
+    """Shared Q/A/L/R, per-instance bounds: a row that is an equality in one instance and an inequality in another.
+    Every instance gives the result it gives alone, whatever its position in the batch (sharding must not change
+    outcomes)."""
     from lcqpow_b200 import problems as P
-    pb = P.circle_batch(128)
-    over = {"stationarityTolerance": 10e-3}
-    x, y, st, _ = _solve_cuda(pb, over, perturb=1)
-    so = oracle.solve_batch(pb, oracle.default_options(perturbStep=1, **over))
-    for f in ("ret", "status", "iterOuter", "iterTotal"):
-        bad = np.nonzero(np.asarray(st[f]) != np.asarray(so.res[f]))[0]
-        assert bad.size == 0, (f, bad.tolist())
-    assert np.abs(x - so.x).max() <= 1e-8 * max(1.0, np.abs(so.x).max())
+    base = P.warm_up_w_A().normalised()
+    lbA = np.array([[-0.5], [-0.5], [-np.inf]])
+    ubA = np.array([[-0.5], [np.inf], [0.25]])
+
+    def batch(order):
+        return dataclasses.replace(base, batch=len(order), g=np.tile(base.g, (len(order), 1)), lbA=lbA[order], ubA=ubA[order],
+                                   shared=frozenset(("Q", "L", "R", "A")))
+    alone = [_solve_cuda(batch([k]), {}, perturb=1) for k in range(3)]
+    for order in ([0, 1, 2], [2, 1, 0], [1, 0, 2]):
+        x, y, st, _ = _solve_cuda(batch(order), {}, perturb=1)
+        for pos, k in enumerate(order):
+            assert int(st["ret"][pos]) == int(alone[k][2]["ret"][0]) == 0, (order, pos)
+            assert int(st["iterOuter"][pos]) == int(alone[k][2]["iterOuter"][0])
 
 
 def test_circle_large_batch_properties():
@@ -107,7 +165,6 @@ def test_circle_large_batch_properties():
     pb = P.circle_batch_fast(4096).normalised()
     g = pb.g.copy(); x0 = pb.x0.copy()
     g[4095] = g[7]; x0[4095] = x0[7]          # a duplicate far away in the batch
-    import dataclasses
     pb = dataclasses.replace(pb, g=g, x0=x0)
     x, y, st, _ = _solve_cuda(pb, {"stationarityTolerance": 10e-3}, perturb=0)
     assert (st["ret"] == 0).all() and (st["status"] == 4).all()
@@ -118,6 +175,7 @@ def test_circle_large_batch_properties():
     assert (u >= -1e-9).all() and (v >= -1e-9).all() and np.abs(u * v).sum(axis=1).max() < 1e-9
     assert np.array_equal(x[7], x[4095]) and int(st["iterTotal"][7]) == int(st["iterTotal"][4095])
 
+
 def test_large_batch_properties():
     """Full-size behaviour through size-independent properties: every solved instance is complementary
     (phi < tol), feasible, and a re-run is bit-identical (deterministic reductions)."""
@@ -127,7 +185,7 @@ def test_large_batch_properties():
     x2, y2, st2, _ = _solve_cuda(pb, {})
     assert np.array_equal(x, x2) and np.array_equal(st["iterTotal"], st2["iterTotal"])
     ok = st["ret"] == 0
-    assert ok.mean() > 0.95
+    assert ok.mean() > 0.99
     n, p = pb.nV, pb.nComp
     Lx = x[:, :p]
     Rx = x[:, p:2 * p]
@@ -138,8 +196,29 @@ def test_large_batch_properties():
     assert (Ax[ok] >= pbn.lbA[ok] - 1e-8).all() and (Ax[ok] <= pbn.ubA[ok] + 1e-8).all()
 
 
+def test_run_is_one_asynchronous_launch():
+    """lcqp_cuda_load prepares the batch-level operands; two consecutive lcqp_cuda_run calls on the same load launch
+    one kernel each."""
+    from lcqpow_b200 import problems as P
+    import lcqpow_b200 as L
+    pb = P.circle_batch_fast(64)
+    prob = L.LCQProblemBatch(pb.nV, pb.nC, pb.nComp, pb.batch)
+    o = L.Options(); o.setStationarityTolerance(10e-3)
+    prob.setOptions(o)
+    assert prob.loadBatch(pb) == 0
+    l0 = prob.launchCount()
+    prob.runSolver(sync=False)
+    l1 = prob.launchCount()
+    prob.runSolver(sync=False)
+    l2 = prob.launchCount()
+    assert l1 - l0 == 1 and l2 - l1 == 1
+    prob.lib.lcqp_cuda_synchronize(prob.h)
+    assert (prob.getOutputStatistics()["ret"] == 0).all()
+
+
 def test_plugin_door_matches_batched_qp():
-    """SubsolverCUDA (SubsolverBase::solve semantics): initial solve then hot start with a new gradient."""
+    """SubsolverCUDA (SubsolverBase::solve semantics): initial solve, hot start with a new gradient, hot start with
+    new bounds (SubsolverQPOASES.cpp:156-158 forwards the bounds of every call)."""
     import lcqpow_b200 as L
     rng = np.random.default_rng(7)
     n, m = 12, 9
@@ -150,13 +229,14 @@ def test_plugin_door_matches_batched_qp():
     lbA = A @ xs - rng.uniform(0.1, 1.0, m)
     ubA = A @ xs + rng.uniform(0.1, 1.0, m)
     sub = L.SubsolverCUDA(n, m, Q, A)
-    for it, g in enumerate([rng.standard_normal(n), rng.standard_normal(n) * 3]):
-        rc, iters, flag = sub.solve(it == 0, g, lbA, ubA, x0=np.zeros(n))
+    calls = [(rng.standard_normal(n), lbA, ubA), (rng.standard_normal(n) * 3, lbA, ubA), (rng.standard_normal(n), lbA + 0.05, ubA - 0.02)]
+    for it, (g, lo, up) in enumerate(calls):
+        rc, iters, flag = sub.solve(it == 0, g, lo, up, x0=np.zeros(n))
         assert rc == 0 and flag == 0
         x, y = sub.getSolution()
         yA = y[n:]
-        # KKT of min 1/2 x'Qx + g'x s.t. lbA <= Ax <= ubA with qpOASES signs: Qx + g = A'y
+        # KKT of min 1/2 x'Qx + g'x s.t. lo <= Ax <= up with qpOASES signs: Qx + g = A'y
         assert np.abs(Q @ x + g - A.T @ yA).max() <= 1e-8
         Ax = A @ x
-        assert (Ax >= lbA - 1e-9).all() and (Ax <= ubA + 1e-9).all()
-        assert (yA[Ax > lbA + 1e-7] <= 1e-9).all() and (yA[Ax < ubA - 1e-7] >= -1e-9).all()
+        assert (Ax >= lo - 1e-9).all() and (Ax <= up + 1e-9).all()
+        assert (yA[Ax > lo + 1e-7] <= 1e-9).all() and (yA[Ax < up - 1e-7] >= -1e-9).all()
