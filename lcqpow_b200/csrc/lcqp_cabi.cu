@@ -537,6 +537,18 @@ __global__ void __launch_bounds__(kThreads) pas_plugin_kernel(const __grid_const
 // =================================================================================================
 using namespace lcqp;
 
+// Launch-plan overrides for development A/B runs (tools/gpu_ab.sh): compiled in only with -DLCQP_TUNING, so the shipped
+// library takes no decision from the environment (LCQP_CUDA_VERBOSE only prints the plan).
+static inline const char* tune_env(const char* name)
+{
+#ifdef LCQP_TUNING
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
+
 struct lcqp_cuda_handle_s {
     int nV, nC, nComp, capacity, device;
     lcqp_cuda_options opts;
@@ -877,15 +889,15 @@ static int run_legacy(lcqp_cuda_handle h, cudaStream_t stream)
     const size_t c_hot = can_cache ? (size_t)h->host_mats->cache_bytes_hot : 0;
     const size_t c_raw = can_cache ? (size_t)h->host_mats->cache_bytes_raw : 0;
     int threads = 128;
-    if (const char* t = getenv("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) threads = v; }
+    if (const char* t = tune_env("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) threads = v; }
     int gmax = kMaxCtaThreads / threads;
     if (gmax > kMaxGroups) gmax = kMaxGroups;
-    if (const char* t = getenv("LCQP_CUDA_GROUPS")) { const int v = atoi(t); if (v >= 1 && v < gmax) gmax = v; }
+    if (const char* t = tune_env("LCQP_CUDA_GROUPS")) { const int v = atoi(t); if (v >= 1 && v < gmax) gmax = v; }
     if (gmax > h->batch) gmax = h->batch;
     int tinv_pref = -1;   // -1: in shared memory when it fits
-    if (const char* t = getenv("LCQP_CUDA_TINV")) tinv_pref = (t[0] == 's') ? 1 : (t[0] == 'l' ? 0 : -1);
+    if (const char* t = tune_env("LCQP_CUDA_TINV")) tinv_pref = (t[0] == 's') ? 1 : (t[0] == 'l' ? 0 : -1);
     int cache_allow = 7;
-    if (const char* t = getenv("LCQP_CUDA_CACHE")) cache_allow = atoi(t) & 7;
+    if (const char* t = tune_env("LCQP_CUDA_CACHE")) cache_allow = atoi(t) & 7;
     cudaFuncAttributes fattr;
     CK(cudaFuncGetAttributes(&fattr, lcqp_solve_kernel), LCQP_CUDA_LAUNCH_FAILED);
     const size_t budget = kSmemMax - fattr.sharedSizeBytes;   // static shared memory: the descriptors of the groups
@@ -899,7 +911,7 @@ static int run_legacy(lcqp_cuda_handle h, cudaStream_t stream)
     bool bounds_shared = can_cache;
     for (int k = 0; k < LCQP_NUM_ARRAYS; k++)
         if (((bound_bits >> k) & 1u) && h->dev_in[k] && !((a.shared_mask >> k) & 1u)) bounds_shared = false;
-    if (getenv("LCQP_CUDA_NO_SLIM")) bounds_shared = false;   // tuning aid
+    if (tune_env("LCQP_CUDA_NO_SLIM")) bounds_shared = false;   // tuning aid
     const size_t bnd_bytes = bounds_shared ? 2 * ev((size_t)d.m) * sizeof(double) : 0;
     const size_t ys_bytes = ev((size_t)d.m) * sizeof(double);
     size_t bounds_bytes_used = 0;
@@ -918,7 +930,7 @@ static int run_legacy(lcqp_cuda_handle h, cudaStream_t stream)
         if ((cache_allow & 2) && c_hot && fits(per, cache + c_hot)) { cache += c_hot; what |= 2; }
         if ((cache_allow & 1) && c_se) {
             if (fits(per, cache + c_se)) { cache += c_se; what |= 1; }
-            else if (!getenv("LCQP_CUDA_NO_SLIM") && fits(per - ys_bytes, cache + c_se)) {
+            else if (!tune_env("LCQP_CUDA_NO_SLIM") && fits(per - ys_bytes, cache + c_se)) {
                 // the accepted duals move to the global scratch (with the outer-loop vectors) to make room
                 per -= ys_bytes; ys_global = true; cache += c_se; what |= 1;
             }
@@ -945,7 +957,7 @@ static int run_legacy(lcqp_cuda_handle h, cudaStream_t stream)
     CK(cudaFuncSetAttribute(lcqp_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), LCQP_CUDA_LAUNCH_FAILED);
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_solve_kernel, threads * groups, smem), LCQP_CUDA_LAUNCH_FAILED);
-    if (const char* t = getenv("LCQP_CUDA_CTAS_PER_SM")) { const int v = atoi(t); if (v >= 1 && v < per_sm) per_sm = v; }  // tuning aid
+    if (const char* t = tune_env("LCQP_CUDA_CTAS_PER_SM")) { const int v = atoi(t); if (v >= 1 && v < per_sm) per_sm = v; }  // tuning aid
     if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
     int grid = per_sm * h->num_sms;
     if ((long long)grid * groups > h->batch) grid = (h->batch + groups - 1) / groups;
@@ -1077,10 +1089,10 @@ static int run_pas(lcqp_cuda_handle h, cudaStream_t stream)
     h->last_mE = a.mats_shared ? a.mEc : -1;
     // a CTA is G groups of T threads; every group keeps the row vectors of its instance in shared memory
     int threads = 128;
-    if (const char* t = getenv("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) threads = v; }
+    if (const char* t = tune_env("LCQP_CUDA_THREADS")) { const int v = atoi(t); if (v >= 32 && v <= 256 && v % 32 == 0) threads = v; }
     int gmax = kPasCtaThreads / threads;
     if (gmax > kPasGroupsMax) gmax = kPasGroupsMax;
-    if (const char* t = getenv("LCQP_CUDA_GROUPS")) { const int v = atoi(t); if (v >= 1 && v < gmax) gmax = v; }
+    if (const char* t = tune_env("LCQP_CUDA_GROUPS")) { const int v = atoi(t); if (v >= 1 && v < gmax) gmax = v; }
     if (gmax > h->batch) gmax = h->batch;
     cudaFuncAttributes fattr;
     CK(cudaFuncGetAttributes(&fattr, lcqp_pas_kernel), LCQP_CUDA_LAUNCH_FAILED);
@@ -1152,7 +1164,7 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     if (!h->loaded) return fail(h, LCQP_CUDA_NOT_LOADED, "run before load");
     cudaStream_t stream = (cudaStream_t)stream_v;
     CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
-    if (h->use_legacy || !h->pas_ready || getenv("LCQP_CUDA_LEGACY")) return run_legacy(h, stream);
+    if (h->use_legacy || !h->pas_ready || tune_env("LCQP_CUDA_LEGACY")) return run_legacy(h, stream);
     return run_pas(h, stream);
 }
 

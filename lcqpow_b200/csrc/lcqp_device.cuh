@@ -1642,9 +1642,6 @@ LCQ_DEVN void tinv_build(QP& s, signed char* W)
     LCQ_LOOP for (int i = 0; i < m; i++) {  // W is in shared memory: uniform branches
         if (!W[i] || s.w->ctype[i] != 0) continue;
         if (s.nw >= s.d->cap || tinv_append(s, i)) {
-#ifdef LCQP_HOST_EMU
-            if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu tinv_build: row %d rejected (nw=%d cap=%d mE=%d)\n", i, s.nw, s.d->cap, s.mt->mE);
-#endif
             LCQ_SYNC();
             if (LCQ_TID == 0) W[i] = 0;
             LCQ_SYNC();
@@ -1761,10 +1758,6 @@ LCQ_DEVN int kkt_check(QP& s, const signed char* W, const double* lam, int* wors
         }
         const double tol = ftol * (1.0 + fabs(zi));
         if (zi < w.l[i] - tol || zi > w.ub[i] + tol) bad |= 1;
-#ifdef LCQP_HOST_EMU
-        if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1 && (zi < w.l[i] - tol || zi > w.ub[i] + tol))
-            fprintf(stderr, "      emu kkt_check: row %d W=%d pin=%d violated z=%.17g l=%.17g u=%.17g\n", i, (int)W[i], (int)w.pin[i], zi, w.l[i], w.ub[i]);
-#endif
     }
     bad = block_or(bad, w.sc);
     if (bad & 2) return 3;
@@ -1876,9 +1869,6 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                 LCQ_PROF(w.sc, 9);
                 tinv_remove(s, worst);
                 LCQ_PROF(w.sc, 7);
-#ifdef LCQP_HOST_EMU
-                if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d drop row %d (reason %d) rn=%.3e\n", it, s.nw, row, reason, rn);
-#endif
                 last_dropped = row;
                 if (LCQ_TID == 0) s.n_changes++;
                 best = INFINITY;
@@ -1887,9 +1877,6 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                 clean = false;
                 continue;
             }
-#ifdef LCQP_HOST_EMU
-            if (getenv("LCQP_EMU_DEBUG")) fprintf(stderr, "    emu as it=%d nw=%d gives up: reason %d rn=%.3e best=%.3e passes=%d\n", it, s.nw, reason, rn, best, passes);
-#endif
             return 1;  // EQP not solvable to tolerance on this set
         }
         if (LCQ_TID == 0) s.n_pass++;
@@ -1946,9 +1933,6 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
                 // selection row): along the working set it cannot move; the apparent motion is the leak of the
                 // regularisation.  It is left out of the ratio tests until a row leaves the working set.
                 if (LCQ_TID == 0) w.pin[block] |= 2;
-#ifdef LCQP_HOST_EMU
-                if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d row %d is dependent (alpha=%.3e, sv=%.3e)\n", it, s.nw, block, amin, w.zp[block]);
-#endif
                 LCQ_SYNC();
                 amin = 1.0;
             }
@@ -1964,9 +1948,6 @@ LCQ_DEVN int active_set(QP& s, signed char* W, bool ratio_test, int* worst_out)
             last_dropped = -1;
             LCQ_SYNC();
             if (LCQ_TID == 0) s.n_changes++;
-#ifdef LCQP_HOST_EMU
-            if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu as it=%d nw=%d add row %d side %d alpha=%.3e rn=%.3e\n", it, s.nw, block, (int)side, amin, rn);
-#endif
             best = INFINITY;
             passes = 0;
             continue;
@@ -2000,9 +1981,6 @@ LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin)
         }
         LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.r1[j] = 0.0;
         rn = block_max(rn, w.sc);
-#ifdef LCQP_HOST_EMU
-        if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 1) fprintf(stderr, "    emu project pass %d rn=%.3e nw=%d\n", pass, rn, s.nw);
-#endif
         if (rn < 1e-15) break;
         kkt_solve(s);
         LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.xa[j] += w.dx[j];
@@ -2019,10 +1997,6 @@ LCQ_DEVN int project_feasible(QP& s, const signed char* W, const double* xin)
             const double b = (W[i] == 1) ? w.l[i] : w.ub[i];
             if (fabs(w.zx[i] - b) > tol) bad = 1;
         }
-#ifdef LCQP_HOST_EMU
-        if (getenv("LCQP_EMU_DEBUG") && atoi(getenv("LCQP_EMU_DEBUG")) > 2 && (w.zx[i] < w.l[i] - tol || w.zx[i] > w.ub[i] + tol || (W[i] && fabs(w.zx[i] - ((W[i] == 1) ? w.l[i] : w.ub[i])) > tol)))
-            fprintf(stderr, "      emu project: row %d W=%d ctype=%d z=%.17g l=%.17g u=%.17g\n", i, (int)W[i], (int)w.ctype[i], w.zx[i], w.l[i], w.ub[i]);
-#endif
     }
     return block_or(bad, w.sc) == 0;
 }
@@ -2099,9 +2073,6 @@ LCQ_DEVN int qp_solve(QP& s, bool initial, const double* g, const double* x0, co
         LCQ_LOOP for (int i = LCQ_TID; i < m; i += LCQ_NT) w.lam[i] = 0.0;
         LCQ_SYNC();
         const int reason = active_set(s, w.Wtry, false, nullptr);
-#ifdef LCQP_HOST_EMU
-        if (getenv("LCQP_EMU_DEBUG")) fprintf(stderr, "  emu admm it=%d nw=%d probe reason=%d\n", it, s.nw, reason);
-#endif
         if (reason == 0) { accept_solution(s, w.Wtry); *iterations = it + (int)(s.n_changes - ch0); return 0; }
         if (reason == 5 || reason == 6) {
             // primal feasible EQP point with a wrong-signed multiplier: a valid active-set start
@@ -2226,15 +2197,6 @@ LCQ_DEVN void lcqp_loop(QP& s, const Inst& in, const RawOps& ro, unsigned long l
         if (fl != 0) { ret = (osqp_flavour && infeasible) ? RET_OSQP_GUESS : RET_SUBPROBLEM; return false; }
         LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.pk[j] = mt.D[j] * w.x[j] - w.xk[j];  // xnew = D xbar (auxil.c:524-562)
         LCQ_SYNC();
-#ifdef LCQP_HOST_EMU
-        if (getenv("LCQP_EMU_DEBUG")) {
-            fprintf(stderr, "emu qp i=%d rho=%g it=%d x=[", totalIter, rho, qpIter);
-            LCQ_LOOP for (int j = 0; j < (n < 4 ? n : 4); j++) fprintf(stderr, "%.17g ", mt.D[j] * w.x[j]);
-            fprintf(stderr, "] ys=[");
-            LCQ_LOOP for (int j = 0; j < (s.d->m < 4 ? s.d->m : 4); j++) fprintf(stderr, "%.17g ", w.ys[j]);
-            fprintf(stderr, "] passes=%lld changes=%lld\n", s.n_pass, s.n_changes);
-        }
-#endif
         return true;
     };
 

@@ -1376,10 +1376,6 @@ LCQ_DEVN void pas_lcqp_loop(PQP& s, const RawOps& ro, unsigned long long instanc
             LCQ_SYNC();
         }
         totalIter++;  // :493-496
-#ifdef LCQP_PAS_TRACE
-        { double sm_ = 0; for (int j = 0; j < n; j++) sm_ = fmax(sm_, fabs(w.stat[j]));
-          fprintf(stderr, "pas i=%d k=%d rho=%g stat=%.3e sub=%d x=[%.17g %.17g] alpha=%.17g\n", totalIter, outerIter, rho, sm_, s.nwsr, w.xk[0], n > 1 ? w.xk[1] : 0.0, alphak); }
-#endif
 
         // leyfferCheckPositive :1275-1313
         {
