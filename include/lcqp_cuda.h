@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LCQP_CUDA_ABI_VERSION 1
+#define LCQP_CUDA_ABI_VERSION 2
 
 /* CUDA-side return codes (LCQPow::ReturnValue stops at 402) */
 #define LCQP_CUDA_OK 0
@@ -61,7 +61,8 @@ typedef struct {
     int maxIterations;                /* 1000                                        */
     int nDynamicPenalty;              /* 3  (<= 16)                                  */
     int qpSolver;                     /* dual layout: 0/1 qpOASES-style (nV box duals first), 2 OSQP-style */
-    int reserved0;
+    int osqp_admm;                    /* qpSolver == 2 only.  0: exact-vertex solver behind the OSQP dual layout;
+                                         1: the OSQP restatement (ADMM + polish, lcqp_osqp.cuh) -- what QPSolver::OSQP_SPARSE means in the reference */
     double qp_rho;                    /* ADMM step of the phase-1 iteration, 0.1     */
     double qp_sigma;                  /* 1e-6                                        */
     double qp_alpha;                  /* 1.6                                         */
@@ -73,6 +74,25 @@ typedef struct {
     int qp_refine_iter;               /* refinement passes per EQP solve, 10         */
     int qp_adaptive_rho;              /* reserved (0)                                */
     unsigned long long perturb_seed;  /* counter-based RNG key for perturbStep       */
+    /* OSQPSettings of the OSQP restatement (/root/reference/external/osqp/include/types.h:158-195, defaults
+     * constants.h:59-114 with LCQPow's overrides eps_prim_inf = EPS, polish = 1, /root/reference/src/Options.cpp:326-331) */
+    double osqp_rho;                  /* 0.1    */
+    double osqp_sigma;                /* 1e-6   */
+    double osqp_alpha;                /* 1.6    */
+    double osqp_delta;                /* 1e-6   */
+    double osqp_eps_abs;              /* 1e-3   */
+    double osqp_eps_rel;              /* 1e-3   */
+    double osqp_eps_prim_inf;         /* 2.221e-16 (LCQPow) */
+    double osqp_eps_dual_inf;         /* 1e-4   */
+    double osqp_adaptive_rho_tolerance; /* 5    */
+    int osqp_max_iter;                /* 4000   */
+    int osqp_check_termination;       /* 25     */
+    int osqp_scaling;                 /* 10 Ruiz passes */
+    int osqp_adaptive_rho;            /* 1      */
+    int osqp_adaptive_rho_interval;   /* 0: every 4 x check_termination iterations (the reference: wall-clock driven) */
+    int osqp_polish;                  /* 1      */
+    int osqp_polish_refine_iter;      /* 3      */
+    int osqp_reserved;
 } lcqp_cuda_options;
 
 /* Mirrors LCQPow::OutputStatistics counters (/root/reference/include/OutputStatistics.hpp:209-226),
@@ -117,6 +137,20 @@ int lcqp_cuda_load_device(lcqp_cuda_handle h, int batch, unsigned shared_mask,
                           const double* lbL, const double* ubL, const double* lbR, const double* ubR,
                           const double* A, const double* lbA, const double* ubA,
                           const double* lb, const double* ub, const double* x0, const double* y0);
+/* LCQProblem::loadLCQP(const csc* Q, g, const csc* L, const csc* R, ..., const csc* A, ...)
+ * (/root/reference/src/LCQProblem.cpp:312-387; csc = /root/reference/external/osqp/include/types.h:21-29: column
+ * pointers p[ncol+1], row indices i[nnz], values x[nnz]) for `batch` instances that share the sparsity PATTERNS:
+ * Q is nV x nV (full symmetric), L and R are nComp x nV, A is nC x nV (NULL pointers when nC == 0).  The index
+ * arrays are read once; a value array whose bit is set in shared_mask is read once, the others hold `batch`
+ * consecutive copies of nnz values.  HOST pointers.  Serves qpSolver == 2 with osqp_admm == 1 (the OSQP flavour:
+ * the reference's sparse door only exists for its sparse subsolvers); other settings return LCQP_CUDA_BAD_ARGUMENT. */
+int lcqp_cuda_load_csc(lcqp_cuda_handle h, int batch, unsigned shared_mask,
+                       const int* Q_p, const int* Q_i, const double* Q_x, const double* g,
+                       const int* L_p, const int* L_i, const double* L_x,
+                       const int* R_p, const int* R_i, const double* R_x,
+                       const double* lbL, const double* ubL, const double* lbR, const double* ubR,
+                       const int* A_p, const int* A_i, const double* A_x, const double* lbA, const double* ubA,
+                       const double* x0, const double* y0);
 /* Global index of instance 0 of this handle (keys the perturbStep RNG so that a batch sharded over
  * several GPUs draws the same perturbations as the unsharded batch).  Default 0. */
 int lcqp_cuda_set_instance_offset(lcqp_cuda_handle h, unsigned long long offset);

@@ -33,7 +33,7 @@ QPOASES_DENSE, QPOASES_SPARSE, OSQP_SPARSE = 0, 1, 2
 
 EXPORTS = (
     "lcqp_cuda_abi_version", "lcqp_cuda_default_options", "lcqp_cuda_create", "lcqp_cuda_destroy",
-    "lcqp_cuda_set_options", "lcqp_cuda_load", "lcqp_cuda_load_device", "lcqp_cuda_set_instance_offset",
+    "lcqp_cuda_set_options", "lcqp_cuda_load", "lcqp_cuda_load_device", "lcqp_cuda_load_csc", "lcqp_cuda_set_instance_offset",
     "lcqp_cuda_run", "lcqp_cuda_synchronize", "lcqp_cuda_get_primal", "lcqp_cuda_get_dual",
     "lcqp_cuda_get_stats", "lcqp_cuda_get_device_results", "lcqp_cuda_num_duals", "lcqp_cuda_launch_count",
     "lcqp_cuda_last_run_ms", "lcqp_cuda_last_launch_info", "lcqp_cuda_last_error", "lcqp_cuda_qp_create", "lcqp_cuda_qp_destroy",
@@ -47,11 +47,18 @@ class CudaOptions(C.Structure):
                 ("initialPenaltyParameter", C.c_double), ("penaltyUpdateFactor", C.c_double),
                 ("maxPenaltyParameter", C.c_double), ("etaDynamicPenalty", C.c_double),
                 ("solveZeroPenaltyFirst", C.c_int), ("perturbStep", C.c_int), ("maxIterations", C.c_int),
-                ("nDynamicPenalty", C.c_int), ("qpSolver", C.c_int), ("reserved0", C.c_int),
+                ("nDynamicPenalty", C.c_int), ("qpSolver", C.c_int), ("osqp_admm", C.c_int),
                 ("qp_rho", C.c_double), ("qp_sigma", C.c_double), ("qp_alpha", C.c_double), ("qp_delta", C.c_double),
                 ("qp_feas_tol", C.c_double), ("qp_dual_tol", C.c_double),
                 ("qp_max_iter", C.c_int), ("qp_check_interval", C.c_int), ("qp_refine_iter", C.c_int),
-                ("qp_adaptive_rho", C.c_int), ("perturb_seed", C.c_ulonglong)]
+                ("qp_adaptive_rho", C.c_int), ("perturb_seed", C.c_ulonglong),
+                # OSQPSettings of the OSQP restatement (ABI 2)
+                ("osqp_rho", C.c_double), ("osqp_sigma", C.c_double), ("osqp_alpha", C.c_double), ("osqp_delta", C.c_double),
+                ("osqp_eps_abs", C.c_double), ("osqp_eps_rel", C.c_double), ("osqp_eps_prim_inf", C.c_double),
+                ("osqp_eps_dual_inf", C.c_double), ("osqp_adaptive_rho_tolerance", C.c_double),
+                ("osqp_max_iter", C.c_int), ("osqp_check_termination", C.c_int), ("osqp_scaling", C.c_int),
+                ("osqp_adaptive_rho", C.c_int), ("osqp_adaptive_rho_interval", C.c_int), ("osqp_polish", C.c_int),
+                ("osqp_polish_refine_iter", C.c_int), ("osqp_reserved", C.c_int)]
 
 
 STATS_DTYPE = np.dtype([("ret", "i4"), ("status", "i4"), ("iterTotal", "i4"), ("iterOuter", "i4"),
@@ -84,6 +91,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
     lib.lcqp_cuda_set_options.argtypes = [vp, C.POINTER(CudaOptions)]
     lib.lcqp_cuda_load.argtypes = [vp, C.c_int, C.c_uint] + [vp] * 15
     lib.lcqp_cuda_load_device.argtypes = [vp, C.c_int, C.c_uint] + [vp] * 15
+    lib.lcqp_cuda_load_csc.argtypes = [vp, C.c_int, C.c_uint] + [vp] * 21
     lib.lcqp_cuda_set_instance_offset.argtypes = [vp, C.c_ulonglong]
     lib.lcqp_cuda_run.argtypes = [vp, vp]
     lib.lcqp_cuda_synchronize.argtypes = [vp]
@@ -170,6 +178,23 @@ class Options:
         if v < QPOASES_DENSE or v > OSQP_SPARSE: return 109
         self.c.qpSolver = int(v); return 0
     def setPerturbSeed(self, v): self.c.perturb_seed = int(v); return 0
+
+    # OSQP flavour: QPSolver::OSQP_SPARSE as the reference runs it (ADMM + polish) instead of the exact-vertex solver
+    # behind the OSQP dual layout; `settings` are OSQPSettings fields (rho, sigma, alpha, delta, eps_abs, eps_rel,
+    # eps_prim_inf, eps_dual_inf, adaptive_rho, adaptive_rho_interval, adaptive_rho_tolerance, max_iter,
+    # check_termination, scaling, polish, polish_refine_iter) -- Options::setOSQPOptions, Options.cpp:275-287
+    def setOSQPADMM(self, on: bool = True, **settings):
+        self.c.osqp_admm = int(bool(on))
+        if on:
+            self.c.qpSolver = OSQP_SPARSE
+        return self.setOSQPOptions(**settings)
+
+    def setOSQPOptions(self, **settings):
+        for k, v in settings.items():
+            if not hasattr(self.c, "osqp_" + k):
+                return 100
+            setattr(self.c, "osqp_" + k, v)
+        return 0
 
 
 class OutputStatistics:
@@ -260,6 +285,47 @@ class LCQProblemBatch:
         n, c, p = self.nV, self.nC, self.nComp
         return {"Q": n * n, "g": n, "L": p * n, "R": p * n, "lbL": p, "ubL": p, "lbR": p, "ubR": p,
                 "A": c * n, "lbA": c, "ubA": c, "lb": n, "ub": n, "x0": n, "y0": n + c + 2 * p}[f]
+
+    def loadCSC(self, Q, g, L, R, lbL=None, ubL=None, lbR=None, ubR=None, A=None, lbA=None, ubA=None, x0=None, y0=None,
+                batch: Optional[int] = None, shared: Sequence[str] = ()) -> int:
+        """LCQProblem::loadLCQP(const csc* ...) (LCQProblem.cpp:312-387) for a batch that shares its sparsity patterns.
+        Q, L, R, A are (colptr int32[nV+1], rowidx int32[nnz], values float64[nnz] or [batch, nnz]) triples; the vectors
+        are as in loadLCQP.  Serves the OSQP flavour (Options.setOSQPADMM)."""
+        batch = self.capacity if batch is None else batch
+        mask = sum(1 << k for k, f in enumerate(FIELDS) if f in shared)
+        keep = []
+
+        def mat(name, t):
+            if t is None:
+                return [None, None, None]
+            p = np.ascontiguousarray(t[0], dtype=np.int32)
+            i = np.ascontiguousarray(t[1], dtype=np.int32)
+            x = np.ascontiguousarray(t[2], dtype=np.float64)
+            if p.size != self.nV + 1 or i.size != int(p[-1]):
+                raise ValueError(f"loadCSC: {name} has inconsistent index arrays")
+            want = int(p[-1]) * (1 if (name in shared or batch == 1) else batch)
+            if x.size != want:
+                raise ValueError(f"loadCSC: {name} has {x.size} values, expected {want}")
+            keep.extend((p, i, x))
+            return [_as_ptr(p), _as_ptr(i), _as_ptr(x)]
+
+        def vec(name, a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            want = self._field_len(name) * (1 if (name in shared or batch == 1) else batch)
+            if a.size != want:
+                raise ValueError(f"loadCSC: {name} has {a.size} entries, expected {want}")
+            keep.append(a)
+            return _as_ptr(a)
+
+        args = mat("Q", Q) + [vec("g", g)] + mat("L", L) + mat("R", R) + [vec("lbL", lbL), vec("ubL", ubL), vec("lbR", lbR), vec("ubR", ubR)] \
+            + mat("A", A) + [vec("lbA", lbA), vec("ubA", ubA), vec("x0", x0), vec("y0", y0)]
+        self._keep = keep
+        rc = self.lib.lcqp_cuda_load_csc(self.h, batch, mask, *args)
+        if rc == 0:
+            self.batch = batch
+        return rc
 
     def loadBatch(self, pb) -> int:
         """Load an lcqpow_b200.problems.LCQPBatch."""

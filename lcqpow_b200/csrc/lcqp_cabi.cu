@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "lcqp_pas.cuh"
+#include "lcqp_osqp.cuh"
+#include "lcqp_sparse_host.hpp"
 
 namespace lcqp {
 
@@ -530,6 +532,65 @@ __global__ void __launch_bounds__(kThreads) pas_plugin_kernel(const __grid_const
     }
 }
 
+
+// ---- the OSQP flavour: one thread per instance, one warp per CTA (lcqp_osqp.cuh) -----------------------------------
+struct OsqpArgs {
+    osq::SymDev S;
+    lcqp_cuda_options o;
+    const double* arr[LCQP_NUM_ARRAYS];          // Q, A, L, R hold VALUE arrays indexed through S.*src (dense or csc layout)
+    unsigned long long stride[LCQP_NUM_ARRAYS];  // doubles between consecutive instances (0: shared)
+    int batch;
+    double* workspace;                           // per resident warp: ws_doubles x 32 doubles, lane-interleaved
+    unsigned long long ws_doubles;
+    double* xout;
+    double* yout;
+    lcqp_cuda_stats* stats;
+    unsigned int* counter;
+    unsigned long long instance_offset;
+    int box_given;                               // lb / ub were loaded: INVALID_OSQP_BOX_CONSTRAINTS (LCQProblem.cpp:930-957)
+};
+
+__global__ void __launch_bounds__(32) lcqp_osqp_kernel(const __grid_constant__ OsqpArgs a)
+{
+    const int lane = threadIdx.x;
+    osq::Work w;
+    osq::carve(w, a.S, a.workspace + (size_t)blockIdx.x * a.ws_doubles * 32 + lane);
+    const int nV = a.S.n, mA = a.S.m, nD = nV + mA;
+    for (;;) {
+        unsigned tile = 0;
+        if (lane == 0) tile = atomicAdd(a.counter, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if ((unsigned long long)tile * 32ull >= (unsigned long long)a.batch) break;
+        const int b = (int)tile * 32 + lane;
+        if (b < a.batch) {
+            osq::View v;
+            auto at = [&](int k) -> const double* { return a.arr[k] ? a.arr[k] + a.stride[k] * (unsigned long long)b : nullptr; };
+            v.Q = at(LCQP_Q); v.A = at(LCQP_A); v.L = at(LCQP_L); v.R = at(LCQP_R); v.g = at(LCQP_G);
+            v.lbL = at(LCQP_LBL); v.ubL = at(LCQP_UBL); v.lbR = at(LCQP_LBR); v.ubR = at(LCQP_UBR);
+            v.lbA = at(LCQP_LBA); v.ubA = at(LCQP_UBA); v.x0 = at(LCQP_X0); v.y0 = at(LCQP_Y0);
+            LoopOut out;
+            osq::State st;
+            st.rho = 0; st.c = 1; st.cinv = 1; st.pri_res = 0; st.dua_res = 0; st.status_val = 0; st.iter = 0; st.interval = 0;
+            st.factor_bad = 0; st.admm_total = 0; st.factor_count = 0;
+            double* xo = a.xout + (size_t)b * nV;
+            double* yo = a.yout + (size_t)b * nD;
+            if (a.box_given) {
+                out.ret = RET_INVALID_OSQP_BOX; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
+                for (int j = 0; j < nV; j++) xo[j] = v.x0 ? v.x0[j] : 0.0;
+                for (int j = 0; j < mA; j++) yo[j] = 0.0;
+            } else
+                osq::lcqp_loop(a.S, v, a.o, w, a.instance_offset + (unsigned long long)b, xo, yo, out, st);
+            for (int j = mA; j < nD; j++) yo[j] = 0.0;
+            lcqp_cuda_stats r;
+            r.ret = out.ret; r.status = out.status; r.iterTotal = out.iterTotal; r.iterOuter = out.iterOuter;
+            r.subproblemIter = out.subIter; r.qpExitFlag = out.exitFlag; r.nDuals = mA; r.kktSolves = (int)st.factor_count;
+            r.rhoOpt = out.rhoOpt; r.admmIters = (double)st.admm_total;
+            a.stats[b] = r;
+        }
+        __syncwarp();
+    }
+}
+
 }  // namespace lcqp
 
 // =================================================================================================
@@ -592,6 +653,17 @@ struct lcqp_cuda_handle_s {
     bool pas_ready = false;               // prepared for the current load
     bool use_legacy = false;              // reduced Hessian not positive definite: the regularised solver runs
     int has_box = 0;
+    // OSQP flavour (qpSolver == 2 with osqp_admm): symbolic analysis of the batch's pattern + value arrays
+    bool osqp_ready = false;
+    osq::Symbolic* sym = nullptr;
+    osq::SymDev symdev;
+    int* sym_ints = nullptr;
+    size_t sym_ints_cap = 0;
+    double* csc_vals[4] = {nullptr, nullptr, nullptr, nullptr};   // Q, A, L, R values of the sparse door
+    size_t csc_vals_cap[4] = {0, 0, 0, 0};
+    const double* osqp_arr[LCQP_NUM_ARRAYS] = {};
+    unsigned long long osqp_stride[LCQP_NUM_ARRAYS] = {};
+    long long osqp_nnzL = 0;
     std::string err;
 };
 
@@ -652,6 +724,13 @@ void lcqp_cuda_default_options(lcqp_cuda_options* o)
     o->qp_refine_iter = 10;
     o->qp_adaptive_rho = 0;
     o->perturb_seed = 1;
+    o->osqp_admm = 0;
+    o->osqp_rho = 0.1; o->osqp_sigma = 1e-6; o->osqp_alpha = 1.6; o->osqp_delta = 1e-6;   // constants.h:59-78
+    o->osqp_eps_abs = 1e-3; o->osqp_eps_rel = 1e-3; o->osqp_eps_prim_inf = kEPS; o->osqp_eps_dual_inf = 1e-4;   // Options.cpp:329
+    o->osqp_adaptive_rho_tolerance = 5.0;
+    o->osqp_max_iter = 4000; o->osqp_check_termination = 25; o->osqp_scaling = 10;
+    o->osqp_adaptive_rho = 1; o->osqp_adaptive_rho_interval = 0; o->osqp_polish = 1; o->osqp_polish_refine_iter = 3;   // Options.cpp:331
+    o->osqp_reserved = 0;
 }
 
 int lcqp_cuda_create(int nV, int nC, int nComp, int batch_capacity, int device, lcqp_cuda_handle* out)
@@ -703,6 +782,9 @@ int lcqp_cuda_destroy(lcqp_cuda_handle h)
     cudaFree(h->pool_i); cudaFree(h->pool_d); cudaFree(h->pool_used); cudaFree(h->workspace);
     if (h->host_mats) cudaFreeHost(h->host_mats);
     cudaFree(h->pas_mats); cudaFree(h->pas_store); cudaFree(h->eqmask); cudaFree(h->fallback_flag);
+    cudaFree(h->sym_ints);
+    for (int k = 0; k < 4; k++) cudaFree(h->csc_vals[k]);
+    delete h->sym;
     if (h->pas_host) cudaFreeHost(h->pas_host);
     if (h->fallback_host) cudaFreeHost(h->fallback_host);
     if (h->load_stream) cudaStreamDestroy(h->load_stream);
@@ -740,6 +822,8 @@ int lcqp_cuda_set_options(lcqp_cuda_handle h, const lcqp_cuda_options* o)
 }
 
 static int pas_prepare_load(lcqp_cuda_handle h);
+static int osqp_prepare_dense(lcqp_cuda_handle h, int batch, unsigned shared_mask, const double* const* ptr);
+static int osqp_upload_symbolic(lcqp_cuda_handle h);
 
 static int load_common(lcqp_cuda_handle h, int batch, unsigned shared_mask, const double* const* ptr, bool device_ptrs)
 {
@@ -774,6 +858,16 @@ static int load_common(lcqp_cuda_handle h, int batch, unsigned shared_mask, cons
     h->loaded = true;
     h->ran = false;
     h->pas_ready = false;
+    h->osqp_ready = false;
+    if (h->opts.qpSolver == 2 && h->opts.osqp_admm) {
+        // the OSQP flavour: pattern analysis on the host (needs the caller's HOST arrays), no operand preparation
+        if (device_ptrs) return fail(h, LCQP_CUDA_BAD_ARGUMENT, "the OSQP flavour (osqp_admm) loads through lcqp_cuda_load or lcqp_cuda_load_csc");
+        const int rc = osqp_prepare_dense(h, batch, shared_mask, ptr);
+        if (rc != LCQP_CUDA_OK) return rc;
+        CK(cudaStreamSynchronize(h->load_stream), LCQP_CUDA_LAUNCH_FAILED);
+        h->osqp_ready = true;
+        return LCQP_CUDA_OK;
+    }
     // a load is complete when it returns: the copies are done (the caller may reuse its buffers, and any stream may
     // run the batch) and the batch-level operands are prepared, so that lcqp_cuda_run is one asynchronous launch
     const int rc = pas_prepare_load(h);
@@ -803,6 +897,90 @@ int lcqp_cuda_load_device(lcqp_cuda_handle h, int batch, unsigned shared_mask,
 {
     const double* p[LCQP_NUM_ARRAYS] = {Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0};
     return load_common(h, batch, shared_mask, p, true);
+}
+
+int lcqp_cuda_load_csc(lcqp_cuda_handle h, int batch, unsigned shared_mask,
+                       const int* Q_p, const int* Q_i, const double* Q_x, const double* g,
+                       const int* L_p, const int* L_i, const double* L_x,
+                       const int* R_p, const int* R_i, const double* R_x,
+                       const double* lbL, const double* ubL, const double* lbR, const double* ubR,
+                       const int* A_p, const int* A_i, const double* A_x, const double* lbA, const double* ubA,
+                       const double* x0, const double* y0)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (batch <= 0 || batch > h->capacity) return fail(h, LCQP_CUDA_BAD_ARGUMENT, "batch out of range");
+    if (!(h->opts.qpSolver == 2 && h->opts.osqp_admm)) return fail(h, LCQP_CUDA_BAD_ARGUMENT, "the sparse door serves the OSQP flavour (qpSolver = 2, osqp_admm = 1)");
+    if (!Q_p || !Q_i || !Q_x) return fail(h, LCQP_CUDA_BAD_ARGUMENT, "Q is NULL");
+    if (!g) return 116;
+    if (h->nC > 0 && (!A_p || !A_i || !A_x)) return 117;
+    if (!L_p || !L_i || !L_x || !R_p || !R_i || !R_x) return 118;
+    if (h->ran && h->last_stream != nullptr) cudaStreamSynchronize(h->last_stream);
+    else if (h->ran) cudaDeviceSynchronize();
+    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+    const int n = h->nV, nC = h->nC, nComp = h->nComp;
+    // index arrays: every column pointer monotone, every row index in range (Utilities.hpp INVALID_INDEX_POINTER / _ARRAY)
+    auto check = [&](const int* p, const int* i, int rows) -> int {
+        if (p[0] != 0) return 400;
+        for (int c = 0; c < n; c++) if (p[c + 1] < p[c]) return 400;
+        for (int e = 0; e < p[n]; e++) if (i[e] < 0 || i[e] >= rows) return 401;
+        return 0;
+    };
+    int rc = check(Q_p, Q_i, n);
+    if (!rc) rc = check(L_p, L_i, nComp);
+    if (!rc) rc = check(R_p, R_i, nComp);
+    if (!rc && nC > 0) rc = check(A_p, A_i, nC);
+    if (rc) return fail(h, rc, "invalid csc index arrays");
+    // vectors through the staging buffers of the dense door; matrices as value arrays
+    const double* vec[LCQP_NUM_ARRAYS] = {nullptr, g, nullptr, nullptr, lbL, ubL, lbR, ubR, nullptr, lbA, ubA, nullptr, nullptr, x0, y0};
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) {
+        h->dev_in[k] = nullptr; h->osqp_arr[k] = nullptr; h->osqp_stride[k] = 0;
+        const size_t len = field_len(k, n, nC, nComp);
+        if (!vec[k] || len == 0) continue;
+        const bool sh = (shared_mask >> k) & 1u;
+        const size_t count = sh ? len : len * (size_t)batch;
+        if (h->own_in_cap[k] < count) {
+            if (h->own_in[k]) cudaFree(h->own_in[k]);
+            h->own_in[k] = nullptr; h->own_in_cap[k] = 0;
+            const size_t want = sh ? count : len * (size_t)h->capacity;
+            if (cudaMalloc(&h->own_in[k], want * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(input)"); }
+            h->own_in_cap[k] = want;
+        }
+        CK(cudaMemcpyAsync(h->own_in[k], vec[k], count * sizeof(double), cudaMemcpyHostToDevice, h->load_stream), LCQP_CUDA_LAUNCH_FAILED);
+        h->osqp_arr[k] = h->own_in[k];
+        h->osqp_stride[k] = sh ? 0ull : (unsigned long long)len;
+    }
+    const int which[4] = {LCQP_Q, LCQP_A, LCQP_L, LCQP_R};
+    const double* vals[4] = {Q_x, A_x, L_x, R_x};
+    const size_t nnz[4] = {(size_t)Q_p[n], (nC > 0) ? (size_t)A_p[n] : 0, (size_t)L_p[n], (size_t)R_p[n]};
+    for (int k = 0; k < 4; k++) {
+        if (!vals[k] || nnz[k] == 0) continue;
+        const bool sh = (shared_mask >> which[k]) & 1u;
+        const size_t count = sh ? nnz[k] : nnz[k] * (size_t)batch;
+        if (h->csc_vals_cap[k] < count) {
+            if (h->csc_vals[k]) cudaFree(h->csc_vals[k]);
+            h->csc_vals[k] = nullptr; h->csc_vals_cap[k] = 0;
+            if (cudaMalloc(&h->csc_vals[k], count * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(csc values)"); }
+            h->csc_vals_cap[k] = count;
+        }
+        CK(cudaMemcpyAsync(h->csc_vals[k], vals[k], count * sizeof(double), cudaMemcpyHostToDevice, h->load_stream), LCQP_CUDA_LAUNCH_FAILED);
+        h->osqp_arr[which[k]] = h->csc_vals[k];
+        h->osqp_stride[which[k]] = sh ? 0ull : (unsigned long long)nnz[k];
+    }
+    std::vector<osq::Trip> Qpat, Apat;
+    osq::csc_patterns(n, nC, nComp, Q_p, Q_i, nC > 0 ? A_p : nullptr, A_i, L_p, L_i, R_p, R_i, Qpat, Apat);
+    if (!h->sym) h->sym = new (std::nothrow) osq::Symbolic();
+    if (!h->sym) return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "symbolic");
+    osq::analyse(n, nC + 2 * nComp, Qpat, Apat, *h->sym);
+    rc = osqp_upload_symbolic(h);
+    if (rc != LCQP_CUDA_OK) return rc;
+    CK(cudaStreamSynchronize(h->load_stream), LCQP_CUDA_LAUNCH_FAILED);
+    h->batch = batch;
+    h->shared_mask = shared_mask;
+    h->loaded = true;
+    h->ran = false;
+    h->pas_ready = false;
+    h->osqp_ready = true;
+    return LCQP_CUDA_OK;
 }
 
 int lcqp_cuda_set_instance_offset(lcqp_cuda_handle h, unsigned long long off)
@@ -1079,6 +1257,107 @@ static int pas_prepare_load(lcqp_cuda_handle h)
     return LCQP_CUDA_OK;
 }
 
+// ---- the OSQP flavour: symbolic analysis at load time, one launch per run -----------------------------------------
+static int osqp_upload_symbolic(lcqp_cuda_handle h)
+{
+    const osq::Symbolic& S = *h->sym;
+    const std::vector<int>* vs[18] = {&S.Pp, &S.Pi, &S.Psrc, &S.Ap, &S.Ai, &S.Asrc, &S.Qp, &S.Qi, &S.Qsrc, &S.perm, &S.Kp, &S.Ki, &S.Ksrc,
+                                      &S.Lp, &S.Li, &S.rp, &S.rcol, &S.rpos};
+    size_t total = 0;
+    size_t off[18];
+    for (int k = 0; k < 18; k++) { off[k] = total; total += (vs[k]->size() + 3) & ~(size_t)3; }
+    std::vector<int> pack(total ? total : 4, 0);
+    for (int k = 0; k < 18; k++) if (!vs[k]->empty()) memcpy(pack.data() + off[k], vs[k]->data(), vs[k]->size() * sizeof(int));
+    if (total > h->sym_ints_cap) {
+        if (h->sym_ints) cudaFree(h->sym_ints);
+        h->sym_ints = nullptr; h->sym_ints_cap = 0;
+        if (cudaMalloc(&h->sym_ints, (total ? total : 4) * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(symbolic)"); }
+        h->sym_ints_cap = total;
+    }
+    CK(cudaMemcpyAsync(h->sym_ints, pack.data(), pack.size() * sizeof(int), cudaMemcpyHostToDevice, h->load_stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaStreamSynchronize(h->load_stream), LCQP_CUDA_LAUNCH_FAILED);   // `pack` goes out of scope
+    osq::SymDev& D = h->symdev;
+    D.n = S.n; D.m = S.m; D.N = S.N; D.nC = h->nC; D.nComp = h->nComp;
+    D.nnzP = (int)S.Pi.size(); D.nnzA = (int)S.Ai.size(); D.nnzQ = (int)S.Qi.size(); D.nnzK = (int)S.Ki.size(); D.nnzL = (int)S.Li.size();
+    const int** dst[18] = {&D.Pp, &D.Pi, &D.Psrc, &D.Ap, &D.Ai, &D.Asrc, &D.Qp, &D.Qi, &D.Qsrc, &D.perm, &D.Kp, &D.Ki, &D.Ksrc, &D.Lp, &D.Li, &D.rp, &D.rcol, &D.rpos};
+    for (int k = 0; k < 18; k++) *dst[k] = h->sym_ints + off[k];
+    h->osqp_nnzL = (long long)S.Li.size();
+    return LCQP_CUDA_OK;
+}
+
+// dense door: the batch's union of non-zeros decides the pattern (host scan of the caller's arrays)
+static int osqp_prepare_dense(lcqp_cuda_handle h, int batch, unsigned shared_mask, const double* const* ptr)
+{
+    const int n = h->nV, nC = h->nC, nComp = h->nComp;
+    auto mask_of = [&](int k, size_t len) {
+        std::vector<unsigned char> mk(len ? len : 1, 0);
+        if (!ptr[k]) return mk;
+        const int reps = ((shared_mask >> k) & 1u) ? 1 : batch;
+        for (int b = 0; b < reps; b++) { const double* a = ptr[k] + len * (size_t)b; for (size_t e = 0; e < len; e++) if (a[e] != 0.0) mk[e] = 1; }
+        return mk;
+    };
+    const std::vector<unsigned char> Qm = mask_of(LCQP_Q, (size_t)n * n), Am = mask_of(LCQP_A, (size_t)nC * n),
+                                     Lm = mask_of(LCQP_L, (size_t)nComp * n), Rm = mask_of(LCQP_R, (size_t)nComp * n);
+    std::vector<osq::Trip> Qpat, Apat;
+    osq::dense_patterns(n, nC, nComp, Qm.data(), Am.data(), Lm.data(), Rm.data(), Qpat, Apat);
+    if (!h->sym) h->sym = new (std::nothrow) osq::Symbolic();
+    if (!h->sym) return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "symbolic");
+    osq::analyse(n, nC + 2 * nComp, Qpat, Apat, *h->sym);
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) {
+        h->osqp_arr[k] = h->dev_in[k];
+        h->osqp_stride[k] = ((shared_mask >> k) & 1u) ? 0ull : (unsigned long long)field_len(k, n, nC, nComp);
+    }
+    return osqp_upload_symbolic(h);
+}
+
+static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
+{
+    if (!h->osqp_ready) return fail(h, LCQP_CUDA_NOT_LOADED, "osqp_admm was set after the load: load again (the pattern analysis happens at load time)");
+    OsqpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.S = h->symdev;
+    a.o = h->opts;
+    for (int k = 0; k < LCQP_NUM_ARRAYS; k++) { a.arr[k] = h->osqp_arr[k]; a.stride[k] = (h->batch == 1) ? 0ull : h->osqp_stride[k]; }
+    a.batch = h->batch;
+    a.box_given = (h->osqp_arr[LCQP_LB] || h->osqp_arr[LCQP_UB]) ? 1 : 0;
+    a.ws_doubles = (osq::ws_doubles(a.S) + 1) & ~(size_t)1;
+    // one warp per CTA; as many resident warps as there are tiles, up to 16 per SM and a quarter of the device memory
+    const long long tiles = ((long long)h->batch + 31) / 32;
+    long long warps = (long long)h->num_sms * 16;
+    if (warps > tiles) warps = tiles;
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t per_warp = a.ws_doubles * 32 * sizeof(double);
+    const size_t budget = total_b / 4 > h->workspace_cap * sizeof(double) ? total_b / 4 : h->workspace_cap * sizeof(double);
+    while (warps > 1 && (size_t)warps * per_warp > budget) warps = (warps * 3) / 4;
+    const size_t ws_total = (size_t)warps * a.ws_doubles * 32;
+    if (ws_total > h->workspace_cap) {
+        if (h->workspace) { cudaDeviceSynchronize(); cudaFree(h->workspace); }
+        h->workspace = nullptr; h->workspace_cap = 0;
+        if (cudaMalloc(&h->workspace, ws_total * sizeof(double)) != cudaSuccess) { cudaGetLastError(); return fail(h, LCQP_CUDA_OUT_OF_MEMORY, "cudaMalloc(workspace)"); }
+        h->workspace_cap = ws_total;
+    }
+    a.workspace = h->workspace;
+    a.xout = h->xout; a.yout = h->yout; a.stats = h->stats; a.counter = h->counter;
+    a.instance_offset = h->instance_offset;
+    CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
+    if (getenv("LCQP_CUDA_VERBOSE"))
+        fprintf(stderr, "lcqp_cuda (OSQP flavour): %lld warps of 32 instances, N %d, nnz(L) %d, nnz(K) %d, workspace %.1f MB/warp, factor flops %lld\n",
+                warps, a.S.N, a.S.nnzL, a.S.nnzK, per_warp / 1.0e6, h->sym ? h->sym->factor_flops : 0ll);
+    lcqp_osqp_kernel<<<(unsigned)warps, 32, 0, stream>>>(a);
+    h->launches++;
+    CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
+    h->last_stream = stream;
+    h->last_grid = (int)warps;
+    h->last_smem = 0;
+    h->last_mE = -1;
+    h->ran = true;
+    return LCQP_CUDA_OK;
+}
+
 static int run_pas(lcqp_cuda_handle h, cudaStream_t stream)
 {
     PasArgs a;
@@ -1164,6 +1443,8 @@ int lcqp_cuda_run(lcqp_cuda_handle h, void* stream_v)
     if (!h->loaded) return fail(h, LCQP_CUDA_NOT_LOADED, "run before load");
     cudaStream_t stream = (cudaStream_t)stream_v;
     CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+    if (h->opts.qpSolver == 2 && h->opts.osqp_admm) return run_osqp(h, stream);
+    if (h->osqp_ready && !h->pas_ready) return fail(h, LCQP_CUDA_NOT_LOADED, "osqp_admm was cleared after the load: load again");
     if (h->use_legacy || !h->pas_ready || tune_env("LCQP_CUDA_LEGACY")) return run_legacy(h, stream);
     return run_pas(h, stream);
 }

@@ -1,0 +1,188 @@
+// lcqp_sparse_host.hpp -- host-side symbolic analysis of the OSQP-flavour path (plain C++17; used by lcqp_cabi.cu
+// and by the CPU build of the device code in tests/emu).
+//
+// What it replaces.  The reference's OSQP run factors the quasi-definite KKT matrix
+//     K = [ P + sigma I   A' ;  A   -diag(1/rho) ]          (/root/reference/external/osqp/src/kkt.c:6-177)
+// with QDLDL after an AMD ordering (lin_sys/direct/qdldl/qdldl_interface.c:177-323, qdldl_sources/src/qdldl.c:11-233).
+// Ordering, elimination tree and the pattern of L depend on the sparsity pattern only, and a batch shares its
+// pattern: this file does that analysis ONCE per load, on the host, and emits flat index "programs" that every
+// instance (one GPU thread each, lcqp_osqp.cuh) executes with its own values -- no integer workspace, no pattern
+// logic and no divergence on the device.
+//     ordering      minimum degree on the elimination graph (bitset adjacency; ties -> lowest index)
+//     etree + L     row-by-row reach through the elimination tree (the up-looking scheme of qdldl.c:72-233)
+//     row program   for row k of L: the columns it touches in elimination order and the slot of L(k, c) in column c
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace lcqp {
+namespace osq {
+
+enum { KSRC_P = 0, KSRC_A = 1, KSRC_RHO = 2, KSRC_SIGMA = 3 };
+inline int ksrc(int type, int idx) { return (type << 28) | idx; }
+
+struct Symbolic {
+    int n = 0, m = 0, N = 0;
+    // P: upper triangle of Q in CSC (rows sorted); A: [A; L; R] in CSC.  *src: index into the caller's value array
+    // (Qsrc: into the Q values; Asrc: (matrix << 28) | index, matrix 0 = A, 1 = L, 2 = R)
+    std::vector<int> Pp, Pi, Psrc;
+    std::vector<int> Ap, Ai, Asrc;
+    // the full symmetric Q in CSC for the outer loop's products (strict lower entries are separate values of the
+    // caller's array; the reference reads them too)
+    std::vector<int> Qp, Qi, Qsrc;
+    // permuted KKT (upper triangle, CSC), perm[new] = old, iperm[old] = new
+    std::vector<int> perm, iperm, Kp, Ki, Ksrc;
+    // L (unit lower, CSC, rows in increasing order) and the row programs
+    std::vector<int> Lp, Li;
+    std::vector<int> rp, rcol, rpos;   // row k: t in [rp[k], rp[k+1]): column rcol[t], slot rpos[t] of L
+    long long factor_flops = 0;        // multiply-subtracts of one numeric factorisation
+};
+
+// minimum-degree ordering of a symmetric pattern given as adjacency lists (no self loops)
+inline std::vector<int> min_degree_order(int N, const std::vector<std::vector<int>>& adj)
+{
+    const int W = (N + 63) / 64;
+    std::vector<uint64_t> bits((size_t)N * W, 0);
+    auto row = [&](int i) { return bits.data() + (size_t)i * W; };
+    for (int i = 0; i < N; i++) for (int j : adj[i]) if (j != i) row(i)[j >> 6] |= 1ull << (j & 63);
+    std::vector<int> deg(N), order;
+    std::vector<char> gone(N, 0);
+    auto popcnt = [&](int i) { int c = 0; for (int w = 0; w < W; w++) c += __builtin_popcountll(row(i)[w]); return c; };
+    for (int i = 0; i < N; i++) deg[i] = popcnt(i);
+    order.reserve(N);
+    std::vector<int> nb;
+    for (int step = 0; step < N; step++) {
+        int best = -1;
+        for (int i = 0; i < N; i++) if (!gone[i] && (best < 0 || deg[i] < deg[best])) best = i;
+        order.push_back(best);
+        gone[best] = 1;
+        nb.clear();
+        for (int w = 0; w < W; w++) { uint64_t b = row(best)[w]; while (b) { const int t = __builtin_ctzll(b); nb.push_back(w * 64 + t); b &= b - 1; } }
+        // the neighbours of the eliminated node become a clique; the node leaves their lists
+        for (int a : nb) {
+            uint64_t* ra = row(a);
+            const uint64_t* rb = row(best);
+            for (int w = 0; w < W; w++) ra[w] |= rb[w];
+            ra[a >> 6] &= ~(1ull << (a & 63));
+            ra[best >> 6] &= ~(1ull << (best & 63));
+            deg[a] = popcnt(a);
+        }
+    }
+    return order;
+}
+
+// Build everything from the patterns.  Qpat: full symmetric n x n pattern as (row, col, source index) triplets;
+// Apat: m x n pattern of [A; L; R] as (row, col, source) triplets.
+struct Trip { int r, c, src; };
+
+inline void analyse(int n, int m, const std::vector<Trip>& Qpat, const std::vector<Trip>& Apat, Symbolic& S)
+{
+    S.n = n; S.m = m; S.N = n + m;
+    const int N = S.N;
+    auto to_csc = [](int ncols, std::vector<Trip> t, std::vector<int>& p, std::vector<int>& i, std::vector<int>& s) {
+        std::sort(t.begin(), t.end(), [](const Trip& a, const Trip& b) { return a.c != b.c ? a.c < b.c : a.r < b.r; });
+        p.assign(ncols + 1, 0); i.clear(); s.clear();
+        for (const Trip& e : t) { p[e.c + 1]++; i.push_back(e.r); s.push_back(e.src); }
+        for (int c = 0; c < ncols; c++) p[c + 1] += p[c];
+    };
+    std::vector<Trip> up;
+    for (const Trip& e : Qpat) if (e.r <= e.c) up.push_back(e);
+    to_csc(n, up, S.Pp, S.Pi, S.Psrc);
+    to_csc(n, Qpat, S.Qp, S.Qi, S.Qsrc);
+    to_csc(n, Apat, S.Ap, S.Ai, S.Asrc);
+
+    // KKT pattern (unpermuted, upper triangle): P + sigma I ; A' ; -1/rho
+    struct KE { int r, c, src; };
+    std::vector<KE> ke;
+    std::vector<char> hasdiag(n, 0);
+    for (int c = 0; c < n; c++) for (int p = S.Pp[c]; p < S.Pp[c + 1]; p++) { ke.push_back({S.Pi[p], c, ksrc(KSRC_P, p)}); if (S.Pi[p] == c) hasdiag[c] = 1; }
+    for (int c = 0; c < n; c++) if (!hasdiag[c]) ke.push_back({c, c, ksrc(KSRC_SIGMA, c)});
+    for (int c = 0; c < n; c++) for (int p = S.Ap[c]; p < S.Ap[c + 1]; p++) ke.push_back({c, n + S.Ai[p], ksrc(KSRC_A, p)});   // A'(c, i) sits at (c, n + i)
+    for (int i = 0; i < m; i++) ke.push_back({n + i, n + i, ksrc(KSRC_RHO, i)});
+    std::vector<std::vector<int>> adj(N);
+    for (const KE& e : ke) if (e.r != e.c) { adj[e.r].push_back(e.c); adj[e.c].push_back(e.r); }
+    S.perm = min_degree_order(N, adj);
+    S.iperm.assign(N, 0);
+    for (int k = 0; k < N; k++) S.iperm[S.perm[k]] = k;
+    // permuted upper triangle
+    {
+        std::vector<Trip> t;
+        for (const KE& e : ke) {
+            int a = S.iperm[e.r], b = S.iperm[e.c];
+            if (a > b) std::swap(a, b);
+            t.push_back({a, b, e.src});
+        }
+        to_csc(N, t, S.Kp, S.Ki, S.Ksrc);
+    }
+    // elimination tree and the pattern of every row of L (reach of the row's entries through the tree), qdldl.c:11-70
+    std::vector<int> parent(N, -1), mark(N, -1);
+    std::vector<std::vector<int>> rowpat(N);   // columns c < k with L(k, c) != 0, in elimination order
+    std::vector<int> colcount(N, 0), stack, path;
+    for (int k = 0; k < N; k++) {
+        mark[k] = k;
+        std::vector<int>& pat = rowpat[k];
+        // QDLDL walks the entries of column k from first to last and pushes every new path in REVERSE on a buffer that
+        // is then read back to front: the resulting order is a topological order of the reach
+        std::vector<int> buf;
+        for (int p = S.Kp[k]; p < S.Kp[k + 1]; p++) {
+            int i = S.Ki[p];
+            if (i == k) continue;
+            path.clear();
+            while (mark[i] != k) {
+                if (parent[i] < 0) parent[i] = k;
+                path.push_back(i);
+                mark[i] = k;
+                i = parent[i];
+            }
+            for (int q = (int)path.size() - 1; q >= 0; q--) buf.push_back(path[q]);
+        }
+        for (int q = (int)buf.size() - 1; q >= 0; q--) pat.push_back(buf[q]);
+        for (int c : pat) colcount[c]++;
+    }
+    S.Lp.assign(N + 1, 0);
+    for (int c = 0; c < N; c++) S.Lp[c + 1] = S.Lp[c] + colcount[c];
+    S.Li.assign(S.Lp[N], 0);
+    std::vector<int> fill(N, 0);
+    S.rp.assign(N + 1, 0);
+    S.rcol.clear(); S.rpos.clear();
+    S.factor_flops = 0;
+    for (int k = 0; k < N; k++) {
+        for (int c : rowpat[k]) {
+            const int pos = S.Lp[c] + fill[c];
+            S.factor_flops += fill[c] + 2;
+            S.rcol.push_back(c);
+            S.rpos.push_back(pos);
+            S.Li[pos] = k;
+            fill[c]++;
+        }
+        S.rp[k + 1] = (int)S.rcol.size();
+    }
+}
+
+// Patterns from dense row-major matrices (the batch's union of non-zeros is passed in as 0/1 masks)
+inline void dense_patterns(int n, int nC, int nComp, const unsigned char* Qmask, const unsigned char* Amask, const unsigned char* Lmask,
+                           const unsigned char* Rmask, std::vector<Trip>& Qpat, std::vector<Trip>& Apat)
+{
+    Qpat.clear(); Apat.clear();
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) if (Qmask[(size_t)i * n + j] || Qmask[(size_t)j * n + i]) Qpat.push_back({i, j, i * n + j});
+    for (int r = 0; r < nC; r++) for (int j = 0; j < n; j++) if (Amask[(size_t)r * n + j]) Apat.push_back({r, j, (0 << 28) | (r * n + j)});
+    for (int r = 0; r < nComp; r++) for (int j = 0; j < n; j++) if (Lmask[(size_t)r * n + j]) Apat.push_back({nC + r, j, (1 << 28) | (r * n + j)});
+    for (int r = 0; r < nComp; r++) for (int j = 0; j < n; j++) if (Rmask[(size_t)r * n + j]) Apat.push_back({nC + nComp + r, j, (2 << 28) | (r * n + j)});
+}
+
+// Patterns from CSC index arrays (LCQProblem::loadLCQP(const csc*...), /root/reference/src/LCQProblem.cpp:312-387)
+inline void csc_patterns(int n, int nC, int nComp, const int* Qp, const int* Qi, const int* Ap, const int* Ai, const int* Lp, const int* Li,
+                         const int* Rp, const int* Ri, std::vector<Trip>& Qpat, std::vector<Trip>& Apat)
+{
+    Qpat.clear(); Apat.clear();
+    for (int c = 0; c < n; c++) for (int p = Qp[c]; p < Qp[c + 1]; p++) Qpat.push_back({Qi[p], c, p});
+    if (Ap) for (int c = 0; c < n; c++) for (int p = Ap[c]; p < Ap[c + 1]; p++) Apat.push_back({Ai[p], c, (0 << 28) | p});
+    for (int c = 0; c < n; c++) for (int p = Lp[c]; p < Lp[c + 1]; p++) Apat.push_back({nC + Li[p], c, (1 << 28) | p});
+    for (int c = 0; c < n; c++) for (int p = Rp[c]; p < Rp[c + 1]; p++) Apat.push_back({nC + nComp + Ri[p], c, (2 << 28) | p});
+}
+
+}  // namespace osq
+}  // namespace lcqp

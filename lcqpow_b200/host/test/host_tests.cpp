@@ -219,9 +219,10 @@ static void testNoDeviceIsLoud()
 }
 
 // ---- GPU tests ---------------------------------------------------------------------------------------------
-static ReturnValue solveWarmUp(LCQProblem& lcqp, const Options& o, bool withGuess = true)
+static ReturnValue solveWarmUp(LCQProblem& lcqp, const Options& o, bool withGuess = true, double g1 = -2.0)
 {
-    const examples::Problem p = examples::warmUp();
+    examples::Problem p = examples::warmUp();
+    p.g[1] = g1;
     lcqp.setOptions(o);
     ReturnValue r = lcqp.loadLCQP(p.Q.data(), p.g.data(), p.L.data(), p.R.data(), 0, 0, 0, 0, 0, 0, 0, 0, 0,
                                   withGuess ? p.x0.data() : nullptr, withGuess ? p.y0.data() : nullptr);
@@ -261,14 +262,18 @@ static void testHostLoopMatchesDeviceLoop()
     dev.setPerturbStep(false);
     host = dev;
     host.setStoreSteps(true);   // forces the host loop over SubsolverCUDA
+    // warm_up with g = (-2, -3): the shipped g = (-2, -2) is exactly symmetric in (x1, x2) and, without the
+    // perturbation, follows a saddle path that any difference in round-off leaves (tests/conftest.py,
+    // SYMMETRIC_SADDLE) -- the two routes need not leave it in the same pass.  The asymmetric problem has one
+    // trajectory: the unmodified reference (perturbStep off) ends S-stationary at (0, 1.5) with k = 8, i = 39.
     LCQProblem a(2, 0, 1), b(2, 0, 1);
-    CHECK_EQ(solveWarmUp(a, dev), SUCCESSFUL_RETURN);
-    CHECK_EQ(solveWarmUp(b, host), SUCCESSFUL_RETURN);
+    CHECK_EQ(solveWarmUp(a, dev, true, -3.0), SUCCESSFUL_RETURN);
+    CHECK_EQ(solveWarmUp(b, host, true, -3.0), SUCCESSFUL_RETURN);
     OutputStatistics sa, sb;
     a.getOutputStatistics(sa);
     b.getOutputStatistics(sb);
-    CHECK_EQ(sa.getIterOuter(), 29);   // perturbStep off: k = 29, i = 52
-    CHECK_EQ(sa.getIterTotal(), 52);
+    CHECK_EQ(sa.getIterOuter(), 8);
+    CHECK_EQ(sa.getIterTotal(), 39);
     CHECK_EQ(sb.getIterOuter(), sa.getIterOuter());
     CHECK_EQ(sb.getIterTotal(), sa.getIterTotal());
     CHECK_EQ(sb.getRhoOpt(), sa.getRhoOpt());

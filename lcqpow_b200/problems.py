@@ -267,3 +267,144 @@ def example_data_batch(data: dict, batch: int = 1, seed0: int = 30000) -> LCQPBa
     kw = {k: np.asarray(data[k], dtype=np.float64) for k in ("Q", "L", "R", "lbL", "ubL", "lbR", "ubR", "A", "lb", "x0")}
     return LCQPBatch(nV=nV, nC=nC, nComp=nComp, batch=batch, g=g, lbA=lbA, ubA=lbA.copy(), ub=ub,
                      shared=frozenset(kw.keys()), name="example_data", **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# Config C4: sparse LCQPs that share their sparsity pattern, in CSC form
+# ------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class SparseLCQPBatch:
+    """A batch of LCQPs in the layout of LCQProblem::loadLCQP(const csc* ...) (/root/reference/src/LCQProblem.cpp:312-387):
+    each matrix is (colptr int32[nV+1], rowidx int32[nnz], values) with values of shape (nnz,) when shared by the
+    batch, else (batch, nnz).  The patterns are shared by the whole batch."""
+
+    nV: int
+    nC: int
+    nComp: int
+    batch: int
+    Q: tuple
+    g: np.ndarray
+    L: tuple
+    R: tuple
+    A: Optional[tuple] = None
+    lbA: Optional[np.ndarray] = None
+    ubA: Optional[np.ndarray] = None
+    lbL: Optional[np.ndarray] = None
+    ubL: Optional[np.ndarray] = None
+    lbR: Optional[np.ndarray] = None
+    ubR: Optional[np.ndarray] = None
+    x0: Optional[np.ndarray] = None
+    y0: Optional[np.ndarray] = None
+    shared: frozenset = frozenset()
+    name: str = ""
+
+    def _dense(self, t, rows, b):
+        p, i, x = t
+        xv = x if x.ndim == 1 else x[b]
+        M = np.zeros((rows, self.nV))
+        for c in range(self.nV):
+            M[i[p[c]:p[c + 1]], c] = xv[p[c]:p[c + 1]]
+        return M
+
+    def to_dense(self, lo: int, hi: int) -> LCQPBatch:
+        """Instances [lo, hi) as a dense LCQPBatch (for the reference's dense front door)."""
+        nb = hi - lo
+        def vec(a, f):
+            if a is None:
+                return None
+            return a if f in self.shared else a[lo:hi]
+        mats = {}
+        for f, rows in (("Q", self.nV), ("L", self.nComp), ("R", self.nComp), ("A", self.nC)):
+            t = getattr(self, f)
+            if t is None:
+                mats[f] = None
+            elif f in self.shared:
+                mats[f] = self._dense(t, rows, 0)
+            else:
+                mats[f] = np.stack([self._dense(t, rows, b) for b in range(lo, hi)])
+        return LCQPBatch(nV=self.nV, nC=self.nC, nComp=self.nComp, batch=nb, Q=mats["Q"], g=vec(self.g, "g"), L=mats["L"], R=mats["R"],
+                         A=mats["A"], lbA=vec(self.lbA, "lbA"), ubA=vec(self.ubA, "ubA"), lbL=vec(self.lbL, "lbL"), ubL=vec(self.ubL, "ubL"),
+                         lbR=vec(self.lbR, "lbR"), ubR=vec(self.ubR, "ubR"), x0=vec(self.x0, "x0"), y0=vec(self.y0, "y0"),
+                         shared=self.shared, name=self.name)
+
+    def slice(self, lo: int, hi: int) -> "SparseLCQPBatch":
+        kw = {}
+        for f in ("Q", "L", "R", "A"):
+            t = getattr(self, f)
+            kw[f] = None if t is None else (t if (f in self.shared) else (t[0], t[1], t[2][lo:hi]))
+        for f in ("g", "lbA", "ubA", "lbL", "ubL", "lbR", "ubR", "x0", "y0"):
+            a = getattr(self, f)
+            kw[f] = None if a is None else (a if f in self.shared else a[lo:hi])
+        return dataclasses.replace(self, batch=hi - lo, **kw)
+
+
+def sparse_banded_batch(batch: int, n: int = 1000, nComp: int = 500, nC: int = 300, seed0: int = 40000, lo: int = 0) -> SparseLCQPBatch:
+    """Config C4: banded Q (off-diagonals (i, i+1..i+3) ~ 0.1 N(0,1), diagonal = sum of |off-diagonals| of the row
+    + 0.5 + U(0,1): strictly diagonally dominant), A with 5 non-zeros per row ~ N(0,1) in a +-8 column window around
+    r n / nC, L picks x_2i and R picks x_2i+1; a feasible complementary x* (one of each pair 0, the other U(0,1)),
+    lbA = A x* - 0.1 - U(0,1), ubA = A x* + 0.1 + U(0,1), g ~ N(0,1).  The pattern comes from default_rng(seed0) and
+    is shared by the batch, the values of instance b from default_rng(seed0 + 1 + b).  Instances [lo, lo + batch)."""
+    assert 2 * nComp <= n
+    prng = np.random.default_rng(seed0)
+    # pattern of A: 5 distinct columns per row
+    arows, acols = [], []
+    for r in range(nC):
+        c = (r * n) // nC
+        window = np.arange(max(0, c - 8), min(n, c + 9))
+        cols = np.sort(prng.choice(window, size=5, replace=False))
+        arows += [r] * 5
+        acols += cols.tolist()
+    arows, acols = np.array(arows), np.array(acols)
+    order = np.lexsort((arows, acols))          # CSC order: by column, then row
+    Ap = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(Ap, acols + 1, 1)
+    Ap = np.cumsum(Ap).astype(np.int32)
+    Ai = arows[order].astype(np.int32)
+    # pattern of Q: |i - j| <= 3
+    qrows, qcols = [], []
+    for j in range(n):
+        for i in range(max(0, j - 3), min(n, j + 4)):
+            qrows.append(i); qcols.append(j)
+    qrows, qcols = np.array(qrows), np.array(qcols)
+    Qp = np.zeros(n + 1, dtype=np.int32)
+    np.add.at(Qp, qcols + 1, 1)
+    Qp = np.cumsum(Qp).astype(np.int32)
+    Qi = qrows.astype(np.int32)
+    Lp = np.zeros(n + 1, dtype=np.int32); Rp = np.zeros(n + 1, dtype=np.int32)
+    for i in range(nComp):
+        Lp[2 * i + 1:] += 1
+        Rp[2 * i + 2:] += 1
+    Li = np.arange(nComp, dtype=np.int32); Ri = np.arange(nComp, dtype=np.int32)
+    Lx = np.ones(nComp); Rx = np.ones(nComp)
+
+    Qx = np.empty((batch, len(Qi))); Ax = np.empty((batch, len(Ai)))
+    g = np.empty((batch, n)); lbA = np.empty((batch, nC)); ubA = np.empty((batch, nC))
+    for k in range(batch):
+        rng = np.random.default_rng(seed0 + 1 + lo + k)
+        off = 0.1 * rng.standard_normal((n, 3))               # off[i, d-1] = Q[i, i+d]
+        for d in range(1, 4):
+            off[n - d:, d - 1] = 0.0
+        rowabs = np.abs(off).sum(axis=1)
+        for d in range(1, 4):
+            rowabs[d:] += np.abs(off[:n - d, d - 1])
+        diag = rowabs + 0.5 + rng.uniform(0.0, 1.0, size=n)
+        dd = qrows - qcols                                     # row - col
+        qv = np.where(dd == 0, diag[qcols], 0.0)
+        for d in range(1, 4):
+            up = dd == -d                                      # (i, i + d): row = col - d
+            qv[up] = off[qrows[up], d - 1]
+            lw = dd == d                                       # (i + d, i): mirrors (col, col + d)
+            qv[lw] = off[qcols[lw], d - 1]
+        Qx[k] = qv
+        av = rng.standard_normal((nC, 5)).reshape(-1)          # row-major (r, slot)
+        Ax[k] = av[order]
+        xs = rng.uniform(0.0, 1.0, size=n)
+        pick = rng.integers(0, 2, size=nComp)
+        xs[2 * np.arange(nComp) + (1 - pick)] = 0.0            # pick = 1: x_2i = 0 ... one of each pair
+        Axs = np.zeros(nC)
+        np.add.at(Axs, arows, av * xs[acols])
+        lbA[k] = Axs - 0.1 - rng.uniform(0.0, 1.0, size=nC)
+        ubA[k] = Axs + 0.1 + rng.uniform(0.0, 1.0, size=nC)
+        g[k] = rng.standard_normal(n)
+    return SparseLCQPBatch(nV=n, nC=nC, nComp=nComp, batch=batch, Q=(Qp, Qi, Qx), g=g, L=(Lp, Li, Lx), R=(Rp, Ri, Rx),
+                           A=(Ap, Ai, Ax), lbA=lbA, ubA=ubA, shared=frozenset(("L", "R")), name=f"sparse_n{n}")

@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "../../lcqpow_b200/csrc/lcqp_pas.cuh"
+#include "../../lcqpow_b200/csrc/lcqp_osqp.cuh"
+#include "../../lcqpow_b200/csrc/lcqp_sparse_host.hpp"
 
 using namespace lcqp;
 
@@ -126,6 +128,76 @@ static int legacy_solve_batch(int batch, int nV, int nC, int nComp, unsigned sha
     return nfail;
 }
 
+// ---- the OSQP flavour (lcqp_osqp.cuh): pattern analysis on the host, then one scalar run per instance ------------
+static long long g_osqp_nnzL = 0, g_osqp_factor_flops = 0;
+extern "C" void lcqp_emu_osqp_info(long long* nnzL, long long* factor_flops) { *nnzL = g_osqp_nnzL; *factor_flops = g_osqp_factor_flops; }
+
+static void sym_to_dev(const osq::Symbolic& S, int nC, int nComp, osq::SymDev& D)
+{
+    D.n = S.n; D.m = S.m; D.N = S.N; D.nC = nC; D.nComp = nComp;
+    D.nnzP = (int)S.Pi.size(); D.nnzA = (int)S.Ai.size(); D.nnzQ = (int)S.Qi.size(); D.nnzK = (int)S.Ki.size(); D.nnzL = (int)S.Li.size();
+    D.Pp = S.Pp.data(); D.Pi = S.Pi.data(); D.Psrc = S.Psrc.data(); D.Ap = S.Ap.data(); D.Ai = S.Ai.data(); D.Asrc = S.Asrc.data();
+    D.Qp = S.Qp.data(); D.Qi = S.Qi.data(); D.Qsrc = S.Qsrc.data(); D.perm = S.perm.data(); D.Kp = S.Kp.data(); D.Ki = S.Ki.data(); D.Ksrc = S.Ksrc.data();
+    D.Lp = S.Lp.data(); D.Li = S.Li.data(); D.rp = S.rp.data(); D.rcol = S.rcol.data(); D.rpos = S.rpos.data();
+}
+
+static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned shared_mask_in, const double* const* base,
+                            const lcqp_cuda_options* o, double* x, double* y, lcqp_cuda_stats* res)
+{
+    const unsigned all_bits = (1u << LCQP_NUM_ARRAYS) - 1u;
+    const unsigned shared_mask = (batch == 1) ? all_bits : shared_mask_in;
+    const int mA = nC + 2 * nComp, nD = nV + mA;
+    auto ptr = [&](int k, int b) { return base[k] ? base[k] + (((shared_mask >> k) & 1u) ? 0 : field_len(k, nV, nC, nComp) * (size_t)b) : nullptr; };
+    if (base[LCQP_LB] || base[LCQP_UB]) {   // LCQProblem.cpp:930-957
+        for (int b = 0; b < batch; b++) {
+            memset(&res[b], 0, sizeof(res[b]));
+            res[b].ret = RET_INVALID_OSQP_BOX; res[b].nDuals = mA;
+            for (int j = 0; j < nV; j++) x[(size_t)b * nV + j] = base[LCQP_X0] ? ptr(LCQP_X0, b)[j] : 0.0;
+            for (int j = 0; j < nD; j++) y[(size_t)b * nD + j] = 0.0;
+        }
+        return batch;
+    }
+    // union of the non-zeros over the batch
+    auto mask_of = [&](int k, size_t len) {
+        std::vector<unsigned char> mk(len, 0);
+        if (!base[k]) return mk;
+        const int reps = ((shared_mask >> k) & 1u) ? 1 : batch;
+        for (int b = 0; b < reps; b++) { const double* a = base[k] + len * (size_t)b; for (size_t e = 0; e < len; e++) if (a[e] != 0.0) mk[e] = 1; }
+        return mk;
+    };
+    const std::vector<unsigned char> Qm = mask_of(LCQP_Q, (size_t)nV * nV), Am = mask_of(LCQP_A, (size_t)nC * nV),
+                                     Lm = mask_of(LCQP_L, (size_t)nComp * nV), Rm = mask_of(LCQP_R, (size_t)nComp * nV);
+    std::vector<osq::Trip> Qpat, Apat;
+    osq::dense_patterns(nV, nC, nComp, Qm.data(), Am.data(), Lm.data(), Rm.data(), Qpat, Apat);
+    osq::Symbolic S;
+    osq::analyse(nV, mA, Qpat, Apat, S);
+    g_osqp_nnzL = (long long)S.Li.size(); g_osqp_factor_flops = S.factor_flops;
+    osq::SymDev D;
+    sym_to_dev(S, nC, nComp, D);
+    std::vector<double> ws(osq::ws_doubles(D) + 8);
+    osq::Work w;
+    osq::carve(w, D, ws.data());
+    int nfail = 0;
+    for (int b = 0; b < batch; b++) {
+        osq::View v;
+        v.Q = ptr(LCQP_Q, b); v.A = ptr(LCQP_A, b); v.L = ptr(LCQP_L, b); v.R = ptr(LCQP_R, b); v.g = ptr(LCQP_G, b);
+        v.lbL = ptr(LCQP_LBL, b); v.ubL = ptr(LCQP_UBL, b); v.lbR = ptr(LCQP_LBR, b); v.ubR = ptr(LCQP_UBR, b);
+        v.lbA = ptr(LCQP_LBA, b); v.ubA = ptr(LCQP_UBA, b); v.x0 = ptr(LCQP_X0, b); v.y0 = ptr(LCQP_Y0, b);
+        LoopOut out;
+        osq::State st;
+        memset(&st, 0, sizeof(st));
+        osq::lcqp_loop(D, v, *o, w, g_instance_offset + (unsigned long long)b, x + (size_t)b * nV, y + (size_t)b * nD, out, st);
+        for (int j = mA; j < nD; j++) y[(size_t)b * nD + j] = 0.0;
+        lcqp_cuda_stats r;
+        r.ret = out.ret; r.status = out.status; r.iterTotal = out.iterTotal; r.iterOuter = out.iterOuter; r.subproblemIter = out.subIter;
+        r.qpExitFlag = out.exitFlag; r.nDuals = mA; r.kktSolves = (int)st.factor_count; r.rhoOpt = out.rhoOpt; r.admmIters = (double)st.admm_total;
+        res[b] = r;
+        nfail += (out.ret != 0);
+    }
+    return nfail;
+}
+
+
 // ---- the parametric active-set path (lcqp_pas.cuh), driven the way lcqp_cabi.cu drives it: the equality mask over the
 // batch, batch-level preparation when Q/A/L/R are shared, then pas_run_instance per instance.  Instances whose Hessian is
 // not positive definite (status 1) go to the regularised solver above, as in the product.
@@ -146,6 +218,7 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
     if (getenv("LCQP_EMU_LEGACY"))
         return legacy_solve_batch(batch, nV, nC, nComp, shared_mask_in, Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0, o, x, y, res);
     const double* base[LCQP_NUM_ARRAYS] = {Q, g, L, R, lbL, ubL, lbR, ubR, A, lbA, ubA, lb, ub, x0, y0};
+    if (o->qpSolver == 2 && o->osqp_admm) return osqp_solve_batch(batch, nV, nC, nComp, shared_mask_in, base, o, x, y, res);
     const PDims d = make_pdims(nV, nC, nComp, (o->qpSolver != 2) && (lb || ub));
     Dims dold = make_dims(nV, nC, nComp, d.has_box);
     const unsigned all_bits = (1u << LCQP_NUM_ARRAYS) - 1u;
@@ -250,4 +323,11 @@ extern "C" void lcqp_emu_default_options(lcqp_cuda_options* o)
     o->qp_refine_iter = 10;
     o->qp_adaptive_rho = 0;
     o->perturb_seed = 1;
+    o->osqp_admm = 0;
+    o->osqp_rho = 0.1; o->osqp_sigma = 1e-6; o->osqp_alpha = 1.6; o->osqp_delta = 1e-6;
+    o->osqp_eps_abs = 1e-3; o->osqp_eps_rel = 1e-3; o->osqp_eps_prim_inf = kEPS; o->osqp_eps_dual_inf = 1e-4;
+    o->osqp_adaptive_rho_tolerance = 5.0;
+    o->osqp_max_iter = 4000; o->osqp_check_termination = 25; o->osqp_scaling = 10;
+    o->osqp_adaptive_rho = 1; o->osqp_adaptive_rho_interval = 0; o->osqp_polish = 1; o->osqp_polish_refine_iter = 3;
+    o->osqp_reserved = 0;
 }

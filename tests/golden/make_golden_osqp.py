@@ -1,0 +1,55 @@
+"""Generate tests/golden/reference_families_osqp.npz: the UNMODIFIED reference's OSQP_SPARSE runs (oracle/_ref) of the
+families the OSQP flavour is checked against.  Run in the dev container after `make -C oracle ref`:
+
+    python tests/golden/make_golden_osqp.py
+
+perturbStep is off and adaptive_rho_interval is fixed to 25: with its default (0) OSQP derives the interval from
+wall-clock timings (external/osqp/src/osqp.c:459-485) and the reference's own iteration counts change from run to run.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from lcqpow_b200 import problems as P  # noqa: E402
+from oracle import pyref  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def osqp_family_cases():
+    """name -> (batch, option overrides).  Dense LCQPBatch, or SparseLCQPBatch for the sparse configuration C4."""
+    return {
+        "dense_bench": (P.dense_random_batch(256), {}),
+        "dense_n32": (P.dense_random_batch(32, n=32, nComp=16, nC=8), {}),
+        "circle_bench": (P.circle_batch_fast(64), {"stationarityTolerance": 10e-3}),
+        "sparse_c4": (P.sparse_banded_batch(16), {}),
+    }
+
+
+def main():
+    ref = pyref.RefLib()
+    fam = {}
+    for name, (pb, over) in osqp_family_cases().items():
+        o = ref.default_options(qpSolver=pyref.OSQP_SPARSE, perturbStep=0, **over)
+        o.osqp_adaptive_rho_interval = 25
+        if isinstance(pb, P.SparseLCQPBatch):
+            parts = [ref.solve_batch(pb.to_dense(b, b + 1), o) for b in range(pb.batch)]
+            x = np.concatenate([s.x for s in parts]); y = np.concatenate([s.y for s in parts]); res = np.concatenate([s.res for s in parts])
+        else:
+            s = ref.solve_batch(pb, o)
+            x, y, res = s.x, s.y, s.res
+        fam[f"{name}/x"] = x
+        fam[f"{name}/y"] = y.astype(np.float32)
+        for f in ("ret", "status", "iterTotal", "iterOuter", "subproblemIter", "qpExitFlag"):
+            fam[f"{name}/{f}"] = res[f].astype(np.int32)
+        fam[f"{name}/rhoOpt"] = res["rhoOpt"]
+        print(name, "ret", np.unique(res["ret"], return_counts=True), "k mean", res["iterOuter"].mean(), "i mean", res["iterTotal"].mean(),
+              "ADMM iterations mean", res["subproblemIter"].mean())
+    np.savez_compressed(os.path.join(HERE, "reference_families_osqp.npz"), **fam)
+
+
+if __name__ == "__main__":
+    main()

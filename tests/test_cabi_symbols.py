@@ -24,13 +24,13 @@ def test_header_symbols_are_exported():
     assert len(names) >= 20
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.lcqp_cuda_abi_version() == 1
+    assert lib.lcqp_cuda_abi_version() == 2
     assert set(L.api.EXPORTS) == set(names)
 
 
 def test_struct_layouts_match_header():
     import lcqpow_b200 as L
-    assert C.sizeof(L.api.CudaOptions) == 6 * 8 + 6 * 4 + 6 * 8 + 4 * 4 + 8
+    assert C.sizeof(L.api.CudaOptions) == 6 * 8 + 6 * 4 + 6 * 8 + 4 * 4 + 8 + 9 * 8 + 8 * 4   # ABI 2: + the OSQPSettings block
     assert L.api.STATS_DTYPE.itemsize == 8 * 4 + 2 * 8
 
 
