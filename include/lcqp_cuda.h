@@ -93,6 +93,10 @@ typedef struct {
     int osqp_polish;                  /* 1      */
     int osqp_polish_refine_iter;      /* 3      */
     int osqp_reserved;
+    /* qpOASES::Options that the parametric active-set solver honours (Options::setqpOASESOptions,
+     * /root/reference/src/Options.cpp:262-266; defaults /root/reference/external/qpOASES/src/Options.cpp:115,116) */
+    double qpoases_terminationTolerance;   /* 5e6 * EPS: remaining relative homotopy length at which a QP ends */
+    double qpoases_boundTolerance;         /* 1e6 * EPS: distance at which a bound counts as active (initial working set, far bounds) */
 } lcqp_cuda_options;
 
 /* Mirrors LCQPow::OutputStatistics counters (/root/reference/include/OutputStatistics.hpp:209-226),

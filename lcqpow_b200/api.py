@@ -58,7 +58,8 @@ class CudaOptions(C.Structure):
                 ("osqp_eps_dual_inf", C.c_double), ("osqp_adaptive_rho_tolerance", C.c_double),
                 ("osqp_max_iter", C.c_int), ("osqp_check_termination", C.c_int), ("osqp_scaling", C.c_int),
                 ("osqp_adaptive_rho", C.c_int), ("osqp_adaptive_rho_interval", C.c_int), ("osqp_polish", C.c_int),
-                ("osqp_polish_refine_iter", C.c_int), ("osqp_reserved", C.c_int)]
+                ("osqp_polish_refine_iter", C.c_int), ("osqp_reserved", C.c_int),
+                ("qpoases_terminationTolerance", C.c_double), ("qpoases_boundTolerance", C.c_double)]
 
 
 STATS_DTYPE = np.dtype([("ret", "i4"), ("status", "i4"), ("iterTotal", "i4"), ("iterOuter", "i4"),
@@ -188,6 +189,15 @@ class Options:
         if on:
             self.c.qpSolver = OSQP_SPARSE
         return self.setOSQPOptions(**settings)
+
+    def setqpOASESOptions(self, **settings):
+        """qpOASES::Options fields the device solver honours: terminationTolerance, boundTolerance
+        (Options::setqpOASESOptions, Options.cpp:262-266)."""
+        for k, v in settings.items():
+            if not hasattr(self.c, "qpoases_" + k):
+                return 100
+            setattr(self.c, "qpoases_" + k, v)
+        return 0
 
     def setOSQPOptions(self, **settings):
         for k, v in settings.items():

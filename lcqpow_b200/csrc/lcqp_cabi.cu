@@ -548,13 +548,15 @@ struct OsqpArgs {
     unsigned int* counter;
     unsigned long long instance_offset;
     int box_given;                               // lb / ub were loaded: INVALID_OSQP_BOX_CONSTRAINTS (LCQProblem.cpp:930-957)
+    unsigned smem_bytes;                         // N x 32 doubles of solve / factor scratch per warp when that fits, else 0 (global, L2)
 };
 
 __global__ void __launch_bounds__(32) lcqp_osqp_kernel(const __grid_constant__ OsqpArgs a)
 {
     const int lane = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char osqp_smem[];
     osq::Work w;
-    osq::carve(w, a.S, a.workspace + (size_t)blockIdx.x * a.ws_doubles * 32 + lane);
+    osq::carve(w, a.S, a.workspace + (size_t)blockIdx.x * a.ws_doubles * 32 + lane, a.smem_bytes ? reinterpret_cast<double*>(osqp_smem) + lane : nullptr);
     const int nV = a.S.n, mA = a.S.m, nD = nV + mA;
     for (;;) {
         unsigned tile = 0;
@@ -731,6 +733,8 @@ void lcqp_cuda_default_options(lcqp_cuda_options* o)
     o->osqp_max_iter = 4000; o->osqp_check_termination = 25; o->osqp_scaling = 10;
     o->osqp_adaptive_rho = 1; o->osqp_adaptive_rho_interval = 0; o->osqp_polish = 1; o->osqp_polish_refine_iter = 3;   // Options.cpp:331
     o->osqp_reserved = 0;
+    o->qpoases_terminationTolerance = 5.0e6 * 2.221e-16;   // qpOASES Options.cpp:115
+    o->qpoases_boundTolerance = 1.0e6 * 2.221e-16;         // :116
 }
 
 int lcqp_cuda_create(int nV, int nC, int nComp, int batch_capacity, int device, lcqp_cuda_handle* out)
@@ -817,6 +821,12 @@ int lcqp_cuda_set_options(lcqp_cuda_handle h, const lcqp_cuda_options* o)
     if (o->qpSolver < 0 || o->qpSolver > 2) return 109;
     if (o->nDynamicPenalty > kMaxLeyffer) return LCQP_CUDA_BAD_ARGUMENT;
     if (!qp_knobs_valid(o)) return LCQP_CUDA_BAD_ARGUMENT;
+    if (!(o->qpoases_terminationTolerance > 0) || !(o->qpoases_boundTolerance > 0)) return LCQP_CUDA_BAD_ARGUMENT;
+    if (o->qpSolver == 2 && o->osqp_admm &&
+        (!(o->osqp_rho > 0) || !(o->osqp_sigma > 0) || !(o->osqp_alpha > 0 && o->osqp_alpha < 2) || !(o->osqp_delta > 0) || o->osqp_max_iter < 1 ||
+         o->osqp_check_termination < 0 || o->osqp_scaling < 0 || o->osqp_polish_refine_iter < 0 || !(o->osqp_adaptive_rho_tolerance >= 1) ||
+         !(o->osqp_eps_abs >= 0) || !(o->osqp_eps_rel >= 0) || !(o->osqp_eps_prim_inf > 0) || !(o->osqp_eps_dual_inf > 0)))
+        return LCQP_CUDA_BAD_ARGUMENT;   // validate_settings, external/osqp/src/auxil.c:880-1000
     h->opts = *o;
     return LCQP_CUDA_OK;
 }
@@ -1321,9 +1331,19 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     a.batch = h->batch;
     a.box_given = (h->osqp_arr[LCQP_LB] || h->osqp_arr[LCQP_UB]) ? 1 : 0;
     a.ws_doubles = (osq::ws_doubles(a.S) + 1) & ~(size_t)1;
-    // one warp per CTA; as many resident warps as there are tiles, up to 16 per SM and a quarter of the device memory
+    // the scratch vector of the triangular solves (a chain of dependent read-modify-writes) sits in shared memory when
+    // N x 32 doubles fit the CTA's budget
+    const size_t sm_need = (size_t)a.S.N * 32 * sizeof(double);
+    a.smem_bytes = (sm_need <= (size_t)kSmemMax - 1024) ? (unsigned)sm_need : 0u;
+    if (tune_env("LCQP_CUDA_OSQP_NOSMEM")) a.smem_bytes = 0;
+    CK(cudaFuncSetAttribute(lcqp_osqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_osqp_kernel, 32, a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);
+    if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
+    if (per_sm > 16) per_sm = 16;
+    // one warp per CTA; as many resident warps as there are tiles, up to per_sm per SM and a quarter of the device memory
     const long long tiles = ((long long)h->batch + 31) / 32;
-    long long warps = (long long)h->num_sms * 16;
+    long long warps = (long long)h->num_sms * per_sm;
     if (warps > tiles) warps = tiles;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
@@ -1344,15 +1364,15 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
     if (getenv("LCQP_CUDA_VERBOSE"))
-        fprintf(stderr, "lcqp_cuda (OSQP flavour): %lld warps of 32 instances, N %d, nnz(L) %d, nnz(K) %d, workspace %.1f MB/warp, factor flops %lld\n",
-                warps, a.S.N, a.S.nnzL, a.S.nnzK, per_warp / 1.0e6, h->sym ? h->sym->factor_flops : 0ll);
-    lcqp_osqp_kernel<<<(unsigned)warps, 32, 0, stream>>>(a);
+        fprintf(stderr, "lcqp_cuda (OSQP flavour): %lld warps of 32 instances (%d per SM), N %d, nnz(L) %d, nnz(K) %d, workspace %.1f MB/warp, smem %u B/warp, factor flops %lld\n",
+                warps, per_sm, a.S.N, a.S.nnzL, a.S.nnzK, per_warp / 1.0e6, a.smem_bytes, h->sym ? h->sym->factor_flops : 0ll);
+    lcqp_osqp_kernel<<<(unsigned)warps, 32, a.smem_bytes, stream>>>(a);
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
     h->last_stream = stream;
     h->last_grid = (int)warps;
-    h->last_smem = 0;
+    h->last_smem = (int)a.smem_bytes;
     h->last_mE = -1;
     h->ran = true;
     return LCQP_CUDA_OK;

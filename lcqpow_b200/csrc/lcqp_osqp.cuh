@@ -69,6 +69,7 @@ struct Work {
     Vec sD, sDi, q, x, xp, dx, Pxv, Aty, px, xk, pk, gk, gt, gphi, stat, tn1, tn2;   // n
     Vec sE, sEi, l, u, z, zp, y, dy, Axv, rv, riv, pz, py, act, yk, tm1, tm2;       // m
     Vec xt, bp, w3;                                            // N
+    Vec sm;                                                    // N: scratch of the factorisation and of the triangular solves -- shared memory when it fits
 };
 
 LCQ_HD inline size_t ws_doubles(const SymDev& S)
@@ -77,7 +78,7 @@ LCQ_HD inline size_t ws_doubles(const SymDev& S)
 }
 
 // `base` points at element 0 of this lane (tile base + lane); consecutive vectors follow each other
-LCQ_HD inline void carve(Work& w, const SymDev& S, double* base)
+LCQ_HD inline void carve(Work& w, const SymDev& S, double* base, double* smem_lane = nullptr)
 {
     size_t off = 0;
     auto take = [&](size_t k) { Vec v; v.p = base + off * OSQ_STRIDE; off += k; return v; };
@@ -87,6 +88,8 @@ LCQ_HD inline void carve(Work& w, const SymDev& S, double* base)
     Vec* mv[17] = {&w.sE, &w.sEi, &w.l, &w.u, &w.z, &w.zp, &w.y, &w.dy, &w.Axv, &w.rv, &w.riv, &w.pz, &w.py, &w.act, &w.yk, &w.tm1, &w.tm2};
     for (int k = 0; k < 17; k++) *mv[k] = take(S.m);
     w.xt = take(S.N); w.bp = take(S.N); w.w3 = take(S.N);
+    w.sm = w.bp;
+    if (smem_lane) w.sm.p = smem_lane;
 }
 
 struct State {
@@ -245,7 +248,7 @@ LCQ_DEV void kkt_factor(const SymDev& S, const Work& w, State& st, int polish, d
 {
     const int N = S.N;
     const Vec Lx = polish ? w.Lxp : w.Lx, Dinv = polish ? w.Dinvp : w.Dinv;
-    const Vec yv = w.w3;
+    const Vec yv = w.sm;
     int positive = 0, bad = 0;
     for (int k = 0; k < N; k++) yv[k] = 0.0;
     for (int k = 0; k < N; k++) {
@@ -259,7 +262,16 @@ LCQ_DEV void kkt_factor(const SymDev& S, const Work& w, State& st, int polish, d
             const int c = S.rcol[t], pos = S.rpos[t];
             const double yc = yv[c];
             yv[c] = 0.0;
-            for (int p = S.Lp[c]; p < pos; p++) yv[S.Li[p]] -= Lx[p] * yc;
+            // (the rows of one column are distinct: four independent updates in flight)
+            int p = S.Lp[c];
+            for (; p + 4 <= pos; p += 4) {
+                const int r0 = S.Li[p], r1 = S.Li[p + 1], r2 = S.Li[p + 2], r3 = S.Li[p + 3];
+                const double l0 = Lx[p], l1 = Lx[p + 1], l2 = Lx[p + 2], l3 = Lx[p + 3];
+                double a0 = yv[r0], a1 = yv[r1], a2 = yv[r2], a3 = yv[r3];
+                a0 -= l0 * yc; a1 -= l1 * yc; a2 -= l2 * yc; a3 -= l3 * yc;
+                yv[r0] = a0; yv[r1] = a1; yv[r2] = a2; yv[r3] = a3;
+            }
+            for (; p < pos; p++) yv[S.Li[p]] -= Lx[p] * yc;
             const double lkc = yc * Dinv[c];
             Lx[pos] = lkc;
             dk -= yc * lkc;
@@ -278,12 +290,21 @@ LCQ_DEV void kkt_factor(const SymDev& S, const Work& w, State& st, int polish, d
 LCQ_DEV void kkt_solve(const SymDev& S, const Work& w, const Vec& b, int polish)
 {
     const int N = S.N, n = S.n;
-    const Vec bp = w.bp;
+    const Vec bp = w.sm;
     const Vec Lx = polish ? w.Lxp : w.Lx, Dinv = polish ? w.Dinvp : w.Dinv;
     for (int k = 0; k < N; k++) bp[k] = b[S.perm[k]];
     for (int i = 0; i < N; i++) {
         const double val = bp[i];
-        for (int p = S.Lp[i]; p < S.Lp[i + 1]; p++) bp[S.Li[p]] -= Lx[p] * val;
+        int p = S.Lp[i];
+        const int p1 = S.Lp[i + 1];
+        for (; p + 4 <= p1; p += 4) {
+            const int r0 = S.Li[p], r1 = S.Li[p + 1], r2 = S.Li[p + 2], r3 = S.Li[p + 3];
+            const double l0 = Lx[p], l1 = Lx[p + 1], l2 = Lx[p + 2], l3 = Lx[p + 3];
+            double a0 = bp[r0], a1 = bp[r1], a2 = bp[r2], a3 = bp[r3];
+            a0 -= l0 * val; a1 -= l1 * val; a2 -= l2 * val; a3 -= l3 * val;
+            bp[r0] = a0; bp[r1] = a1; bp[r2] = a2; bp[r3] = a3;
+        }
+        for (; p < p1; p++) bp[S.Li[p]] -= Lx[p] * val;
     }
     for (int i = 0; i < N; i++) bp[i] *= Dinv[i];
     for (int i = N - 1; i >= 0; i--) {
@@ -429,8 +450,7 @@ LCQ_DEV void polish(const SymDev& S, const lcqp_cuda_options& o, const Work& w, 
     kkt_factor(S, w, st, 1, sig, del);
     if (st.factor_bad) { st.factor_bad = 0; return; }   // polishing failed (:262-270); the ADMM factor is untouched
     // rhs_red = [-q; l_low; u_upp] (:112-128) in xt; solve, then iterative refinement against the unregularised K (:141-197)
-    const Vec sol = w.xt, rhs = w.bp;   // (bp is the solve's scratch: the refinement rhs is rebuilt into tn/tm first)
-    (void)rhs;
+    const Vec sol = w.xt;
     for (int j = 0; j < n; j++) sol[j] = -w.q[j];
     for (int i = 0; i < m; i++) sol[n + i] = (w.act[i] < 0.0) ? w.l[i] : (w.act[i] > 0.0 ? w.u[i] : 0.0);
     kkt_solve(S, w, sol, 1);
@@ -449,7 +469,7 @@ LCQ_DEV void polish(const SymDev& S, const lcqp_cuda_options& o, const Work& w, 
             for (int p = S.Ap[j]; p < S.Ap[j + 1]; p++) w.tm1[S.Ai[p]] += w.Ax[p] * xj;
         }
         for (int i = 0; i < m; i++) r[n + i] = (w.act[i] < 0.0) ? (w.l[i] - w.tm1[i]) : (w.act[i] > 0.0 ? (w.u[i] - w.tm1[i]) : 0.0);
-        // (w3 is the factorisation's scratch, free here; the solve uses bp)
+        // (the factorisation and the solves use their own scratch, w.sm)
         kkt_solve(S, w, r, 1);
         for (int k = 0; k < N; k++) sol[k] += r[k];
     }

@@ -42,8 +42,7 @@ namespace pas {
 // qpOASES constants / default options (Constants.hpp:50-61, Options.cpp:91-146)
 constexpr double qEPS = 2.221e-16;
 constexpr double qINFTY = 1.0e20;
-constexpr double kTermTol = 5.0e6 * qEPS;        // terminationTolerance
-constexpr double kBoundTol = 1.0e6 * qEPS;       // boundTolerance
+// terminationTolerance (5e6 EPS) and boundTolerance (1e6 EPS) come from the options (qpoases_*): Options::setqpOASESOptions
 constexpr double kBoundRelax = 1.0e4;            // boundRelaxation
 constexpr double kEpsNum = -1.0e3 * qEPS;        // epsNum
 constexpr double kEpsDen = 1.0e3 * qEPS;         // epsDen
@@ -1033,7 +1032,7 @@ LCQ_DEVN int pas_homotopy(PQP& s)
         if (LCQ_TID == 0 && tau > 0.0) s.phi *= (1.0 - tau);
         hl = block_max(hl, w.sc);
         hl = fmax(hl, s.phi * s.len0);
-        if (hl <= kTermTol) { LCQ_PROF(w.sc, 14); return QP_OK; }
+        if (hl <= s.o->qpoases_terminationTolerance) { LCQ_PROF(w.sc, 14); return QP_OK; }
         if (LCQ_TID == 0) s.nwsr++;
         LCQ_SYNC();
         // change the working set (QProblem.cpp:5284-5365)
@@ -1167,7 +1166,7 @@ LCQ_DEVN int pas_hotstart(PQP& s, const RawOps& ro)
             if (far >= qINFTY) break;
             far_bounds(s, far);
         } else if (rc == QP_OK) {
-            const double tol = far / kFarGrow * kBoundTol;
+            const double tol = far / kFarGrow * s.o->qpoases_boundTolerance;
             int nact = 0;
             LCQ_LOOP for (int i = LCQ_TID; i < mI; i += LCQ_NT) {
                 double lo, up;
@@ -1215,8 +1214,8 @@ LCQ_DEVN int pas_init(PQP& s, const RawOps& ro, const double* x0, const double* 
         int aux = ST_INACTIVE;
         if (have_y) aux = (yi > qEPS) ? ST_LOWER : ((yi < -qEPS) ? ST_UPPER : ST_INACTIVE);
         else if (x0) {
-            if (zi - lo <= kBoundTol) aux = ST_LOWER;
-            else if (up - zi <= kBoundTol) aux = ST_UPPER;
+            if (zi - lo <= s.o->qpoases_boundTolerance) aux = ST_LOWER;
+            else if (up - zi <= s.o->qpoases_boundTolerance) aux = ST_UPPER;
         } else aux = (r >= d.mA) ? ST_LOWER : ST_INACTIVE;   // initialStatusBounds = ST_LOWER
         w.z[i] = zi; w.y[i] = yi; w.st[i] = ST_INACTIVE; w.stamp[i] = i;
         w.dz[i] = (double)aux;

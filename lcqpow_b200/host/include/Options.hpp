@@ -47,16 +47,22 @@ struct OSQPSettings {
     double alpha;      // relaxation (1.6)
     double delta;      // polish regularisation (1e-6)
     int max_iter;      // 4000
-    int check_termination;   // iterations between active-set probes (device default 10)
-    int polish_refine_iter;  // refinement passes per EQP solve
-    int polish;        // always on: the device solver returns the exact vertex
+    int check_termination;   // iterations between termination checks (25); exact-vertex solver: between active-set probes (10)
+    int polish_refine_iter;  // refinement passes (3)
+    int polish;        // 1 (LCQPow switches it on, Options.cpp:331)
     int verbose;
     double eps_prim_inf;
+    // read by the OSQP restatement only (Options::setOSQPADMM)
+    double eps_abs, eps_rel, eps_dual_inf, adaptive_rho_tolerance;
+    int scaling, adaptive_rho, adaptive_rho_interval;
 };
+// 0 / 0.0 means "keep the device default" (the defaults of constants.h:59-114 live in lcqp_cuda_default_options)
 inline void osqp_set_default_settings(OSQPSettings* s)
 {
     s->rho = 0.0; s->sigma = 0.0; s->alpha = 0.0; s->delta = 0.0; s->max_iter = 0; s->check_termination = 0;
     s->polish_refine_iter = 0; s->polish = 1; s->verbose = 0; s->eps_prim_inf = 0.0;
+    s->eps_abs = 0.0; s->eps_rel = 0.0; s->eps_dual_inf = 0.0; s->adaptive_rho_tolerance = 0.0;
+    s->scaling = -1; s->adaptive_rho = -1; s->adaptive_rho_interval = -1;
 }
 #endif
 
@@ -110,6 +116,11 @@ public:
     // instead of srand(time)/rand() (reference: LCQProblem.cpp:1016,1353-1362): runs are reproducible.
     unsigned long long getPerturbSeed() const;
     ReturnValue setPerturbSeed(unsigned long long seed);
+    // QPSolver::OSQP_SPARSE runs the exact-vertex solver behind the OSQP dual layout unless this is set: then the
+    // device runs the restatement of OSQP itself (ADMM + polish, lcqp_osqp.cuh), as the reference does
+    // (SubsolverOSQP.cpp:124-200).  Device loop only (no step tracking / iteration table).
+    bool getOSQPADMM() const;
+    ReturnValue setOSQPADMM(bool on);
     // CUDA device ordinal used by LCQProblem / SubsolverCUDA
     int getDevice() const;
     ReturnValue setDevice(int dev);
@@ -136,6 +147,7 @@ protected:
     OSQPSettings* OSQP_opts = nullptr;
     unsigned long long perturbSeed;
     int device;
+    bool osqpADMM = false;
 };
 
 }  // namespace LCQPow

@@ -255,7 +255,8 @@ ReturnValue LCQProblem::runSolver()
     xk.assign((size_t)nV, 0.0);
     if (has_x0) xk = x0;
     yk.assign((size_t)nDuals, 0.0);
-    const bool hostLoop = (options.getPrintLevel() != NONE) || options.getStoreSteps();
+    // (the OSQP restatement exists on the device only: no plug-in door, hence no host loop)
+    const bool hostLoop = ((options.getPrintLevel() != NONE) || options.getStoreSteps()) && !(osqpLayout && options.getOSQPADMM());
     const ReturnValue ret = hostLoop ? runHostLoop() : runDeviceLoop();
     if (ret != SUCCESSFUL_RETURN) return err(ret);
     return SUCCESSFUL_RETURN;

@@ -40,6 +40,7 @@ void Options::copy(const Options& rhs)
     printLevel = rhs.printLevel;
     qpOASES_opts = rhs.qpOASES_opts;
     perturbSeed = rhs.perturbSeed;
+    osqpADMM = rhs.osqpADMM;
     device = rhs.device;
     setOSQPOptions(rhs.OSQP_opts);
 }
@@ -68,6 +69,7 @@ void Options::setToDefault()
     def.polish = 1;
     setOSQPOptions(&def);
     perturbSeed = 1;
+    osqpADMM = false;
     device = 0;
 }
 
@@ -182,6 +184,9 @@ ReturnValue Options::setOSQPOptions(OSQPSettings* _options)
 
 OSQPSettings* Options::getOSQPOptions() { return OSQP_opts; }
 
+bool Options::getOSQPADMM() const { return osqpADMM; }
+ReturnValue Options::setOSQPADMM(bool on) { osqpADMM = on; return SUCCESSFUL_RETURN; }
+
 unsigned long long Options::getPerturbSeed() const { return perturbSeed; }
 ReturnValue Options::setPerturbSeed(unsigned long long seed) { perturbSeed = seed; return SUCCESSFUL_RETURN; }
 
@@ -219,13 +224,34 @@ void Options::toCuda(lcqp_cuda_options& o) const
         if (s.max_iter > 0) o.qp_max_iter = s.max_iter;
         if (s.check_termination > 0) o.qp_check_interval = s.check_termination;
         if (s.polish_refine_iter > 0) o.qp_refine_iter = s.polish_refine_iter < 2 ? 2 : s.polish_refine_iter;
+        // the OSQP restatement reads the settings under their own names
+        if (s.rho > 0) o.osqp_rho = s.rho;
+        if (s.sigma > 0) o.osqp_sigma = s.sigma;
+        if (s.alpha > 0 && s.alpha < 2) o.osqp_alpha = s.alpha;
+        if (s.delta > 0) o.osqp_delta = s.delta;
+        if (s.max_iter > 0) o.osqp_max_iter = s.max_iter;
+        if (s.check_termination > 0) o.osqp_check_termination = s.check_termination;
+        if (s.polish_refine_iter > 0) o.osqp_polish_refine_iter = s.polish_refine_iter;
+        o.osqp_polish = s.polish ? 1 : 0;
+        if (s.eps_prim_inf > 0) o.osqp_eps_prim_inf = s.eps_prim_inf;
+        if (s.eps_abs > 0) o.osqp_eps_abs = s.eps_abs;
+        if (s.eps_rel > 0) o.osqp_eps_rel = s.eps_rel;
+        if (s.eps_dual_inf > 0) o.osqp_eps_dual_inf = s.eps_dual_inf;
+        if (s.adaptive_rho_tolerance >= 1) o.osqp_adaptive_rho_tolerance = s.adaptive_rho_tolerance;
+        if (s.scaling >= 0) o.osqp_scaling = s.scaling;
+        if (s.adaptive_rho >= 0) o.osqp_adaptive_rho = s.adaptive_rho;
+        if (s.adaptive_rho_interval >= 0) o.osqp_adaptive_rho_interval = s.adaptive_rho_interval;
     } else if (qpSolver != OSQP_SPARSE) {
         const qpOASES::Options& q = qpOASES_opts;
         if (q.terminationTolerance > 0) o.qp_dual_tol = q.terminationTolerance;
         if (q.boundTolerance > 0) o.qp_feas_tol = q.boundTolerance;
         if (q.enableRegularisation && q.epsRegularisation > 0) o.qp_delta = q.epsRegularisation;
         if (q.numRefinementSteps > 0) o.qp_refine_iter = q.numRefinementSteps < 2 ? 2 : q.numRefinementSteps;
+        // the parametric active-set solver (positive definite reduced Hessians) reads qpOASES' own two tolerances
+        if (q.terminationTolerance > 0) o.qpoases_terminationTolerance = q.terminationTolerance;
+        if (q.boundTolerance > 0) o.qpoases_boundTolerance = q.boundTolerance;
     }
+    o.osqp_admm = (qpSolver == OSQP_SPARSE && osqpADMM) ? 1 : 0;
 }
 
 }  // namespace LCQPow

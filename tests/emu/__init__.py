@@ -33,7 +33,8 @@ class EmuOptions(C.Structure):
         ("osqp_eps_abs", C.c_double), ("osqp_eps_rel", C.c_double), ("osqp_eps_prim_inf", C.c_double), ("osqp_eps_dual_inf", C.c_double),
         ("osqp_adaptive_rho_tolerance", C.c_double),
         ("osqp_max_iter", C.c_int), ("osqp_check_termination", C.c_int), ("osqp_scaling", C.c_int), ("osqp_adaptive_rho", C.c_int),
-        ("osqp_adaptive_rho_interval", C.c_int), ("osqp_polish", C.c_int), ("osqp_polish_refine_iter", C.c_int), ("osqp_reserved", C.c_int)]
+        ("osqp_adaptive_rho_interval", C.c_int), ("osqp_polish", C.c_int), ("osqp_polish_refine_iter", C.c_int), ("osqp_reserved", C.c_int),
+        ("qpoases_terminationTolerance", C.c_double), ("qpoases_boundTolerance", C.c_double)]
 
 
 class EmuLib(pyref._Lib):

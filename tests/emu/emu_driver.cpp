@@ -330,4 +330,6 @@ extern "C" void lcqp_emu_default_options(lcqp_cuda_options* o)
     o->osqp_max_iter = 4000; o->osqp_check_termination = 25; o->osqp_scaling = 10;
     o->osqp_adaptive_rho = 1; o->osqp_adaptive_rho_interval = 0; o->osqp_polish = 1; o->osqp_polish_refine_iter = 3;
     o->osqp_reserved = 0;
+    o->qpoases_terminationTolerance = 5.0e6 * 2.221e-16;   // qpOASES Options.cpp:115
+    o->qpoases_boundTolerance = 1.0e6 * 2.221e-16;         // :116
 }

@@ -30,7 +30,7 @@ def test_header_symbols_are_exported():
 
 def test_struct_layouts_match_header():
     import lcqpow_b200 as L
-    assert C.sizeof(L.api.CudaOptions) == 6 * 8 + 6 * 4 + 6 * 8 + 4 * 4 + 8 + 9 * 8 + 8 * 4   # ABI 2: + the OSQPSettings block
+    assert C.sizeof(L.api.CudaOptions) == 6 * 8 + 6 * 4 + 6 * 8 + 4 * 4 + 8 + 9 * 8 + 8 * 4 + 2 * 8   # ABI 2: + the OSQPSettings block + two qpOASES tolerances
     assert L.api.STATS_DTYPE.itemsize == 8 * 4 + 2 * 8
 
 
