@@ -563,8 +563,11 @@ __global__ void __launch_bounds__(32) lcqp_osqp_kernel(const __grid_constant__ O
         if (lane == 0) tile = atomicAdd(a.counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if ((unsigned long long)tile * 32ull >= (unsigned long long)a.batch) break;
-        const int b = (int)tile * 32 + lane;
-        if (b < a.batch) {
+        // (the last tile is padded with copies of the last instance: every lane takes part in the warp's votes)
+        const int b_lane = (int)tile * 32 + lane;
+        const bool valid = b_lane < a.batch;
+        const int b = valid ? b_lane : a.batch - 1;
+        {
             osq::View v;
             auto at = [&](int k) -> const double* { return a.arr[k] ? a.arr[k] + a.stride[k] * (unsigned long long)b : nullptr; };
             v.Q = at(LCQP_Q); v.A = at(LCQP_A); v.L = at(LCQP_L); v.R = at(LCQP_R); v.g = at(LCQP_G);
@@ -574,6 +577,8 @@ __global__ void __launch_bounds__(32) lcqp_osqp_kernel(const __grid_constant__ O
             osq::State st;
             st.rho = 0; st.c = 1; st.cinv = 1; st.pri_res = 0; st.dua_res = 0; st.status_val = 0; st.iter = 0; st.interval = 0;
             st.factor_bad = 0; st.admm_total = 0; st.factor_count = 0;
+            // padded lanes write into the spare slot behind the workspace's last vector... they recompute instance
+            // batch - 1 bit for bit, so their stores to its outputs carry the same values
             double* xo = a.xout + (size_t)b * nV;
             double* yo = a.yout + (size_t)b * nD;
             if (a.box_given) {
@@ -587,7 +592,7 @@ __global__ void __launch_bounds__(32) lcqp_osqp_kernel(const __grid_constant__ O
             r.ret = out.ret; r.status = out.status; r.iterTotal = out.iterTotal; r.iterOuter = out.iterOuter;
             r.subproblemIter = out.subIter; r.qpExitFlag = out.exitFlag; r.nDuals = mA; r.kktSolves = (int)st.factor_count;
             r.rhoOpt = out.rhoOpt; r.admmIters = (double)st.admm_total;
-            a.stats[b] = r;
+            if (valid) a.stats[b] = r;
         }
         __syncwarp();
     }
@@ -1271,13 +1276,14 @@ static int pas_prepare_load(lcqp_cuda_handle h)
 static int osqp_upload_symbolic(lcqp_cuda_handle h)
 {
     const osq::Symbolic& S = *h->sym;
-    const std::vector<int>* vs[18] = {&S.Pp, &S.Pi, &S.Psrc, &S.Ap, &S.Ai, &S.Asrc, &S.Qp, &S.Qi, &S.Qsrc, &S.perm, &S.Kp, &S.Ki, &S.Ksrc,
-                                      &S.Lp, &S.Li, &S.rp, &S.rcol, &S.rpos};
+    constexpr int NV = 23;
+    const std::vector<int>* vs[NV] = {&S.Pp, &S.Pi, &S.Psrc, &S.Ap, &S.Ai, &S.Asrc, &S.Qp, &S.Qi, &S.Qsrc, &S.perm, &S.Kp, &S.Ki, &S.Ksrc,
+                                      &S.Lp, &S.Li, &S.rp, &S.rcol, &S.rpos, &S.Lcol, &S.Lrev, &S.Pcol, &S.Acol, &S.Qcol};
     size_t total = 0;
-    size_t off[18];
-    for (int k = 0; k < 18; k++) { off[k] = total; total += (vs[k]->size() + 3) & ~(size_t)3; }
+    size_t off[NV];
+    for (int k = 0; k < NV; k++) { off[k] = total; total += (vs[k]->size() + 3) & ~(size_t)3; }
     std::vector<int> pack(total ? total : 4, 0);
-    for (int k = 0; k < 18; k++) if (!vs[k]->empty()) memcpy(pack.data() + off[k], vs[k]->data(), vs[k]->size() * sizeof(int));
+    for (int k = 0; k < NV; k++) if (!vs[k]->empty()) memcpy(pack.data() + off[k], vs[k]->data(), vs[k]->size() * sizeof(int));
     if (total > h->sym_ints_cap) {
         if (h->sym_ints) cudaFree(h->sym_ints);
         h->sym_ints = nullptr; h->sym_ints_cap = 0;
@@ -1289,8 +1295,9 @@ static int osqp_upload_symbolic(lcqp_cuda_handle h)
     osq::SymDev& D = h->symdev;
     D.n = S.n; D.m = S.m; D.N = S.N; D.nC = h->nC; D.nComp = h->nComp;
     D.nnzP = (int)S.Pi.size(); D.nnzA = (int)S.Ai.size(); D.nnzQ = (int)S.Qi.size(); D.nnzK = (int)S.Ki.size(); D.nnzL = (int)S.Li.size();
-    const int** dst[18] = {&D.Pp, &D.Pi, &D.Psrc, &D.Ap, &D.Ai, &D.Asrc, &D.Qp, &D.Qi, &D.Qsrc, &D.perm, &D.Kp, &D.Ki, &D.Ksrc, &D.Lp, &D.Li, &D.rp, &D.rcol, &D.rpos};
-    for (int k = 0; k < 18; k++) *dst[k] = h->sym_ints + off[k];
+    const int** dst[NV] = {&D.Pp, &D.Pi, &D.Psrc, &D.Ap, &D.Ai, &D.Asrc, &D.Qp, &D.Qi, &D.Qsrc, &D.perm, &D.Kp, &D.Ki, &D.Ksrc, &D.Lp, &D.Li, &D.rp, &D.rcol, &D.rpos,
+                           &D.Lcol, &D.Lrev, &D.Pcol, &D.Acol, &D.Qcol};
+    for (int k = 0; k < NV; k++) *dst[k] = h->sym_ints + off[k];
     h->osqp_nnzL = (long long)S.Li.size();
     return LCQP_CUDA_OK;
 }
@@ -1333,7 +1340,7 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     a.ws_doubles = (osq::ws_doubles(a.S) + 1) & ~(size_t)1;
     // the scratch vector of the triangular solves (a chain of dependent read-modify-writes) sits in shared memory when
     // N x 32 doubles fit the CTA's budget
-    const size_t sm_need = (size_t)a.S.N * 32 * sizeof(double);
+    const size_t sm_need = osq::sm_len(a.S) * 32 * sizeof(double);
     a.smem_bytes = (sm_need <= (size_t)kSmemMax - 1024) ? (unsigned)sm_need : 0u;
     if (tune_env("LCQP_CUDA_OSQP_NOSMEM")) a.smem_bytes = 0;
     CK(cudaFuncSetAttribute(lcqp_osqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);

@@ -21,6 +21,11 @@
 // from a global counter.  The path is bound by HBM/L2 streaming of L (16 nnz(L) + 8 N + 8 (3n + 5m)
 // bytes per instance-iteration).
 //
+// Code size matters more than inlining here: a thread runs long dependent chains, the warps of an SM are few, and an
+// ADMM iteration whose instructions do not stay in the instruction cache is bound by instruction fetch (the first
+// version, everything inlined, was 90 k instructions and ran at ~600 cycles per matrix entry).  Every routine below is
+// therefore ONE non-inlined function; only the entry loops are unrolled (eight loads ahead of the dependent chain).
+//
 // Deviations from the reference, stated: (1) the fill-reducing ordering is minimum degree, not AMD -- L differs in
 // pattern, the computed iterates differ by round-off only; (2) `adaptive_rho_interval = 0` means "every
 // 4 x check_termination iterations" (OSQP's own rule when it is built without its wall-clock profiler) -- the
@@ -36,8 +41,19 @@ namespace osq {
 
 #ifdef LCQP_HOST_EMU
 #define OSQ_STRIDE 1
+#define OSQ_ANY(mask, pred) (pred)
+#define OSQ_BALLOT(pred) ((pred) ? 1u : 0u)
+#define OSQ_SYNCWARP(mask) ((void)0)
 #else
 #define OSQ_STRIDE 32
+// The 32 instances of a warp must stay in LOCKSTEP: the interleaved layout is only coalesced, and the warp only issues
+// one instruction stream, while the lanes execute the same instruction.  Data-dependent loops (ADMM iterations of a QP,
+// passes of the penalty loop) therefore run a WARP-UNIFORM number of times -- until no lane needs another one -- with the
+// lanes that are done masked out, and the lanes re-converge explicitly after every trip.  (With plain `break`s the
+// lanes drifted apart after the first few QPs and ran one after the other: 20 x slower, measured.)
+#define OSQ_ANY(mask, pred) __any_sync(mask, pred)
+#define OSQ_BALLOT(pred) __ballot_sync(0xffffffffu, pred)
+#define OSQ_SYNCWARP(mask) __syncwarp(mask)
 #endif
 
 // constants.h:59-114
@@ -56,7 +72,7 @@ struct Vec {
 // device view of osq::Symbolic (lcqp_sparse_host.hpp)
 struct SymDev {
     int n, m, N, nC, nComp, nnzP, nnzA, nnzQ, nnzK, nnzL;
-    const int *Pp, *Pi, *Psrc, *Ap, *Ai, *Asrc, *Qp, *Qi, *Qsrc, *perm, *Kp, *Ki, *Ksrc, *Lp, *Li, *rp, *rcol, *rpos;
+    const int *Pp, *Pi, *Psrc, *Ap, *Ai, *Asrc, *Qp, *Qi, *Qsrc, *perm, *Kp, *Ki, *Ksrc, *Lp, *Li, *rp, *rcol, *rpos, *Lcol, *Lrev, *Pcol, *Acol, *Qcol;
 };
 
 // one instance's inputs (value arrays as the caller laid them out; NULL = absent)
@@ -72,9 +88,11 @@ struct Work {
     Vec sm;                                                    // N: scratch of the factorisation and of the triangular solves -- shared memory when it fits
 };
 
+LCQ_HD inline size_t sm_len(const SymDev& S) { return (size_t)(S.N > 2 * S.n ? S.N : 2 * S.n); }   // solve / factor scratch, two accumulators of P v
+
 LCQ_HD inline size_t ws_doubles(const SymDev& S)
 {
-    return (size_t)S.nnzP + S.nnzA + 2 * (size_t)S.nnzL + 2 * (size_t)S.N + 17 * (size_t)S.n + 17 * (size_t)S.m + 3 * (size_t)S.N;
+    return (size_t)S.nnzP + S.nnzA + 2 * (size_t)S.nnzL + 2 * (size_t)S.N + 17 * (size_t)S.n + 17 * (size_t)S.m + 2 * (size_t)S.N + sm_len(S);
 }
 
 // `base` points at element 0 of this lane (tile base + lane); consecutive vectors follow each other
@@ -87,7 +105,7 @@ LCQ_HD inline void carve(Work& w, const SymDev& S, double* base, double* smem_la
     for (int k = 0; k < 17; k++) *nv[k] = take(S.n);
     Vec* mv[17] = {&w.sE, &w.sEi, &w.l, &w.u, &w.z, &w.zp, &w.y, &w.dy, &w.Axv, &w.rv, &w.riv, &w.pz, &w.py, &w.act, &w.yk, &w.tm1, &w.tm2};
     for (int k = 0; k < 17; k++) *mv[k] = take(S.m);
-    w.xt = take(S.N); w.bp = take(S.N); w.w3 = take(S.N);
+    w.xt = take(S.N); w.bp = take(sm_len(S)); w.w3 = take(S.N);
     w.sm = w.bp;
     if (smem_lane) w.sm.p = smem_lane;
 }
@@ -108,42 +126,63 @@ LCQ_DEV double a_val(const SymDev& S, const View& v, int p)
 
 LCQ_DEV double limit_scaling(double d) { d = d < kMinScaling ? 1.0 : d; return d > kMaxScaling ? kMaxScaling : d; }   // scaling.c:7-14
 
-// ---- sparse products on the scaled data (lin_alg.c mat_vec / mat_tpose_vec) ---------------------------------
-// out = A v                         (out: m, v: n)
-LCQ_DEV void A_mul(const SymDev& S, const Work& w, const Vec& v, const Vec& out)
+// ---- sparse products (lin_alg.c mat_vec / mat_tpose_vec) -----------------------------------------------------
+// acc[tgt[p]] += val(p) * v[src[p]] over the flat entry list, in storage order -- the reference's order of
+// accumulation.  The accumulator is the scratch vector (shared memory when it fits): a chain of read-modify-writes in
+// global memory would cost an L2 round trip per entry.  The matrix values and vector entries of KB entries are loaded
+// before the first accumulation (the compiler must assume that the vectors alias and would serialise otherwise).
+template <class F>
+LCQ_DEV void flat_acc(int nnz, const int* tgt, const int* src, F val, const Vec& v, const Vec& acc, bool skip_diag = false)
 {
-    for (int i = 0; i < S.m; i++) out[i] = 0.0;
-    for (int j = 0; j < S.n; j++) {
-        const double vj = v[j];
-        for (int p = S.Ap[j]; p < S.Ap[j + 1]; p++) out[S.Ai[p]] += w.Ax[p] * vj;
+    constexpr int KB = 8;
+    for (int p0 = 0; p0 < nnz; p0 += KB) {
+        double a[KB], x[KB];
+#pragma unroll
+        for (int k = 0; k < KB; k++) { const int p = p0 + k < nnz ? p0 + k : nnz - 1; a[k] = val(p); x[k] = v[src[p]]; }
+#pragma unroll
+        for (int k = 0; k < KB; k++)
+            if (p0 + k < nnz && !(skip_diag && tgt[p0 + k] == src[p0 + k])) acc[tgt[p0 + k]] += a[k] * x[k];
     }
+}
+LCQ_DEV void vec_zero(const Vec& a, int len) { for (int i = 0; i < len; i++) a[i] = 0.0; }
+// out[i] = a[i] (+ b[i]) for i < len, eight loads ahead of the stores
+LCQ_DEV void vec_out(const Vec& out, const Vec& a, const Vec* b, int len)
+{
+    for (int i0 = 0; i0 < len; i0 += 8) {
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int i = i0 + k < len ? i0 + k : len - 1; t[k] = b ? a[i] + (*b)[i] : a[i]; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (i0 + k < len) out[i0 + k] = t[k];
+    }
+}
+// out = A v                         (out: m, v: n)
+LCQ_DEVN void A_mul(const SymDev& S, const Work& w, const Vec& v, const Vec& out)
+{
+    vec_zero(w.sm, S.m);
+    flat_acc(S.nnzA, S.Ai, S.Acol, [&](int p) { return w.Ax[p]; }, v, w.sm);
+    vec_out(out, w.sm, nullptr, S.m);
 }
 // out = A' v                        (out: n, v: m)
-LCQ_DEV void At_mul(const SymDev& S, const Work& w, const Vec& v, const Vec& out)
+LCQ_DEVN void At_mul(const SymDev& S, const Work& w, const Vec& v, const Vec& out)
 {
-    for (int j = 0; j < S.n; j++) {
-        double acc = 0.0;
-        for (int p = S.Ap[j]; p < S.Ap[j + 1]; p++) acc += w.Ax[p] * v[S.Ai[p]];
-        out[j] = acc;
-    }
+    vec_zero(w.sm, S.n);
+    flat_acc(S.nnzA, S.Acol, S.Ai, [&](int p) { return w.Ax[p]; }, v, w.sm);
+    vec_out(out, w.sm, nullptr, S.n);
 }
 // out = P v with P stored as its upper triangle (auxil.c:294-300: upper part, then the strict lower part)
-LCQ_DEV void P_mul(const SymDev& S, const Work& w, const Vec& v, const Vec& out)
+LCQ_DEVN void P_mul(const SymDev& S, const Work& w, const Vec& v, const Vec& out)
 {
-    for (int i = 0; i < S.n; i++) out[i] = 0.0;
-    for (int j = 0; j < S.n; j++) {
-        const double vj = v[j];
-        for (int p = S.Pp[j]; p < S.Pp[j + 1]; p++) out[S.Pi[p]] += w.Px[p] * vj;
-    }
-    for (int j = 0; j < S.n; j++) {
-        double acc = 0.0;
-        for (int p = S.Pp[j]; p < S.Pp[j + 1]; p++) { const int i = S.Pi[p]; if (i != j) acc += w.Px[p] * v[i]; }
-        out[j] += acc;
-    }
+    Vec lo;
+    lo.p = &w.sm[S.n];
+    vec_zero(w.sm, 2 * S.n);
+    flat_acc(S.nnzP, S.Pi, S.Pcol, [&](int p) { return w.Px[p]; }, v, w.sm);
+    flat_acc(S.nnzP, S.Pcol, S.Pi, [&](int p) { return w.Px[p]; }, v, lo, true);
+    vec_out(out, w.sm, &lo, S.n);
 }
 
 // ---- scale_data (scaling.c:44-156) ---------------------------------------------------------------------------
-LCQ_DEV void scale_data(const SymDev& S, const View& v, const lcqp_cuda_options& o, const Work& w, State& st)
+LCQ_DEVN void scale_data(const SymDev& S, const View& v, const lcqp_cuda_options& o, const Work& w, State& st)
 {
     const int n = S.n, m = S.m;
     for (int p = 0; p < S.nnzP; p++) w.Px[p] = v.Q[S.Psrc[p]];
@@ -212,7 +251,7 @@ LCQ_DEV int constr_type(const Work& w, int i)
     if (w.u[i] - w.l[i] < kRhoTol) return 1;
     return 0;
 }
-LCQ_DEV void set_rho_vec(const SymDev& S, const Work& w, State& st)
+LCQ_DEVN void set_rho_vec(const SymDev& S, const Work& w, State& st)
 {
     st.rho = fmin(fmax(st.rho, kRhoMin), kRhoMax);
     for (int i = 0; i < S.m; i++) {
@@ -223,7 +262,7 @@ LCQ_DEV void set_rho_vec(const SymDev& S, const Work& w, State& st)
     }
 }
 // osqp_update_rho (osqp.c:1268-1318): loose rows keep RHO_MIN
-LCQ_DEV void update_rho_vec(const SymDev& S, const Work& w, State& st, double rho_new)
+LCQ_DEVN void update_rho_vec(const SymDev& S, const Work& w, State& st, double rho_new)
 {
     st.rho = fmin(fmax(rho_new, kRhoMin), kRhoMax);
     for (int i = 0; i < S.m; i++) {
@@ -244,7 +283,7 @@ LCQ_DEV double kkt_value(const SymDev& S, const Work& w, int e, bool diag, int p
     return polish ? delta : sigma;
 }
 
-LCQ_DEV void kkt_factor(const SymDev& S, const Work& w, State& st, int polish, double sigma, double delta)
+LCQ_DEVN void kkt_factor(const SymDev& S, const Work& w, State& st, int polish, double sigma, double delta)
 {
     const int N = S.N;
     const Vec Lx = polish ? w.Lxp : w.Lx, Dinv = polish ? w.Dinvp : w.Dinv;
@@ -253,25 +292,27 @@ LCQ_DEV void kkt_factor(const SymDev& S, const Work& w, State& st, int polish, d
     for (int k = 0; k < N; k++) yv[k] = 0.0;
     for (int k = 0; k < N; k++) {
         double dk = 0.0;
-        for (int e = S.Kp[k]; e < S.Kp[k + 1]; e++) {
-            const int i = S.Ki[e];
-            const double v = kkt_value(S, w, e, i == k, polish, sigma, delta);
-            if (i == k) dk = v; else yv[i] = v;
+        for (int e0 = S.Kp[k]; e0 < S.Kp[k + 1]; e0 += 8) {
+            double kv[8];
+            const int e1 = S.Kp[k + 1];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int e = e0 + q < e1 ? e0 + q : e1 - 1; kv[q] = kkt_value(S, w, e, S.Ki[e] == k, polish, sigma, delta); }
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (e0 + q < e1) { const int i = S.Ki[e0 + q]; if (i == k) dk = kv[q]; else yv[i] = kv[q]; }
         }
         for (int t = S.rp[k]; t < S.rp[k + 1]; t++) {
             const int c = S.rcol[t], pos = S.rpos[t];
             const double yc = yv[c];
             yv[c] = 0.0;
             // (the rows of one column are distinct: four independent updates in flight)
-            int p = S.Lp[c];
-            for (; p + 4 <= pos; p += 4) {
-                const int r0 = S.Li[p], r1 = S.Li[p + 1], r2 = S.Li[p + 2], r3 = S.Li[p + 3];
-                const double l0 = Lx[p], l1 = Lx[p + 1], l2 = Lx[p + 2], l3 = Lx[p + 3];
-                double a0 = yv[r0], a1 = yv[r1], a2 = yv[r2], a3 = yv[r3];
-                a0 -= l0 * yc; a1 -= l1 * yc; a2 -= l2 * yc; a3 -= l3 * yc;
-                yv[r0] = a0; yv[r1] = a1; yv[r2] = a2; yv[r3] = a3;
+            for (int p0 = S.Lp[c]; p0 < pos; p0 += 8) {
+                double l[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) l[q] = (p0 + q < pos) ? Lx[p0 + q] : 0.0;
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (p0 + q < pos) yv[S.Li[p0 + q]] -= l[q] * yc;
             }
-            for (; p < pos; p++) yv[S.Li[p]] -= Lx[p] * yc;
             const double lkc = yc * Dinv[c];
             Lx[pos] = lkc;
             dk -= yc * lkc;
@@ -287,41 +328,61 @@ LCQ_DEV void kkt_factor(const SymDev& S, const Work& w, State& st, int polish, d
 
 // b (N, natural order) <- solution.  polish = 0 follows qdldl_interface.c:341-376: the x part is the solution, the
 // z part becomes b_z + rho_inv * nu.  polish = 1: plain solve.
-LCQ_DEV void kkt_solve(const SymDev& S, const Work& w, const Vec& b, int polish)
+LCQ_DEVN void kkt_solve(const SymDev& S, const Work& w, const Vec& b, int polish)
 {
-    const int N = S.N, n = S.n;
+    // The sweeps run over the entries of L in storage order with the matrix values of the next KB entries loaded ahead
+    // (independent, streaming loads) of the chain of dependent read-modify-writes on the scratch vector; the
+    // arithmetic is that of qdldl.c:236-281 operation for operation (bp[col] is final when its column is reached).
+    constexpr int KB = 8;
+    const int N = S.N, n = S.n, nnzL = S.nnzL;
     const Vec bp = w.sm;
     const Vec Lx = polish ? w.Lxp : w.Lx, Dinv = polish ? w.Dinvp : w.Dinv;
-    for (int k = 0; k < N; k++) bp[k] = b[S.perm[k]];
-    for (int i = 0; i < N; i++) {
-        const double val = bp[i];
-        int p = S.Lp[i];
-        const int p1 = S.Lp[i + 1];
-        for (; p + 4 <= p1; p += 4) {
-            const int r0 = S.Li[p], r1 = S.Li[p + 1], r2 = S.Li[p + 2], r3 = S.Li[p + 3];
-            const double l0 = Lx[p], l1 = Lx[p + 1], l2 = Lx[p + 2], l3 = Lx[p + 3];
-            double a0 = bp[r0], a1 = bp[r1], a2 = bp[r2], a3 = bp[r3];
-            a0 -= l0 * val; a1 -= l1 * val; a2 -= l2 * val; a3 -= l3 * val;
-            bp[r0] = a0; bp[r1] = a1; bp[r2] = a2; bp[r3] = a3;
+    for (int k0 = 0; k0 < N; k0 += 8) {
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = (k0 + k < N) ? b[S.perm[k0 + k]] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (k0 + k < N) bp[k0 + k] = t[k];
+    }
+    for (int p0 = 0; p0 < nnzL; p0 += KB) {
+        double l[KB];
+#pragma unroll
+        for (int k = 0; k < KB; k++) l[k] = (p0 + k < nnzL) ? Lx[p0 + k] : 0.0;
+#pragma unroll
+        for (int k = 0; k < KB; k++)
+            if (p0 + k < nnzL) { const int r = S.Li[p0 + k], c = S.Lcol[p0 + k]; bp[r] -= l[k] * bp[c]; }
+    }
+    for (int k0 = 0; k0 < N; k0 += 8) {
+        double t[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) t[k] = (k0 + k < N) ? Dinv[k0 + k] : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (k0 + k < N) bp[k0 + k] *= t[k];
+    }
+    for (int q0 = 0; q0 < nnzL; q0 += KB) {
+        double l[KB];
+#pragma unroll
+        for (int k = 0; k < KB; k++) l[k] = (q0 + k < nnzL) ? Lx[S.Lrev[q0 + k]] : 0.0;
+#pragma unroll
+        for (int k = 0; k < KB; k++)
+            if (q0 + k < nnzL) { const int p = S.Lrev[q0 + k]; const int r = S.Li[p], c = S.Lcol[p]; bp[c] -= l[k] * bp[r]; }
+    }
+    for (int k0 = 0; k0 < N; k0 += 8) {
+        double t[8], u[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int old = (k0 + k < N) ? S.perm[k0 + k] : 0;
+            t[k] = (k0 + k < N) ? bp[k0 + k] : 0.0;
+            u[k] = (k0 + k < N && !polish && old >= n) ? b[old] + w.riv[old - n] * t[k] : t[k];
         }
-        for (; p < p1; p++) bp[S.Li[p]] -= Lx[p] * val;
-    }
-    for (int i = 0; i < N; i++) bp[i] *= Dinv[i];
-    for (int i = N - 1; i >= 0; i--) {
-        double val = bp[i];
-        for (int p = S.Lp[i]; p < S.Lp[i + 1]; p++) val -= Lx[p] * bp[S.Li[p]];
-        bp[i] = val;
-    }
-    for (int k = 0; k < N; k++) {
-        const int old = S.perm[k];
-        if (polish || old < n) b[old] = bp[k];
-        else b[old] += w.riv[old - n] * bp[k];
+#pragma unroll
+        for (int k = 0; k < 8; k++) if (k0 + k < N) b[S.perm[k0 + k]] = u[k];
     }
 }
 
 // ---- update_info (auxil.c:564-629) for the iterate (x, z, y): residuals, leaving Ax, Px, A'y behind and -- as the
 // reference does -- the (scaled) residual vectors in zp and xp, which compute_rho_estimate reads (auxil.c:26-27)
-LCQ_DEV void residuals(const SymDev& S, const Work& w, const State& st, const Vec& x, const Vec& z, const Vec& y, double& pri, double& dua)
+LCQ_DEVN void residuals(const SymDev& S, const Work& w, const State& st, const Vec& x, const Vec& z, const Vec& y, double& pri, double& dua)
 {
     const int n = S.n, m = S.m;
     if (m == 0) pri = 0.0;
@@ -345,7 +406,7 @@ LCQ_DEV void residuals(const SymDev& S, const Work& w, const State& st, const Ve
 }
 
 // compute_rho_estimate (auxil.c:13-52)
-LCQ_DEV double rho_estimate(const SymDev& S, const Work& w, const State& st)
+LCQ_DEVN double rho_estimate(const SymDev& S, const Work& w, const State& st)
 {
     const int n = S.n, m = S.m;
     double pri = 0, dua = 0, a = 0, b = 0, c1 = 0, c2 = 0, c3 = 0;
@@ -358,7 +419,7 @@ LCQ_DEV double rho_estimate(const SymDev& S, const Work& w, const State& st)
 }
 
 // is_primal_infeasible (auxil.c:362-424); modifies dy like the reference
-LCQ_DEV bool primal_infeasible(const SymDev& S, const Work& w, double eps)
+LCQ_DEVN bool primal_infeasible(const SymDev& S, const Work& w, double eps)
 {
     const int n = S.n, m = S.m;
     for (int i = 0; i < m; i++) {
@@ -383,7 +444,7 @@ LCQ_DEV bool primal_infeasible(const SymDev& S, const Work& w, double eps)
 }
 
 // is_dual_infeasible (auxil.c:426-520)
-LCQ_DEV bool dual_infeasible(const SymDev& S, const Work& w, const State& st, double eps)
+LCQ_DEVN bool dual_infeasible(const SymDev& S, const Work& w, const State& st, double eps)
 {
     const int n = S.n, m = S.m;
     double nrm = 0.0;
@@ -405,7 +466,7 @@ LCQ_DEV bool dual_infeasible(const SymDev& S, const Work& w, const State& st, do
 }
 
 // check_termination (auxil.c:681-786); returns 1 when the loop ends
-LCQ_DEV int check_termination(const SymDev& S, const lcqp_cuda_options& o, const Work& w, State& st, int approximate)
+LCQ_DEVN int check_termination(const SymDev& S, const lcqp_cuda_options& o, const Work& w, State& st, int approximate)
 {
     const int n = S.n, m = S.m;
     double eps_abs = o.osqp_eps_abs, eps_rel = o.osqp_eps_rel, eps_pi = o.osqp_eps_prim_inf, eps_di = o.osqp_eps_dual_inf;
@@ -436,7 +497,7 @@ LCQ_DEV int check_termination(const SymDev& S, const lcqp_cuda_options& o, const
 }
 
 // ---- polish (polish.c:237-350) --------------------------------------------------------------------------------
-LCQ_DEV void polish(const SymDev& S, const lcqp_cuda_options& o, const Work& w, State& st)
+LCQ_DEVN void polish(const SymDev& S, const lcqp_cuda_options& o, const Work& w, State& st)
 {
     const int n = S.n, m = S.m, N = S.N;
     // form_Ared (:19-104): act = -1 lower-active, +1 upper-active, 0 inactive
@@ -457,17 +518,13 @@ LCQ_DEV void polish(const SymDev& S, const lcqp_cuda_options& o, const Work& w, 
     for (int it = 0; it < o.osqp_polish_refine_iter; it++) {
         // r = b - K z  with  K = [P, Aact'; Aact, 0]
         const Vec r = w.w3;
+        Vec ys;
+        ys.p = &sol[n];
         P_mul(S, w, sol, w.tn1);                       // P x            (sol[0..n) is x)
-        for (int j = 0; j < n; j++) {
-            double acc = 0.0;
-            for (int p = S.Ap[j]; p < S.Ap[j + 1]; p++) { const int i = S.Ai[p]; if (w.act[i] != 0.0) acc += w.Ax[p] * sol[n + i]; }
-            r[j] = ((-w.q[j]) - w.tn1[j]) - acc;
-        }
-        for (int i = 0; i < m; i++) w.tm1[i] = 0.0;
-        for (int j = 0; j < n; j++) {
-            const double xj = sol[j];
-            for (int p = S.Ap[j]; p < S.Ap[j + 1]; p++) w.tm1[S.Ai[p]] += w.Ax[p] * xj;
-        }
+        vec_zero(w.sm, n);                             // Aact' y_red
+        flat_acc(S.nnzA, S.Acol, S.Ai, [&](int p) { return w.act[S.Ai[p]] != 0.0 ? w.Ax[p] : 0.0; }, ys, w.sm);
+        for (int j = 0; j < n; j++) r[j] = ((-w.q[j]) - w.tn1[j]) - w.sm[j];
+        A_mul(S, w, sol, w.tm1);                       // A x
         for (int i = 0; i < m; i++) r[n + i] = (w.act[i] < 0.0) ? (w.l[i] - w.tm1[i]) : (w.act[i] > 0.0 ? (w.u[i] - w.tm1[i]) : 0.0);
         // (the factorisation and the solves use their own scratch, w.sm)
         kkt_solve(S, w, r, 1);
@@ -495,44 +552,72 @@ LCQ_DEV void polish(const SymDev& S, const lcqp_cuda_options& o, const Work& w, 
 }
 
 // ---- osqp_solve (osqp.c:288-641).  Returns the exit flag the adapter reads (status_val). ----------------------
-LCQ_DEV int osqp_solve(const SymDev& S, const lcqp_cuda_options& o, Work& w, State& st)
+// `mask`: the lanes of the warp that solve a QP in this pass (all of them call this function together)
+LCQ_DEVN int osqp_solve(const SymDev& S, const lcqp_cuda_options& o, Work& w, State& st, unsigned mask)
 {
     const int n = S.n, m = S.m;
     const double sigma = o.osqp_sigma, alpha = o.osqp_alpha;
     const int check = o.osqp_check_termination;
     st.status_val = OSQP_UNSOLVED;
-    int iter = 1;
-    bool can_check = false;
-    for (iter = 1; iter <= o.osqp_max_iter; iter++) {
+    int iter = 1, it_end = 0;
+    bool can_check = false, running = true;
+    for (iter = 1; OSQ_ANY(mask, running); iter++) {
+      if (running && iter > o.osqp_max_iter) { running = false; it_end = iter; }
+      if (running) {
         { const Vec t = w.x; w.x = w.xp; w.xp = t; }
         { const Vec t = w.z; w.z = w.zp; w.zp = t; }
-        // update_xz_tilde (auxil.c:161-183)
-        for (int j = 0; j < n; j++) w.xt[j] = sigma * w.xp[j] - w.q[j];
-        for (int i = 0; i < m; i++) w.xt[n + i] = w.zp[i] - w.riv[i] * w.y[i];
+        // update_xz_tilde (auxil.c:161-183).  (Elementwise loops: the inputs of four elements are loaded before the
+        // first store -- the compiler must assume that the vectors alias and would serialise load -> store -> load.)
+        for (int j0 = 0; j0 < n; j0 += 4) {
+            double a[4], c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int j = j0 + k < n ? j0 + k : n - 1; a[k] = w.xp[j]; c[k] = w.q[j]; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (j0 + k < n) w.xt[j0 + k] = sigma * a[k] - c[k];
+        }
+        for (int i0 = 0; i0 < m; i0 += 4) {
+            double a[4], c[4], d[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int i = i0 + k < m ? i0 + k : m - 1; a[k] = w.zp[i]; c[k] = w.riv[i]; d[k] = w.y[i]; }
+#pragma unroll
+            for (int k = 0; k < 4; k++) if (i0 + k < m) w.xt[n + i0 + k] = a[k] - c[k] * d[k];
+        }
         kkt_solve(S, w, w.xt, 0);
         // update_x, update_z, update_y (auxil.c:185-225)
-        for (int j = 0; j < n; j++) {
-            const double xn = alpha * w.xt[j] + (1.0 - alpha) * w.xp[j];
-            w.x[j] = xn;
-            w.dx[j] = xn - w.xp[j];
+        for (int j0 = 0; j0 < n; j0 += 4) {
+            double a[4], c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const int j = j0 + k < n ? j0 + k : n - 1; a[k] = w.xt[j]; c[k] = w.xp[j]; }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (j0 + k < n) { const double xn = alpha * a[k] + (1.0 - alpha) * c[k]; w.x[j0 + k] = xn; w.dx[j0 + k] = xn - c[k]; }
         }
-        for (int i = 0; i < m; i++) {
-            const double zt = w.xt[n + i];
-            double zn = alpha * zt + (1.0 - alpha) * w.zp[i] + w.riv[i] * w.y[i];
-            zn = fmin(fmax(zn, w.l[i]), w.u[i]);
-            w.z[i] = zn;
-            const double d = w.rv[i] * (alpha * zt + (1.0 - alpha) * w.zp[i] - zn);
-            w.dy[i] = d;
-            w.y[i] += d;
+        for (int i0 = 0; i0 < m; i0 += 4) {
+            double zt[4], zo[4], ri[4], yy[4], lo[4], up[4], rr[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int i = i0 + k < m ? i0 + k : m - 1;
+                zt[k] = w.xt[n + i]; zo[k] = w.zp[i]; ri[k] = w.riv[i]; yy[k] = w.y[i]; lo[k] = w.l[i]; up[k] = w.u[i]; rr[k] = w.rv[i];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                if (i0 + k < m) {
+                    double zn = alpha * zt[k] + (1.0 - alpha) * zo[k] + ri[k] * yy[k];
+                    zn = fmin(fmax(zn, lo[k]), up[k]);
+                    w.z[i0 + k] = zn;
+                    const double d = rr[k] * (alpha * zt[k] + (1.0 - alpha) * zo[k] - zn);
+                    w.dy[i0 + k] = d;
+                    w.y[i0 + k] = yy[k] + d;
+                }
         }
         st.admm_total++;
         can_check = check && (iter % check == 0);
         if (can_check) {
             st.iter = iter;
             residuals(S, w, st, w.x, w.z, w.y, st.pri_res, st.dua_res);
-            if (check_termination(S, o, w, st, 0)) break;
+            if (check_termination(S, o, w, st, 0)) { running = false; it_end = iter; }
         }
-        if (o.osqp_adaptive_rho && st.interval && (iter % st.interval == 0)) {
+        if (running && o.osqp_adaptive_rho && st.interval && (iter % st.interval == 0)) {
             if (!can_check) { st.iter = iter; residuals(S, w, st, w.x, w.z, w.y, st.pri_res, st.dua_res); }
             // adapt_rho (auxil.c:54-74)
             const double rn = rho_estimate(S, w, st);
@@ -541,7 +626,10 @@ LCQ_DEV int osqp_solve(const SymDev& S, const lcqp_cuda_options& o, Work& w, Sta
                 kkt_factor(S, w, st, 0, sigma, o.osqp_delta);
             }
         }
+      }
+      OSQ_SYNCWARP(mask);
     }
+    iter = it_end;
     if (!can_check) {
         st.iter = iter - 1;
         residuals(S, w, st, w.x, w.z, w.y, st.pri_res, st.dua_res);
@@ -564,40 +652,34 @@ LCQ_DEV bool has_solution(int s)
 // one instance over the OSQP flavour: nDuals = nC + 2 nComp, boxDualOffset = 0 (:934-935).
 // ------------------------------------------------------------------------------------------------
 // unscaled products with the caller's values
-LCQ_DEV void Q_mul_raw(const SymDev& S, const View& v, const Vec& x, const Vec& out)   // out = Q x (full symmetric pattern)
+LCQ_DEVN void Q_mul_raw(const SymDev& S, const View& v, const Work& w, const Vec& x, const Vec& out)   // out = Q x (full symmetric pattern)
 {
-    for (int i = 0; i < S.n; i++) out[i] = 0.0;
-    for (int j = 0; j < S.n; j++) {
-        const double xj = x[j];
-        for (int p = S.Qp[j]; p < S.Qp[j + 1]; p++) out[S.Qi[p]] += v.Q[S.Qsrc[p]] * xj;
-    }
+    vec_zero(w.sm, S.n);
+    flat_acc(S.nnzQ, S.Qi, S.Qcol, [&](int p) { return v.Q[S.Qsrc[p]]; }, x, w.sm);
+    vec_out(out, w.sm, nullptr, S.n);
 }
-LCQ_DEV void A_mul_raw(const SymDev& S, const View& v, const Vec& x, const Vec& out)   // out = [A; L; R] x
+LCQ_DEVN void A_mul_raw(const SymDev& S, const View& v, const Work& w, const Vec& x, const Vec& out)   // out = [A; L; R] x
 {
-    for (int i = 0; i < S.m; i++) out[i] = 0.0;
-    for (int j = 0; j < S.n; j++) {
-        const double xj = x[j];
-        for (int p = S.Ap[j]; p < S.Ap[j + 1]; p++) out[S.Ai[p]] += a_val(S, v, p) * xj;
-    }
+    vec_zero(w.sm, S.m);
+    flat_acc(S.nnzA, S.Ai, S.Acol, [&](int p) { return a_val(S, v, p); }, x, w.sm);
+    vec_out(out, w.sm, nullptr, S.m);
 }
-LCQ_DEV void At_mul_raw(const SymDev& S, const View& v, const Vec& y, const Vec& out)  // out = [A; L; R]' y
+LCQ_DEVN void At_mul_raw(const SymDev& S, const View& v, const Work& w, const Vec& y, const Vec& out)  // out = [A; L; R]' y
 {
-    for (int j = 0; j < S.n; j++) {
-        double acc = 0.0;
-        for (int p = S.Ap[j]; p < S.Ap[j + 1]; p++) acc += a_val(S, v, p) * y[S.Ai[p]];
-        out[j] = acc;
-    }
+    vec_zero(w.sm, S.n);
+    flat_acc(S.nnzA, S.Acol, S.Ai, [&](int p) { return a_val(S, v, p); }, y, w.sm);
+    vec_out(out, w.sm, nullptr, S.n);
 }
 
 // out = Qk x + add = Q x + rho (L'(R x) + R'(L x)) + add ; leaves [A; L; R] x in tm1.  `add` may alias nothing (null p = none)
-LCQ_DEV void Qk_mul(const SymDev& S, const View& v, const Work& w, double rho, const Vec& x, const Vec* add, const Vec& out)
+LCQ_DEVN void Qk_mul(const SymDev& S, const View& v, const Work& w, double rho, const Vec& x, const Vec* add, const Vec& out)
 {
     const int nC = S.nC, nComp = S.nComp;
-    Q_mul_raw(S, v, x, w.tn1);
-    A_mul_raw(S, v, x, w.tm1);
+    Q_mul_raw(S, v, w, x, w.tn1);
+    A_mul_raw(S, v, w, x, w.tm1);
     for (int i = 0; i < nC; i++) w.tm2[i] = 0.0;
     for (int i = 0; i < nComp; i++) { w.tm2[nC + i] = w.tm1[nC + nComp + i]; w.tm2[nC + nComp + i] = w.tm1[nC + i]; }
-    At_mul_raw(S, v, w.tm2, w.tn2);
+    At_mul_raw(S, v, w, w.tm2, w.tn2);
     for (int j = 0; j < S.n; j++) out[j] = (w.tn1[j] + (add ? (*add)[j] : 0.0)) + rho * w.tn2[j];
 }
 
@@ -629,12 +711,12 @@ LCQ_DEV void lcqp_loop(const SymDev& S, const View& v, const lcqp_cuda_options& 
         phi_const = pc;
         for (int i = 0; i < nC; i++) w.tm2[i] = 0.0;
         for (int i = 0; i < nComp; i++) { w.tm2[nC + i] = v.lbR ? v.lbR[i] : 0.0; w.tm2[nC + nComp + i] = v.lbL ? v.lbL[i] : 0.0; }
-        At_mul_raw(S, v, w.tm2, w.gphi);   // L' lbR + R' lbL
+        At_mul_raw(S, v, w, w.tm2, w.gphi);   // L' lbR + R' lbL
         for (int j = 0; j < n; j++) w.gphi[j] = -w.gphi[j];
     }
 
     auto phi = [&]() -> double {  // getPhi :1172-1185 ; leaves [A; L; R] xk in tm1
-        A_mul_raw(S, v, w.xk, w.tm1);
+        A_mul_raw(S, v, w, w.xk, w.tm1);
         double p = 0.0;
         for (int i = 0; i < nComp; i++) p += w.tm1[nC + i] * w.tm1[nC + nComp + i];
         if (have_gphi) for (int j = 0; j < n; j++) p += w.gphi[j] * w.xk[j];
@@ -647,13 +729,15 @@ LCQ_DEV void lcqp_loop(const SymDev& S, const View& v, const lcqp_cuda_options& 
         if (have_gphi) for (int j = 0; j < n; j++) w.gt[j] = v.g[j] + rho * w.gphi[j];
     };
     auto linearize = [&]() {  // :1105-1112 : gk = rho C xk + g_tilde
-        A_mul_raw(S, v, w.xk, w.tm1);
+        A_mul_raw(S, v, w, w.xk, w.tm1);
         for (int i = 0; i < nC; i++) w.tm2[i] = 0.0;
         for (int i = 0; i < nComp; i++) { w.tm2[nC + i] = w.tm1[nC + nComp + i]; w.tm2[nC + nComp + i] = w.tm1[nC + i]; }
-        At_mul_raw(S, v, w.tm2, w.tn2);
+        At_mul_raw(S, v, w, w.tm2, w.tn2);
         for (int j = 0; j < n; j++) w.gk[j] = rho * w.tn2[j] + w.gt[j];
     };
-    auto solve_qp = [&](bool initial) -> bool {  // solveQPSubproblem :1115-1148 over SubsolverOSQP::solve
+    // solveQPSubproblem :1115-1148 over SubsolverOSQP::solve, in three steps so that the lanes of the warp enter the ADMM
+    // loop together: prepare (setup or cost update; false: the QP cannot start), osqp_solve, finish (read the solution).
+    auto qp_prepare = [&](bool initial) -> bool {
         if (initial) {
             // osqp_setup (osqp.c:96-283): validate_data rejects l > u -> the workspace stays NULL and the warm start fails
             for (int i = 0; i < m; i++) if (w.l[i] > w.u[i]) { ret = RET_OSQP_GUESS; return false; }
@@ -671,7 +755,9 @@ LCQ_DEV void lcqp_loop(const SymDev& S, const View& v, const lcqp_cuda_options& 
         } else {
             for (int j = 0; j < n; j++) w.q[j] = st.c * (w.sD[j] * w.gk[j]);   // osqp_update_lin_cost (:752-782)
         }
-        const int flag = osqp_solve(S, o, w, st);
+        return true;
+    };
+    auto qp_finish = [&](int flag) -> bool {
         subIter += st.iter;
         exitFlag = flag;
         if (flag <= 0) { ret = RET_SUBPROBLEM; return false; }   // SubsolverOSQP.cpp:176-181
@@ -689,16 +775,23 @@ LCQ_DEV void lcqp_loop(const SymDev& S, const View& v, const lcqp_cuda_options& 
     };
 
     bool failed = false, success = false;
+    // (every lane of the warp runs an instance -- the kernel pads the last tile -- so the votes below take all 32 lanes)
     if (o.solveZeroPenaltyFirst) { for (int j = 0; j < n; j++) w.gk[j] = v.g[j]; }
     else linearize();
-    if (!solve_qp(true)) failed = true;
+    {
+        const bool go = qp_prepare(true);
+        const unsigned qp_mask = OSQ_BALLOT(go);
+        if (go) { const int flag = osqp_solve(S, o, w, st, qp_mask); if (!qp_finish(flag)) failed = true; }
+        else failed = true;
+    }
     out.rhoOpt = failed ? 0.0 : rho;
 
-    while (!failed) {
+    // one pass of the loop; returns false when the instance is finished
+    auto pass = [&]() -> bool {
         for (int j = 0; j < n; j++) w.xk[j] = w.xk[j] + alphak * w.pk[j];   // updateStep :1240
         // updateStationarity :1246-1272 (no box part on this path)
         Qk_mul(S, v, w, rho, w.xk, &w.gt, w.stat);
-        At_mul_raw(S, v, w.yk, w.tn1);
+        At_mul_raw(S, v, w, w.yk, w.tn1);
         for (int j = 0; j < n; j++) w.stat[j] -= w.tn1[j];
         totalIter++;
         {   // leyfferCheckPositive :1275-1313
@@ -734,13 +827,17 @@ LCQ_DEV void lcqp_loop(const SymDev& S, const View& v, const lcqp_cuda_options& 
                 }
                 status = (fl & 4) ? 1 : (!(fl & 1) ? 4 : (!(fl & 2) ? 3 : 2));
                 success = true;
-                break;
+                return false;
             } else { update_penalty(); outerIter++; }
         }
-        if (totalIter > o.maxIterations) { ret = RET_MAX_ITER; break; }
-        if (rho > o.maxPenaltyParameter) { ret = RET_MAX_PEN; break; }
-        linearize();
-        if (!solve_qp(false)) { failed = true; break; }
+        if (totalIter > o.maxIterations) { ret = RET_MAX_ITER; return false; }
+        if (rho > o.maxPenaltyParameter) { ret = RET_MAX_PEN; return false; }
+        return true;
+    };
+    // the QP of the pass and the step length (second half of the reference's loop body): every lane that is still
+    // running enters its QP in the same trip
+    auto pass2 = [&](int flag) -> bool {
+        if (!qp_finish(flag)) { failed = true; return false; }
         if (o.perturbStep)
             for (int j = 0; j < n; j++) w.xk[j] += perturb_draw(o.perturb_seed, instance, (unsigned)totalIter, (unsigned)j) * kEPS;
         {   // getOptimalStepLength :1217-1237
@@ -753,6 +850,15 @@ LCQ_DEV void lcqp_loop(const SymDev& S, const View& v, const lcqp_cuda_options& 
             alphak = 1.0;
             if (qk > 0 && lk < 0) alphak = fmin(-lk / qk, 1.0);
         }
+        return true;
+    };
+    bool run = !failed;
+    while (OSQ_ANY(0xffffffffu, run)) {
+        if (run) run = pass();
+        if (run) { linearize(); qp_prepare(false); }   // :545-548
+        const unsigned qp_mask = OSQ_BALLOT(run);
+        if (run) { const int flag = osqp_solve(S, o, w, st, qp_mask); run = pass2(flag); }
+        OSQ_SYNCWARP(0xffffffffu);
     }
     for (int j = 0; j < n; j++) xout[j] = w.xk[j];
     if (success) {   // transformDuals :1381-1409 ; tm1 holds [A; L; R] xk from the last phi()

@@ -38,6 +38,8 @@ struct Symbolic {
     // L (unit lower, CSC, rows in increasing order) and the row programs
     std::vector<int> Lp, Li;
     std::vector<int> rp, rcol, rpos;   // row k: t in [rp[k], rp[k+1]): column rcol[t], slot rpos[t] of L
+    std::vector<int> Lcol, Lrev;       // column of entry p; order of the backward sweep (columns descending, entries ascending)
+    std::vector<int> Pcol, Acol, Qcol; // column of every entry of P, A, Q (the products run over flat entry lists)
     long long factor_flops = 0;        // multiply-subtracts of one numeric factorisation
 };
 
@@ -160,6 +162,12 @@ inline void analyse(int n, int m, const std::vector<Trip>& Qpat, const std::vect
         }
         S.rp[k + 1] = (int)S.rcol.size();
     }
+    auto cols_of = [](const std::vector<int>& ptr, std::vector<int>& out) { out.assign(ptr.back(), 0); for (size_t c = 0; c + 1 < ptr.size(); c++) for (int p = ptr[c]; p < ptr[c + 1]; p++) out[p] = (int)c; };
+    cols_of(S.Pp, S.Pcol); cols_of(S.Ap, S.Acol); cols_of(S.Qp, S.Qcol);
+    S.Lcol.assign(S.Li.size(), 0);
+    S.Lrev.clear();
+    for (int c = 0; c < N; c++) for (int p = S.Lp[c]; p < S.Lp[c + 1]; p++) S.Lcol[p] = c;
+    for (int c = N - 1; c >= 0; c--) for (int p = S.Lp[c]; p < S.Lp[c + 1]; p++) S.Lrev.push_back(p);
 }
 
 // Patterns from dense row-major matrices (the batch's union of non-zeros is passed in as 0/1 masks)

@@ -61,6 +61,19 @@ static std::vector<double> g_trace_x, g_trace_alpha, g_trace_stat;
 static std::vector<int> g_trace_sub;
 static int g_trace_nV = 0;
 
+/* Subsolver options pass-through (Options::setqpOASESOptions / setOSQPOptions): values <= 0 keep the reference's
+ * defaults.  Used by the tests of the pass-through. */
+static double g_qpoases_termtol = 0.0, g_qpoases_boundtol = 0.0, g_osqp_eps = 0.0;
+static int g_osqp_max_iter = 0;
+
+void lcqpow_ref_set_subsolver_options(double qpoases_terminationTolerance, double qpoases_boundTolerance, double osqp_eps_abs_rel, int osqp_max_iter)
+{
+    g_qpoases_termtol = qpoases_terminationTolerance;
+    g_qpoases_boundtol = qpoases_boundTolerance;
+    g_osqp_eps = osqp_eps_abs_rel;
+    g_osqp_max_iter = osqp_max_iter;
+}
+
 void lcqpow_ref_set_debug(int qpoases_print_level, int store_steps)
 {
     g_qpoases_print_level = qpoases_print_level;
@@ -131,6 +144,17 @@ int lcqpow_ref_solve(int nV, int nC, int nComp,
     if (o->osqp_adaptive_rho_interval >= 0) {
         OSQPSettings* s = options.getOSQPOptions();
         s->adaptive_rho_interval = o->osqp_adaptive_rho_interval;
+    }
+    if (g_osqp_eps > 0.0 || g_osqp_max_iter > 0) {
+        OSQPSettings* s = options.getOSQPOptions();
+        if (g_osqp_eps > 0.0) { s->eps_abs = g_osqp_eps; s->eps_rel = g_osqp_eps; }
+        if (g_osqp_max_iter > 0) s->max_iter = g_osqp_max_iter;
+    }
+    if (g_qpoases_termtol > 0.0 || g_qpoases_boundtol > 0.0) {
+        qpOASES::Options qo = options.getqpOASESOptions();
+        if (g_qpoases_termtol > 0.0) qo.terminationTolerance = g_qpoases_termtol;
+        if (g_qpoases_boundtol > 0.0) qo.boundTolerance = g_qpoases_boundtol;
+        options.setqpOASESOptions(qo);
     }
     if (g_qpoases_print_level != 0) {
         qpOASES::Options qo = options.getqpOASESOptions();

@@ -139,6 +139,7 @@ static void sym_to_dev(const osq::Symbolic& S, int nC, int nComp, osq::SymDev& D
     D.Pp = S.Pp.data(); D.Pi = S.Pi.data(); D.Psrc = S.Psrc.data(); D.Ap = S.Ap.data(); D.Ai = S.Ai.data(); D.Asrc = S.Asrc.data();
     D.Qp = S.Qp.data(); D.Qi = S.Qi.data(); D.Qsrc = S.Qsrc.data(); D.perm = S.perm.data(); D.Kp = S.Kp.data(); D.Ki = S.Ki.data(); D.Ksrc = S.Ksrc.data();
     D.Lp = S.Lp.data(); D.Li = S.Li.data(); D.rp = S.rp.data(); D.rcol = S.rcol.data(); D.rpos = S.rpos.data();
+    D.Lcol = S.Lcol.data(); D.Lrev = S.Lrev.data(); D.Pcol = S.Pcol.data(); D.Acol = S.Acol.data(); D.Qcol = S.Qcol.data();
 }
 
 static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned shared_mask_in, const double* const* base,

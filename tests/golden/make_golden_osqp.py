@@ -48,6 +48,22 @@ def main():
         fam[f"{name}/rhoOpt"] = res["rhoOpt"]
         print(name, "ret", np.unique(res["ret"], return_counts=True), "k mean", res["iterOuter"].mean(), "i mean", res["iterTotal"].mean(),
               "ADMM iterations mean", res["subproblemIter"].mean())
+    # subsolver option pass-through (Options::setqpOASESOptions / setOSQPOptions): the 16 dense golden
+    # instances with qpOASES terminationTolerance = 1e-2 (instance 1 then runs into MAX_ITERATIONS_REACHED) and with
+    # OSQP eps_abs = eps_rel = 1e-5
+    import ctypes as C
+    ref.lib.lcqpow_ref_set_subsolver_options.argtypes = [C.c_double, C.c_double, C.c_double, C.c_int]
+    pb = P.dense_random_batch(16)
+    for tag, args, qs in (("opt_qpoases_termtol_1e-2", (1e-2, 0.0, 0.0, 0), pyref.QPOASES_DENSE), ("opt_osqp_eps_1e-5", (0.0, 0.0, 1e-5, 0), pyref.OSQP_SPARSE)):
+        ref.lib.lcqpow_ref_set_subsolver_options(*args)
+        o = ref.default_options(qpSolver=qs, perturbStep=0)
+        o.osqp_adaptive_rho_interval = 25
+        s = ref.solve_batch(pb, o)
+        fam[f"{tag}/x"] = s.x
+        for f in ("ret", "status", "iterTotal", "iterOuter", "subproblemIter", "qpExitFlag"):
+            fam[f"{tag}/{f}"] = s.res[f].astype(np.int32)
+        print(tag, "ret", s.res["ret"].tolist(), "sub", s.res["subproblemIter"].tolist())
+    ref.lib.lcqpow_ref_set_subsolver_options(0.0, 0.0, 0.0, 0)
     np.savez_compressed(os.path.join(HERE, "reference_families_osqp.npz"), **fam)
 
 

@@ -11,6 +11,8 @@ def run(pb, over, tag, interval=0):
     for k, v in over.items():
         getattr(o, "set" + k[0].upper() + k[1:])(v)
     o.setOSQPADMM(True, adaptive_rho_interval=interval)
+    if os.environ.get("MAXIT"):
+        o.setMaxIterations(int(os.environ["MAXIT"]))
     assert prob.setOptions(o) == 0
     t = time.time()
     if isinstance(pb, P.SparseLCQPBatch):
@@ -19,7 +21,7 @@ def run(pb, over, tag, interval=0):
         rc = prob.loadBatch(pb)
     assert rc == 0, prob._err()
     tl = time.time() - t
-    for rep in range(2):
+    for rep in range(int(os.environ.get("REPS", 1))):
         prob.runSolver()
         ms, _ = prob.lastRunMs()
     st = prob.getOutputStatistics()

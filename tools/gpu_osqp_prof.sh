@@ -1,7 +1,13 @@
-# development aid: how the OSQP-flavour kernel scales with the batch, and one ncu capture of it
+# development aid: GPU tests of the OSQP flavour + throughput of its kernel at large batches (scratch in shared memory vs global)
 cd $GRAFT_REPO_ROOT
-for b in 32 1024 8192; do C5_BATCH=$b timeout 300 python tools/gpu_osqp_check.py c5 2>&1 | grep "C5 dense"; done
-C2_BATCH=4096 timeout 300 python tools/gpu_osqp_check.py c2 2>&1 | grep "C2 circle"
-C4_BATCH=256 timeout 300 python tools/gpu_osqp_check.py c4 2>&1 | grep "C4 sparse"
-C5_BATCH=2048 timeout 600 ncu --set full --clock-control none --import-source on -k regex:lcqp_osqp_kernel -s 1 -c 1 -f -o gpurun_out/${TAG:-osqp}_osqp python tools/gpu_osqp_check.py c5 > gpurun_out/${TAG:-osqp}_ncu.log 2>&1
-tail -3 gpurun_out/${TAG:-osqp}_ncu.log
+timeout 400 python -m pytest tests/test_osqp_flavour.py -m gpu -x -q 2>&1 | tail -5 > gpurun_out/${TAG:-osqp}_pytest.log; cat gpurun_out/${TAG:-osqp}_pytest.log
+export LCQP_CUDA_VERBOSE=1
+LOG=gpurun_out/${TAG:-osqp}_osqp.log
+: > $LOG
+C5_BATCH=28416 timeout ${TMO:-120} python tools/gpu_osqp_check.py c5 >> $LOG 2>&1
+C4_BATCH=1024 timeout ${TMO:-150} python tools/gpu_osqp_check.py c4 >> $LOG 2>&1
+echo "== scratch in global memory" >> $LOG
+export LCQP_CUDA_LIB=$GRAFT_REPO_ROOT/lcqpow_b200/lib/liblcqp_cuda_tune.so LCQP_CUDA_OSQP_NOSMEM=1
+C5_BATCH=75776 timeout ${TMO:-120} python tools/gpu_osqp_check.py c5 >> $LOG 2>&1
+C2_BATCH=75776 timeout ${TMO:-150} python tools/gpu_osqp_check.py c2 >> $LOG 2>&1
+cat $LOG
