@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblcqp_cuda.so")
 SOURCES = [os.path.join(CSRC, "lcqp_cabi.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("lcqp_device.cuh", "lcqp_pas.cuh", "lcqp_osqp.cuh", "lcqp_sparse_host.hpp")] + [os.path.join(HERE, "..", "include", "lcqp_cuda.h")]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("lcqp_device.cuh", "lcqp_pas.cuh", "lcqp_osqp.cuh", "lcqp_osqp_impl.inc", "lcqp_sparse_host.hpp")] + [os.path.join(HERE, "..", "include", "lcqp_cuda.h")]
 # LCQP_NO_ASSUME: the address-space hints (__builtin_assume(__isShared(p))) of lcqp_device.cuh are off -- with
 # them nvcc 12.9 miscompiles the solver for sm_100a (garbage return values of the non-inlined device functions;
 # seen on the B200, gpurun_out/dbg1.log vs dbg2.log of round 1).

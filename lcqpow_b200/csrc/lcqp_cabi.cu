@@ -533,14 +533,14 @@ __global__ void __launch_bounds__(kThreads) pas_plugin_kernel(const __grid_const
 }
 
 
-// ---- the OSQP flavour: one thread per instance, one warp per CTA (lcqp_osqp.cuh) -----------------------------------
+// ---- the OSQP flavour (lcqp_osqp.cuh): one warp per CTA; mode T = 32 instances per warp, mode W = one instance per warp ----
 struct OsqpArgs {
     osq::SymDev S;
     lcqp_cuda_options o;
     const double* arr[LCQP_NUM_ARRAYS];          // Q, A, L, R hold VALUE arrays indexed through S.*src (dense or csc layout)
     unsigned long long stride[LCQP_NUM_ARRAYS];  // doubles between consecutive instances (0: shared)
     int batch;
-    double* workspace;                           // per resident warp: ws_doubles x 32 doubles, lane-interleaved
+    double* workspace;                           // per resident warp: ws_doubles x (32 | 1) doubles
     unsigned long long ws_doubles;
     double* xout;
     double* yout;
@@ -548,52 +548,94 @@ struct OsqpArgs {
     unsigned int* counter;
     unsigned long long instance_offset;
     int box_given;                               // lb / ub were loaded: INVALID_OSQP_BOX_CONSTRAINTS (LCQProblem.cpp:930-957)
-    unsigned smem_bytes;                         // N x 32 doubles of solve / factor scratch per warp when that fits, else 0 (global, L2)
+    unsigned smem_bytes;                         // solve / factor scratch per warp in shared memory when that fits, else 0 (global, L2)
 };
 
+LCQ_DEV osq::View osqp_view(const OsqpArgs& a, int b)
+{
+    osq::View v;
+    auto at = [&](int k) -> const double* { return a.arr[k] ? a.arr[k] + a.stride[k] * (unsigned long long)b : nullptr; };
+    v.Q = at(LCQP_Q); v.A = at(LCQP_A); v.L = at(LCQP_L); v.R = at(LCQP_R); v.g = at(LCQP_G);
+    v.lbL = at(LCQP_LBL); v.ubL = at(LCQP_UBL); v.lbR = at(LCQP_LBR); v.ubR = at(LCQP_UBR);
+    v.lbA = at(LCQP_LBA); v.ubA = at(LCQP_UBA); v.x0 = at(LCQP_X0); v.y0 = at(LCQP_Y0);
+    return v;
+}
+LCQ_DEV void osqp_state_init(osq::State& st)
+{
+    st.rho = 0; st.c = 1; st.cinv = 1; st.pri_res = 0; st.dua_res = 0; st.status_val = 0; st.iter = 0; st.interval = 0;
+    st.factor_bad = 0; st.admm_total = 0; st.factor_count = 0;
+}
+LCQ_DEV lcqp_cuda_stats osqp_stats(const LoopOut& out, const osq::State& st, int mA)
+{
+    lcqp_cuda_stats r;
+    r.ret = out.ret; r.status = out.status; r.iterTotal = out.iterTotal; r.iterOuter = out.iterOuter;
+    r.subproblemIter = out.subIter; r.qpExitFlag = out.exitFlag; r.nDuals = mA; r.kktSolves = (int)st.factor_count;
+    r.rhoOpt = out.rhoOpt; r.admmIters = (double)st.admm_total;
+    return r;
+}
+
+// mode T: thread = instance; the last tile is padded with copies of the last instance (every lane takes part in the
+// warp's votes; the padded lanes recompute instance batch - 1 bit for bit, so their stores carry the same values)
 __global__ void __launch_bounds__(32) lcqp_osqp_kernel(const __grid_constant__ OsqpArgs a)
 {
     const int lane = threadIdx.x;
     extern __shared__ __align__(16) unsigned char osqp_smem[];
-    osq::Work w;
-    osq::carve(w, a.S, a.workspace + (size_t)blockIdx.x * a.ws_doubles * 32 + lane, a.smem_bytes ? reinterpret_cast<double*>(osqp_smem) + lane : nullptr);
+    osqt::Work w;
+    osqt::carve(w, a.S, a.workspace + (size_t)blockIdx.x * a.ws_doubles * 32 + lane, a.smem_bytes ? reinterpret_cast<double*>(osqp_smem) + lane : nullptr);
     const int nV = a.S.n, mA = a.S.m, nD = nV + mA;
     for (;;) {
         unsigned tile = 0;
         if (lane == 0) tile = atomicAdd(a.counter, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         if ((unsigned long long)tile * 32ull >= (unsigned long long)a.batch) break;
-        // (the last tile is padded with copies of the last instance: every lane takes part in the warp's votes)
         const int b_lane = (int)tile * 32 + lane;
         const bool valid = b_lane < a.batch;
         const int b = valid ? b_lane : a.batch - 1;
-        {
-            osq::View v;
-            auto at = [&](int k) -> const double* { return a.arr[k] ? a.arr[k] + a.stride[k] * (unsigned long long)b : nullptr; };
-            v.Q = at(LCQP_Q); v.A = at(LCQP_A); v.L = at(LCQP_L); v.R = at(LCQP_R); v.g = at(LCQP_G);
-            v.lbL = at(LCQP_LBL); v.ubL = at(LCQP_UBL); v.lbR = at(LCQP_LBR); v.ubR = at(LCQP_UBR);
-            v.lbA = at(LCQP_LBA); v.ubA = at(LCQP_UBA); v.x0 = at(LCQP_X0); v.y0 = at(LCQP_Y0);
-            LoopOut out;
-            osq::State st;
-            st.rho = 0; st.c = 1; st.cinv = 1; st.pri_res = 0; st.dua_res = 0; st.status_val = 0; st.iter = 0; st.interval = 0;
-            st.factor_bad = 0; st.admm_total = 0; st.factor_count = 0;
-            // padded lanes write into the spare slot behind the workspace's last vector... they recompute instance
-            // batch - 1 bit for bit, so their stores to its outputs carry the same values
-            double* xo = a.xout + (size_t)b * nV;
-            double* yo = a.yout + (size_t)b * nD;
-            if (a.box_given) {
-                out.ret = RET_INVALID_OSQP_BOX; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
-                for (int j = 0; j < nV; j++) xo[j] = v.x0 ? v.x0[j] : 0.0;
-                for (int j = 0; j < mA; j++) yo[j] = 0.0;
-            } else
-                osq::lcqp_loop(a.S, v, a.o, w, a.instance_offset + (unsigned long long)b, xo, yo, out, st);
-            for (int j = mA; j < nD; j++) yo[j] = 0.0;
-            lcqp_cuda_stats r;
-            r.ret = out.ret; r.status = out.status; r.iterTotal = out.iterTotal; r.iterOuter = out.iterOuter;
-            r.subproblemIter = out.subIter; r.qpExitFlag = out.exitFlag; r.nDuals = mA; r.kktSolves = (int)st.factor_count;
-            r.rhoOpt = out.rhoOpt; r.admmIters = (double)st.admm_total;
-            if (valid) a.stats[b] = r;
-        }
+        const osq::View v = osqp_view(a, b);
+        LoopOut out;
+        osq::State st;
+        osqp_state_init(st);
+        double* xo = a.xout + (size_t)b * nV;
+        double* yo = a.yout + (size_t)b * nD;
+        if (a.box_given) {
+            out.ret = RET_INVALID_OSQP_BOX; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
+            for (int j = 0; j < nV; j++) xo[j] = v.x0 ? v.x0[j] : 0.0;
+            for (int j = 0; j < mA; j++) yo[j] = 0.0;
+        } else
+            osqt::lcqp_loop(a.S, v, a.o, w, a.instance_offset + (unsigned long long)b, xo, yo, out, st);
+        for (int j = mA; j < nD; j++) yo[j] = 0.0;
+        if (valid) a.stats[b] = osqp_stats(out, st, mA);
+        __syncwarp();
+    }
+}
+
+// mode W: warp = instance
+__global__ void __launch_bounds__(32) lcqp_osqpw_kernel(const __grid_constant__ OsqpArgs a)
+{
+    const int lane = threadIdx.x;
+    extern __shared__ __align__(16) unsigned char osqp_smem[];
+    osqw::Work w;
+    osqw::carve(w, a.S, a.workspace + (size_t)blockIdx.x * a.ws_doubles, a.smem_bytes ? reinterpret_cast<double*>(osqp_smem) : nullptr);
+    const int nV = a.S.n, mA = a.S.m, nD = nV + mA;
+    for (;;) {
+        unsigned b = 0;
+        if (lane == 0) b = atomicAdd(a.counter, 1u);
+        b = __shfl_sync(0xffffffffu, b, 0);
+        if (b >= (unsigned)a.batch) break;
+        const osq::View v = osqp_view(a, (int)b);
+        LoopOut out;
+        osq::State st;
+        osqp_state_init(st);
+        double* xo = a.xout + (size_t)b * nV;
+        double* yo = a.yout + (size_t)b * nD;
+        if (a.box_given) {
+            out.ret = RET_INVALID_OSQP_BOX; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;
+            for (int j = lane; j < nV; j += 32) xo[j] = v.x0 ? v.x0[j] : 0.0;
+            for (int j = lane; j < mA; j += 32) yo[j] = 0.0;
+        } else
+            osqw::lcqp_loop(a.S, v, a.o, w, a.instance_offset + (unsigned long long)b, xo, yo, out, st);
+        for (int j = mA + lane; j < nD; j += 32) yo[j] = 0.0;
+        if (lane == 0) a.stats[b] = osqp_stats(out, st, mA);
         __syncwarp();
     }
 }
@@ -1276,9 +1318,10 @@ static int pas_prepare_load(lcqp_cuda_handle h)
 static int osqp_upload_symbolic(lcqp_cuda_handle h)
 {
     const osq::Symbolic& S = *h->sym;
-    constexpr int NV = 23;
+    constexpr int NV = osq::kSymArrays;
     const std::vector<int>* vs[NV] = {&S.Pp, &S.Pi, &S.Psrc, &S.Ap, &S.Ai, &S.Asrc, &S.Qp, &S.Qi, &S.Qsrc, &S.perm, &S.Kp, &S.Ki, &S.Ksrc,
-                                      &S.Lp, &S.Li, &S.rp, &S.rcol, &S.rpos, &S.Lcol, &S.Lrev, &S.Pcol, &S.Acol, &S.Qcol};
+                                      &S.Lp, &S.Li, &S.rp, &S.rcol, &S.rpos, &S.Pcol, &S.Acol, &S.Qcol,
+                                      &S.ArP, &S.ArE, &S.PrP, &S.PrE, &S.QrP, &S.QrE, &S.LrP, &S.LrC, &S.rposr, &S.flP, &S.flR, &S.blP, &S.blC};
     size_t total = 0;
     size_t off[NV];
     for (int k = 0; k < NV; k++) { off[k] = total; total += (vs[k]->size() + 3) & ~(size_t)3; }
@@ -1295,8 +1338,9 @@ static int osqp_upload_symbolic(lcqp_cuda_handle h)
     osq::SymDev& D = h->symdev;
     D.n = S.n; D.m = S.m; D.N = S.N; D.nC = h->nC; D.nComp = h->nComp;
     D.nnzP = (int)S.Pi.size(); D.nnzA = (int)S.Ai.size(); D.nnzQ = (int)S.Qi.size(); D.nnzK = (int)S.Ki.size(); D.nnzL = (int)S.Li.size();
+    D.nflev = (int)S.flP.size() - 1; D.nblev = (int)S.blP.size() - 1;
     const int** dst[NV] = {&D.Pp, &D.Pi, &D.Psrc, &D.Ap, &D.Ai, &D.Asrc, &D.Qp, &D.Qi, &D.Qsrc, &D.perm, &D.Kp, &D.Ki, &D.Ksrc, &D.Lp, &D.Li, &D.rp, &D.rcol, &D.rpos,
-                           &D.Lcol, &D.Lrev, &D.Pcol, &D.Acol, &D.Qcol};
+                           &D.Pcol, &D.Acol, &D.Qcol, &D.ArP, &D.ArE, &D.PrP, &D.PrE, &D.QrP, &D.QrE, &D.LrP, &D.LrC, &D.rposr, &D.flP, &D.flR, &D.blP, &D.blC};
     for (int k = 0; k < NV; k++) *dst[k] = h->sym_ints + off[k];
     h->osqp_nnzL = (long long)S.Li.size();
     return LCQP_CUDA_OK;
@@ -1338,26 +1382,33 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     a.batch = h->batch;
     a.box_given = (h->osqp_arr[LCQP_LB] || h->osqp_arr[LCQP_UB]) ? 1 : 0;
     a.ws_doubles = (osq::ws_doubles(a.S) + 1) & ~(size_t)1;
-    // the scratch vector of the triangular solves (a chain of dependent read-modify-writes) sits in shared memory when
-    // N x 32 doubles fit the CTA's budget
-    const size_t sm_need = osq::sm_len(a.S) * 32 * sizeof(double);
+    // One warp per instance when the factor is sparse (the level sets give the lanes something to share) or the problem
+    // is large, or when the batch would not fill the GPU with one thread per instance; else one thread per instance.
+    const long long tiles32 = ((long long)h->batch + 31) / 32;
+    bool warp_mode = (a.S.nnzL <= 8 * a.S.N) || a.S.N > 512 || tiles32 < 4ll * h->num_sms;
+    if (const char* t = tune_env("LCQP_CUDA_OSQP_MODE")) warp_mode = (t[0] == 'w');
+    const int lanes = warp_mode ? 1 : 32;
+    // the scratch vector of the triangular solves and of the factorisation (chains of dependent read-modify-writes) sits
+    // in shared memory when it fits the CTA's budget
+    const size_t sm_need = osq::sm_len(a.S) * lanes * sizeof(double);
     a.smem_bytes = (sm_need <= (size_t)kSmemMax - 1024) ? (unsigned)sm_need : 0u;
     if (tune_env("LCQP_CUDA_OSQP_NOSMEM")) a.smem_bytes = 0;
-    CK(cudaFuncSetAttribute(lcqp_osqp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);
+    auto kern = warp_mode ? lcqp_osqpw_kernel : lcqp_osqp_kernel;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lcqp_osqp_kernel, 32, a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);
     if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
     if (per_sm > 16) per_sm = 16;
-    // one warp per CTA; as many resident warps as there are tiles, up to per_sm per SM and a quarter of the device memory
-    const long long tiles = ((long long)h->batch + 31) / 32;
+    // one warp per CTA; as many resident warps as there are work items, up to per_sm per SM and a quarter of the device memory
+    const long long items = warp_mode ? (long long)h->batch : tiles32;
     long long warps = (long long)h->num_sms * per_sm;
-    if (warps > tiles) warps = tiles;
+    if (warps > items) warps = items;
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const size_t per_warp = a.ws_doubles * 32 * sizeof(double);
+    const size_t per_warp = a.ws_doubles * lanes * sizeof(double);
     const size_t budget = total_b / 4 > h->workspace_cap * sizeof(double) ? total_b / 4 : h->workspace_cap * sizeof(double);
     while (warps > 1 && (size_t)warps * per_warp > budget) warps = (warps * 3) / 4;
-    const size_t ws_total = (size_t)warps * a.ws_doubles * 32;
+    const size_t ws_total = (size_t)warps * a.ws_doubles * lanes;
     if (ws_total > h->workspace_cap) {
         if (h->workspace) { cudaDeviceSynchronize(); cudaFree(h->workspace); }
         h->workspace = nullptr; h->workspace_cap = 0;
@@ -1371,9 +1422,11 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
     if (getenv("LCQP_CUDA_VERBOSE"))
-        fprintf(stderr, "lcqp_cuda (OSQP flavour): %lld warps of 32 instances (%d per SM), N %d, nnz(L) %d, nnz(K) %d, workspace %.1f MB/warp, smem %u B/warp, factor flops %lld\n",
-                warps, per_sm, a.S.N, a.S.nnzL, a.S.nnzK, per_warp / 1.0e6, a.smem_bytes, h->sym ? h->sym->factor_flops : 0ll);
-    lcqp_osqp_kernel<<<(unsigned)warps, 32, a.smem_bytes, stream>>>(a);
+        fprintf(stderr, "lcqp_cuda (OSQP flavour, %s): %lld warps (%d per SM), N %d, nnz(L) %d, nnz(K) %d, levels %d + %d, workspace %.2f MB/warp, smem %u B/warp, factor flops %lld\n",
+                warp_mode ? "one warp per instance" : "one thread per instance", warps, per_sm, a.S.N, a.S.nnzL, a.S.nnzK, a.S.nflev, a.S.nblev, per_warp / 1.0e6,
+                a.smem_bytes, h->sym ? h->sym->factor_flops : 0ll);
+    if (warp_mode) lcqp_osqpw_kernel<<<(unsigned)warps, 32, a.smem_bytes, stream>>>(a);
+    else lcqp_osqp_kernel<<<(unsigned)warps, 32, a.smem_bytes, stream>>>(a);
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);

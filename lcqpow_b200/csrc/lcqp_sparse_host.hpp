@@ -8,7 +8,7 @@
 // pattern: this file does that analysis ONCE per load, on the host, and emits flat index "programs" that every
 // instance (one GPU thread each, lcqp_osqp.cuh) executes with its own values -- no integer workspace, no pattern
 // logic and no divergence on the device.
-//     ordering      minimum degree on the elimination graph (bitset adjacency; ties -> lowest index)
+//     ordering      multiple minimum degree on the elimination graph (bitset adjacency; independent sets per round)
 //     etree + L     row-by-row reach through the elimination tree (the up-looking scheme of qdldl.c:72-233)
 //     row program   for row k of L: the columns it touches in elimination order and the slot of L(k, c) in column c
 #pragma once
@@ -39,7 +39,15 @@ struct Symbolic {
     std::vector<int> Lp, Li;
     std::vector<int> rp, rcol, rpos;   // row k: t in [rp[k], rp[k+1]): column rcol[t], slot rpos[t] of L
     std::vector<int> Lcol, Lrev;       // column of entry p; order of the backward sweep (columns descending, entries ascending)
-    std::vector<int> Pcol, Acol, Qcol; // column of every entry of P, A, Q (the products run over flat entry lists)
+    std::vector<int> Pcol, Acol, Qcol; // column of every entry of P, A, Q
+    // the same entries listed by ROW (entry ids sorted by row, then column): a product accumulates every output element
+    // in a register, in the reference's order of accumulation, and rows are independent of each other
+    std::vector<int> ArP, ArE, PrP, PrE, QrP, QrE;
+    // L by rows: row i holds slots [LrP[i], LrP[i+1]) of a second, row-major copy of the values; LrC = column of a slot;
+    // rposr[t] = row-major slot of the entry that step t of the row programs produces
+    std::vector<int> LrP, LrC, rposr;
+    // level sets of the triangular solves: rows (forward) / columns (backward) of one level do not depend on each other
+    std::vector<int> flP, flR, blP, blC;
     long long factor_flops = 0;        // multiply-subtracts of one numeric factorisation
 };
 
@@ -56,22 +64,87 @@ inline std::vector<int> min_degree_order(int N, const std::vector<std::vector<in
     for (int i = 0; i < N; i++) deg[i] = popcnt(i);
     order.reserve(N);
     std::vector<int> nb;
-    for (int step = 0; step < N; step++) {
-        int best = -1;
-        for (int i = 0; i < N; i++) if (!gone[i] && (best < 0 || deg[i] < deg[best])) best = i;
-        order.push_back(best);
-        gone[best] = 1;
-        nb.clear();
-        for (int w = 0; w < W; w++) { uint64_t b = row(best)[w]; while (b) { const int t = __builtin_ctzll(b); nb.push_back(w * 64 + t); b &= b - 1; } }
-        // the neighbours of the eliminated node become a clique; the node leaves their lists
-        for (int a : nb) {
-            uint64_t* ra = row(a);
-            const uint64_t* rb = row(best);
-            for (int w = 0; w < W; w++) ra[w] |= rb[w];
-            ra[a >> 6] &= ~(1ull << (a & 63));
-            ra[best >> 6] &= ~(1ull << (best & 63));
-            deg[a] = popcnt(a);
+    // MULTIPLE elimination: a round eliminates an independent set of nodes of minimum degree (a node is skipped when a
+    // neighbour went in the same round).  On chain-like graphs (banded KKT systems) this halves the graph per round and
+    // the elimination tree gets logarithmic height instead of linear -- the height is the number of levels, i.e. of
+    // warp-wide synchronisations, of every triangular solve on the device.
+    std::vector<int> blocked(N, -1);
+    int round = 0;
+    while ((int)order.size() < N) {
+        int mind = 1 << 30;
+        for (int i = 0; i < N; i++) if (!gone[i] && deg[i] < mind) mind = deg[i];
+        for (int best = 0; best < N; best++) {
+            if (gone[best] || deg[best] != mind || blocked[best] == round) continue;
+            order.push_back(best);
+            gone[best] = 1;
+            nb.clear();
+            for (int w = 0; w < W; w++) { uint64_t b = row(best)[w]; while (b) { const int t = __builtin_ctzll(b); nb.push_back(w * 64 + t); b &= b - 1; } }
+            // the neighbours of the eliminated node become a clique; the node leaves their lists
+            for (int a : nb) {
+                uint64_t* ra = row(a);
+                const uint64_t* rb = row(best);
+                for (int w = 0; w < W; w++) ra[w] |= rb[w];
+                ra[a >> 6] &= ~(1ull << (a & 63));
+                ra[best >> 6] &= ~(1ull << (best & 63));
+                deg[a] = popcnt(a);
+                blocked[a] = round;
+            }
         }
+        round++;
+    }
+    return order;
+}
+
+// Nested dissection by breadth-first level structures: a connected piece is split at the middle level of the BFS from
+// a pseudo-peripheral node, the two sides are ordered first (recursively), the separator last.  For chain-like graphs
+// (banded KKT systems) the elimination tree gets height O(separator x log N) where minimum degree gives O(N).
+inline std::vector<int> nested_dissection_order(int N, const std::vector<std::vector<int>>& adj, int leaf = 24)
+{
+    std::vector<int> order, tag(N, 0), dist(N, -1), queue;
+    order.reserve(N);
+    int next_tag = 1;
+    // work items: (tag of the node set, emit separator afterwards?) -- an explicit stack of "ordered output" pieces
+    struct Item { std::vector<int> nodes; bool emit_only; };
+    std::vector<Item> stack;
+    { Item all; all.nodes.resize(N); for (int i = 0; i < N; i++) all.nodes[i] = i; all.emit_only = false; stack.push_back(std::move(all)); }
+    auto bfs = [&](int start, int t, std::vector<int>& out) {   // BFS inside the set tagged t; returns the visit order, dist[] filled
+        out.clear();
+        out.push_back(start); dist[start] = 0;
+        for (size_t h = 0; h < out.size(); h++) { const int u = out[h]; for (int v : adj[u]) if (tag[v] == t && dist[v] < 0) { dist[v] = dist[u] + 1; out.push_back(v); } }
+    };
+    while (!stack.empty()) {
+        Item it = std::move(stack.back());
+        stack.pop_back();
+        if (it.emit_only || (int)it.nodes.size() <= leaf) { for (int u : it.nodes) order.push_back(u); continue; }
+        const int t = next_tag++;
+        for (int u : it.nodes) { tag[u] = t; dist[u] = -1; }
+        // one connected component at a time
+        std::vector<int> comp, rest;
+        bfs(it.nodes[0], t, comp);
+        if (comp.size() < it.nodes.size()) {
+            for (int u : it.nodes) if (dist[u] < 0) rest.push_back(u);
+            for (int u : comp) dist[u] = -1;
+            Item a; a.nodes = rest; a.emit_only = false;
+            Item b; b.nodes = comp; b.emit_only = false;
+            stack.push_back(std::move(a));
+            stack.push_back(std::move(b));
+            continue;
+        }
+        // pseudo-peripheral start: the last node of a BFS, twice
+        int start = comp.back();
+        for (int rep = 0; rep < 2; rep++) { for (int u : comp) dist[u] = -1; bfs(start, t, comp); start = comp.back(); }
+        for (int u : comp) dist[u] = -1;
+        bfs(start, t, comp);
+        const int depth = dist[comp.back()];
+        if (depth < 2) { for (int u : comp) order.push_back(u); continue; }
+        const int mid = depth / 2;
+        Item A, B, Sep;
+        for (int u : comp) { if (dist[u] < mid) A.nodes.push_back(u); else if (dist[u] > mid) B.nodes.push_back(u); else Sep.nodes.push_back(u); }
+        A.emit_only = false; B.emit_only = false; Sep.emit_only = true;
+        // output order: A, B, separator -> push in reverse
+        stack.push_back(std::move(Sep));
+        stack.push_back(std::move(B));
+        stack.push_back(std::move(A));
     }
     return order;
 }
@@ -80,7 +153,7 @@ inline std::vector<int> min_degree_order(int N, const std::vector<std::vector<in
 // Apat: m x n pattern of [A; L; R] as (row, col, source) triplets.
 struct Trip { int r, c, src; };
 
-inline void analyse(int n, int m, const std::vector<Trip>& Qpat, const std::vector<Trip>& Apat, Symbolic& S)
+inline void analyse_with(int n, int m, const std::vector<Trip>& Qpat, const std::vector<Trip>& Apat, Symbolic& S, int strategy)
 {
     S.n = n; S.m = m; S.N = n + m;
     const int N = S.N;
@@ -106,7 +179,7 @@ inline void analyse(int n, int m, const std::vector<Trip>& Qpat, const std::vect
     for (int i = 0; i < m; i++) ke.push_back({n + i, n + i, ksrc(KSRC_RHO, i)});
     std::vector<std::vector<int>> adj(N);
     for (const KE& e : ke) if (e.r != e.c) { adj[e.r].push_back(e.c); adj[e.c].push_back(e.r); }
-    S.perm = min_degree_order(N, adj);
+    S.perm = (strategy == 1) ? nested_dissection_order(N, adj) : min_degree_order(N, adj);
     S.iperm.assign(N, 0);
     for (int k = 0; k < N; k++) S.iperm[S.perm[k]] = k;
     // permuted upper triangle
@@ -164,10 +237,53 @@ inline void analyse(int n, int m, const std::vector<Trip>& Qpat, const std::vect
     }
     auto cols_of = [](const std::vector<int>& ptr, std::vector<int>& out) { out.assign(ptr.back(), 0); for (size_t c = 0; c + 1 < ptr.size(); c++) for (int p = ptr[c]; p < ptr[c + 1]; p++) out[p] = (int)c; };
     cols_of(S.Pp, S.Pcol); cols_of(S.Ap, S.Acol); cols_of(S.Qp, S.Qcol);
+    auto by_rows = [](int nrows, const std::vector<int>& ptr, const std::vector<int>& idx, std::vector<int>& rp, std::vector<int>& re) {
+        rp.assign(nrows + 1, 0); re.assign(idx.size(), 0);
+        for (int r : idx) rp[r + 1]++;
+        for (int r = 0; r < nrows; r++) rp[r + 1] += rp[r];
+        std::vector<int> fillr(nrows, 0);
+        for (size_t c = 0; c + 1 < ptr.size(); c++) for (int p = ptr[c]; p < ptr[c + 1]; p++) { const int r = idx[p]; re[rp[r] + fillr[r]++] = p; }   // columns ascend
+    };
+    by_rows(m, S.Ap, S.Ai, S.ArP, S.ArE);
+    by_rows(n, S.Pp, S.Pi, S.PrP, S.PrE);
+    by_rows(n, S.Qp, S.Qi, S.QrP, S.QrE);
+    {
+        std::vector<int> re;
+        by_rows(N, S.Lp, S.Li, S.LrP, re);             // re[slot] = column-major entry id
+        std::vector<int> slot_of(S.Li.size(), 0);
+        S.LrC.assign(S.Li.size(), 0);
+        std::vector<int> colof(S.Li.size(), 0);
+        for (int c = 0; c < N; c++) for (int p = S.Lp[c]; p < S.Lp[c + 1]; p++) colof[p] = c;
+        for (size_t sl = 0; sl < re.size(); sl++) { slot_of[re[sl]] = (int)sl; S.LrC[sl] = colof[re[sl]]; }
+        S.rposr.assign(S.rpos.size(), 0);
+        for (size_t t = 0; t < S.rpos.size(); t++) S.rposr[t] = slot_of[S.rpos[t]];
+        // levels
+        std::vector<int> lev(N, 0), blev(N, 0);
+        int maxl = 0, maxb = 0;
+        for (int i = 0; i < N; i++) { int l = 0; for (int sl = S.LrP[i]; sl < S.LrP[i + 1]; sl++) l = std::max(l, lev[S.LrC[sl]] + 1); lev[i] = l; maxl = std::max(maxl, l); }
+        for (int i = N - 1; i >= 0; i--) { int l = 0; for (int p = S.Lp[i]; p < S.Lp[i + 1]; p++) l = std::max(l, blev[S.Li[p]] + 1); blev[i] = l; maxb = std::max(maxb, l); }
+        S.flP.assign(1, 0); S.flR.clear();
+        for (int l = 1; l <= maxl; l++) { for (int i = 0; i < N; i++) if (lev[i] == l) S.flR.push_back(i); S.flP.push_back((int)S.flR.size()); }
+        S.blP.assign(1, 0); S.blC.clear();
+        for (int l = 1; l <= maxb; l++) { for (int i = N - 1; i >= 0; i--) if (blev[i] == l) S.blC.push_back(i); S.blP.push_back((int)S.blC.size()); }
+    }
     S.Lcol.assign(S.Li.size(), 0);
     S.Lrev.clear();
     for (int c = 0; c < N; c++) for (int p = S.Lp[c]; p < S.Lp[c + 1]; p++) S.Lcol[p] = c;
     for (int c = N - 1; c >= 0; c--) for (int p = S.Lp[c]; p < S.Lp[c + 1]; p++) S.Lrev.push_back(p);
+}
+
+// Minimum degree gives the least fill; when its elimination tree is tall (many levels = many warp-wide synchronisations
+// per triangular solve) nested dissection is tried too and taken if it at least halves the levels at no more than three
+// times the fill.
+inline void analyse(int n, int m, const std::vector<Trip>& Qpat, const std::vector<Trip>& Apat, Symbolic& S)
+{
+    analyse_with(n, m, Qpat, Apat, S, 0);
+    if (S.flP.size() - 1 > 64) {
+        Symbolic T;
+        analyse_with(n, m, Qpat, Apat, T, 1);
+        if (2 * (T.flP.size() - 1) <= (S.flP.size() - 1) && T.Li.size() <= 3 * S.Li.size()) S = std::move(T);
+    }
 }
 
 // Patterns from dense row-major matrices (the batch's union of non-zeros is passed in as 0/1 masks)

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 EMU_SO = os.path.join(HERE, "liblcqp_emu.so")
 SOURCES = [os.path.join(HERE, "emu_driver.cpp"), os.path.join(ROOT, "lcqpow_b200", "csrc", "lcqp_device.cuh"),
-           os.path.join(ROOT, "lcqpow_b200", "csrc", "lcqp_pas.cuh"), os.path.join(ROOT, "lcqpow_b200", "csrc", "lcqp_osqp.cuh"),
+           os.path.join(ROOT, "lcqpow_b200", "csrc", "lcqp_pas.cuh"), os.path.join(ROOT, "lcqpow_b200", "csrc", "lcqp_osqp.cuh"), os.path.join(ROOT, "lcqpow_b200", "csrc", "lcqp_osqp_impl.inc"),
            os.path.join(ROOT, "lcqpow_b200", "csrc", "lcqp_sparse_host.hpp"),
            os.path.join(ROOT, "include", "lcqp_cuda.h")]
 

@@ -136,12 +136,17 @@ static void sym_to_dev(const osq::Symbolic& S, int nC, int nComp, osq::SymDev& D
 {
     D.n = S.n; D.m = S.m; D.N = S.N; D.nC = nC; D.nComp = nComp;
     D.nnzP = (int)S.Pi.size(); D.nnzA = (int)S.Ai.size(); D.nnzQ = (int)S.Qi.size(); D.nnzK = (int)S.Ki.size(); D.nnzL = (int)S.Li.size();
+    D.nflev = (int)S.flP.size() - 1; D.nblev = (int)S.blP.size() - 1;
     D.Pp = S.Pp.data(); D.Pi = S.Pi.data(); D.Psrc = S.Psrc.data(); D.Ap = S.Ap.data(); D.Ai = S.Ai.data(); D.Asrc = S.Asrc.data();
     D.Qp = S.Qp.data(); D.Qi = S.Qi.data(); D.Qsrc = S.Qsrc.data(); D.perm = S.perm.data(); D.Kp = S.Kp.data(); D.Ki = S.Ki.data(); D.Ksrc = S.Ksrc.data();
     D.Lp = S.Lp.data(); D.Li = S.Li.data(); D.rp = S.rp.data(); D.rcol = S.rcol.data(); D.rpos = S.rpos.data();
-    D.Lcol = S.Lcol.data(); D.Lrev = S.Lrev.data(); D.Pcol = S.Pcol.data(); D.Acol = S.Acol.data(); D.Qcol = S.Qcol.data();
+    D.Pcol = S.Pcol.data(); D.Acol = S.Acol.data(); D.Qcol = S.Qcol.data();
+    D.ArP = S.ArP.data(); D.ArE = S.ArE.data(); D.PrP = S.PrP.data(); D.PrE = S.PrE.data(); D.QrP = S.QrP.data(); D.QrE = S.QrE.data();
+    D.LrP = S.LrP.data(); D.LrC = S.LrC.data(); D.rposr = S.rposr.data(); D.flP = S.flP.data(); D.flR = S.flR.data(); D.blP = S.blP.data(); D.blC = S.blC.data();
 }
 
+// osqp_admm = 1: the one-thread-per-instance build of the solver; osqp_admm = 2 (test only): the one-warp-per-instance
+// build, whose CPU variant walks every loop that is declared parallel BACKWARDS (lcqp_osqp_impl.inc)
 static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned shared_mask_in, const double* const* base,
                             const lcqp_cuda_options* o, double* x, double* y, lcqp_cuda_stats* res)
 {
@@ -176,8 +181,11 @@ static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned share
     osq::SymDev D;
     sym_to_dev(S, nC, nComp, D);
     std::vector<double> ws(osq::ws_doubles(D) + 8);
-    osq::Work w;
-    osq::carve(w, D, ws.data());
+    const bool warp_build = (o->osqp_admm == 2);
+    osqt::Work wt;
+    osqw::Work ww;
+    osqt::carve(wt, D, ws.data());
+    osqw::carve(ww, D, ws.data());
     int nfail = 0;
     for (int b = 0; b < batch; b++) {
         osq::View v;
@@ -187,7 +195,8 @@ static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned share
         LoopOut out;
         osq::State st;
         memset(&st, 0, sizeof(st));
-        osq::lcqp_loop(D, v, *o, w, g_instance_offset + (unsigned long long)b, x + (size_t)b * nV, y + (size_t)b * nD, out, st);
+        if (warp_build) osqw::lcqp_loop(D, v, *o, ww, g_instance_offset + (unsigned long long)b, x + (size_t)b * nV, y + (size_t)b * nD, out, st);
+        else osqt::lcqp_loop(D, v, *o, wt, g_instance_offset + (unsigned long long)b, x + (size_t)b * nV, y + (size_t)b * nD, out, st);
         for (int j = mA; j < nD; j++) y[(size_t)b * nD + j] = 0.0;
         lcqp_cuda_stats r;
         r.ret = out.ret; r.status = out.status; r.iterTotal = out.iterTotal; r.iterOuter = out.iterOuter; r.subproblemIter = out.subIter;
