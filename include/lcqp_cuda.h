@@ -177,6 +177,9 @@ int lcqp_cuda_last_run_ms(lcqp_cuda_handle h, float* solve_kernel_ms, float* tot
 /* launch geometry of the last run: CTAs, dynamic shared memory per CTA, order of the static equality block */
 int lcqp_cuda_last_launch_info(lcqp_cuda_handle h, int* grid, int* smem_bytes, int* equality_rows);
 const char* lcqp_cuda_last_error(lcqp_cuda_handle h);
+/* OSQP flavour: order N of the KKT system, non-zeros of its factor L and levels of a triangular solve (forward +
+ * backward) of the loaded pattern; mode = 1 when the last run used one warp per instance, 0 for one thread per instance */
+int lcqp_cuda_osqp_info(lcqp_cuda_handle h, int* N, int* nnzL, int* levels, int* mode);
 /* fp64 FMA throughput of the device measured by a short probe kernel (TFLOP/s): the denominator bench.py uses for
  * the fp64 SIMT work of the solver */
 int lcqp_cuda_measure_fp64_tflops(int device, double* tflops);

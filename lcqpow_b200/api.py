@@ -36,7 +36,7 @@ EXPORTS = (
     "lcqp_cuda_set_options", "lcqp_cuda_load", "lcqp_cuda_load_device", "lcqp_cuda_load_csc", "lcqp_cuda_set_instance_offset",
     "lcqp_cuda_run", "lcqp_cuda_synchronize", "lcqp_cuda_get_primal", "lcqp_cuda_get_dual",
     "lcqp_cuda_get_stats", "lcqp_cuda_get_device_results", "lcqp_cuda_num_duals", "lcqp_cuda_launch_count",
-    "lcqp_cuda_last_run_ms", "lcqp_cuda_last_launch_info", "lcqp_cuda_last_error", "lcqp_cuda_qp_create", "lcqp_cuda_qp_destroy",
+    "lcqp_cuda_last_run_ms", "lcqp_cuda_last_launch_info", "lcqp_cuda_last_error", "lcqp_cuda_osqp_info", "lcqp_cuda_qp_create", "lcqp_cuda_qp_destroy",
     "lcqp_cuda_qp_set_options", "lcqp_cuda_qp_solve", "lcqp_cuda_qp_get_solution", "lcqp_cuda_measure_fp64_tflops",
 )
 
@@ -106,6 +106,7 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
     lib.lcqp_cuda_last_run_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
     lib.lcqp_cuda_last_launch_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.lcqp_cuda_last_error.argtypes = [vp]
+    lib.lcqp_cuda_osqp_info.argtypes = [vp] + [C.POINTER(C.c_int)] * 4
     lib.lcqp_cuda_last_error.restype = C.c_char_p
     lib.lcqp_cuda_qp_create.argtypes = [C.c_int, C.c_int, dp, dp, C.c_int, C.POINTER(vp)]
     lib.lcqp_cuda_qp_destroy.argtypes = [vp]
@@ -403,6 +404,14 @@ class LCQProblemBatch:
         if rc != 0:
             raise LCQPError(rc, "lcqp_cuda_last_launch_info")
         return g.value, sm.value, me.value
+
+    def osqpInfo(self):
+        """(N, nnz(L), levels of a forward + backward solve, 1 if the last run used one warp per instance) of an OSQP-flavour load."""
+        v = [C.c_int() for _ in range(4)]
+        rc = self.lib.lcqp_cuda_osqp_info(self.h, *[C.byref(t) for t in v])
+        if rc != 0:
+            raise LCQPError(rc, "lcqp_cuda_osqp_info")
+        return tuple(t.value for t in v)
 
     def lastRunMs(self):
         a, b = C.c_float(), C.c_float()

@@ -713,6 +713,7 @@ struct lcqp_cuda_handle_s {
     const double* osqp_arr[LCQP_NUM_ARRAYS] = {};
     unsigned long long osqp_stride[LCQP_NUM_ARRAYS] = {};
     long long osqp_nnzL = 0;
+    int osqp_warp_mode = 0;
     std::string err;
 };
 
@@ -1425,6 +1426,7 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
         fprintf(stderr, "lcqp_cuda (OSQP flavour, %s): %lld warps (%d per SM), N %d, nnz(L) %d, nnz(K) %d, levels %d + %d, workspace %.2f MB/warp, smem %u B/warp, factor flops %lld\n",
                 warp_mode ? "one warp per instance" : "one thread per instance", warps, per_sm, a.S.N, a.S.nnzL, a.S.nnzK, a.S.nflev, a.S.nblev, per_warp / 1.0e6,
                 a.smem_bytes, h->sym ? h->sym->factor_flops : 0ll);
+    h->osqp_warp_mode = warp_mode ? 1 : 0;
     if (warp_mode) lcqp_osqpw_kernel<<<(unsigned)warps, 32, a.smem_bytes, stream>>>(a);
     else lcqp_osqp_kernel<<<(unsigned)warps, 32, a.smem_bytes, stream>>>(a);
     h->launches++;
@@ -1604,6 +1606,17 @@ int lcqp_cuda_last_launch_info(lcqp_cuda_handle h, int* grid, int* smem_bytes, i
 }
 
 const char* lcqp_cuda_last_error(lcqp_cuda_handle h) { return h ? h->err.c_str() : "bad handle"; }
+
+int lcqp_cuda_osqp_info(lcqp_cuda_handle h, int* N, int* nnzL, int* levels, int* mode)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!h->osqp_ready) return fail(h, LCQP_CUDA_NOT_LOADED, "no OSQP-flavour load");
+    if (N) *N = h->symdev.N;
+    if (nnzL) *nnzL = h->symdev.nnzL;
+    if (levels) *levels = h->symdev.nflev + h->symdev.nblev;
+    if (mode) *mode = h->osqp_warp_mode;
+    return LCQP_CUDA_OK;
+}
 
 int lcqp_cuda_measure_fp64_tflops(int device, double* tflops)
 {
