@@ -8,6 +8,10 @@ Workloads, chosen by --config:
       x_ref per instance), stationarityTolerance = 1e-2 as the example sets it; 2^20 instances per GPU per step.
   c5: random dense LCQPs (n=64, 32 pairs, 16 constraints), every matrix per instance; 131072 per GPU per step.
   c3: examples/example_data (nV=151, nC=50, nComp=100, box bounds) replicated with perturbed g / lbA=ubA / ub.
+  c4: synthetic sparse LCQPs (n=1000, 500 pairs, 300 constraints, banded Q; one sparsity pattern, per-instance values)
+      through the CSC door and the OSQP-ADMM flavour (QPSolver::OSQP_SPARSE semantics); 4096 per GPU per step.  A step
+      is minutes long (one warp per instance, thousands of ADMM iterations each): --warmup is honoured as given (>= 1).
+--flavour osqp runs c2 / c5 through the OSQP restatement as well (c4 always does).
 perturbStep is on (the default of the reference's Options).
 
 One "step" = one pass of the hot path over one batch of `--batch` instances per GPU (weak scaling).
@@ -76,12 +80,24 @@ class Config:
             self.ref_solver_shipped = 1   # QPOASES_SPARSE (examples/solve_lcqp_from_file.cpp:128)
             self.ref_solver_parity = 0
             self.cpu_per_core = 16
+        elif name == "c4":
+            self.nV, self.nC, self.nComp = 1000, 300, 500
+            self.over = {}
+            self.default_batch = 4096
+            self.workload = "C4 sparse banded LCQPs (n=1000, 500 pairs, nC=300), one pattern, per-instance values, CSC door, OSQP-ADMM flavour"
+            self.ref_solver_shipped = 2
+            self.ref_solver_parity = 2
+            self.cpu_per_core = 2
         else:
             raise SystemExit("unknown --config " + name)
+        self.sparse = (name == "c4")
 
-    def generate(self, n, lo=0, hi=None):
+    def generate(self, n, lo=0, hi=None, dense=True):
         from lcqpow_b200 import problems as P
         hi = n if hi is None else hi
+        if self.name == "c4":
+            sb = P.sparse_banded_batch(hi - lo, lo=lo)
+            return sb.to_dense(0, hi - lo) if dense else sb
         if self.name == "c2":
             return P.circle_batch_fast(n).slice(lo, hi)
         if self.name == "c5":
@@ -290,6 +306,61 @@ def parity_subset(cfg, prob_cls, L, pb, batch, lo_global, n_check, device, seed=
             "criterion": "ReturnValue, stationarity type, iterOuter, iterTotal identical; x within 1e-6 relative; perturbStep off"}
 
 
+def parity_subset_osqp(cfg, L, batch, lo_global, n_check, device):
+    """OSQP flavour: the first `n_check` instances of this rank's batch, perturbStep off and adaptive_rho_interval = 25 on
+    both sides (the reference's default interval is wall-clock driven), against the reference's OSQP_SPARSE run.  Bar of
+    tests/test_osqp_flavour.py: an instance the reference solves must be reproduced with identical ReturnValue,
+    stationarity type, iteration counts (ADMM iterations included) and x to 1e-6; one it fails must fail here too."""
+    kind = cpu_kind()
+    if kind != "reference":
+        return {"n": 0, "mismatches": None, "error": "the OSQP flavour is checked against oracle/_ref only"}
+    n = min(n_check, batch)
+    src = cfg.generate(lo_global + n, lo_global, lo_global + n, dense=False) if cfg.sparse else cfg.generate(lo_global + n, lo_global, lo_global + n).normalised()
+    prob = L.LCQProblemBatch(cfg.nV, cfg.nC, cfg.nComp, n, device=device)
+    o = L.Options()
+    o.setPerturbStep(False)
+    for k, v in cfg.over.items():
+        getattr(o, "set" + k[0].upper() + k[1:])(v)
+    o.setOSQPADMM(True, adaptive_rho_interval=25)
+    prob.setOptions(o)
+    if cfg.sparse:
+        assert prob.loadCSC(src.Q, src.g, src.L, src.R, A=src.A, lbA=src.lbA, ubA=src.ubA, batch=n, shared=tuple(src.shared)) == 0, prob._err()
+        dense = src.to_dense(0, n).normalised()
+    else:
+        assert prob.loadBatch(src) == 0, prob._err()
+        dense = src
+    prob.runSolver()
+    x, st = prob.getPrimalSolution(), prob.getOutputStatistics()
+    prob.close()
+    import dataclasses
+    cores = min(len(os.sched_getaffinity(0)), n)
+    chunks = np.array_split(np.arange(n), cores)
+
+    def solve_chunk(ch):
+        kw2 = {}
+        for f in L.api.FIELDS:
+            a = getattr(dense, f)
+            kw2[f] = None if a is None else (a if f in dense.shared else np.ascontiguousarray(a[ch]))
+        s2 = dataclasses.replace(dense, batch=len(ch), **kw2)
+        return _REFLIB.solve_batch(s2, _REFLIB.default_options(perturbStep=0, qpSolver=2, osqp_adaptive_rho_interval=25, **cfg.over))
+    global _PARITY_JOB
+    _PARITY_JOB = solve_chunk
+    with mp.get_context("fork").Pool(cores) as pool:
+        outs = pool.map(_parity_call, [c for c in chunks if len(c)])
+    rx = np.concatenate([o.x for o in outs]); rres = np.concatenate([o.res for o in outs])
+    mism = 0
+    for b in range(n):
+        if rres["ret"][b] == 0:
+            same = all(rres[f][b] == st[f][b] for f in ("ret", "status", "iterOuter", "iterTotal", "subproblemIter"))
+            same = same and np.abs(rx[b] - x[b]).max() <= 1e-6 * max(1.0, np.abs(rx[b]).max())
+        else:
+            same = st["ret"][b] != 0
+        mism += (not same)
+    return {"n": int(n), "mismatches": int(mism), "checker": kind, "reference_solved": int((rres["ret"] == 0).sum()),
+            "criterion": "instances the reference's OSQP run solves: ReturnValue, stationarity type, iterOuter, iterTotal, ADMM iterations "
+                         "identical and x within 1e-6 relative; instances it fails: a failure code here too; perturbStep off, adaptive_rho_interval 25"}
+
+
 _PARITY_JOB = None
 
 
@@ -303,7 +374,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c2", "c5", "c3"])
+    ap.add_argument("--config", default="c2", choices=["c2", "c5", "c3", "c4"])
+    ap.add_argument("--flavour", default="exact", choices=["exact", "osqp"], help="QP subsolver flavour: the exact-vertex solver "
+                    "(qpOASES semantics) or the OSQP restatement (ADMM + polish); c4 always runs the latter")
     ap.add_argument("--batch", type=int, default=0, help="instances per GPU per step (0: the configuration's own size: "
                     "2^20 for c2, 2^17 for c5, 10000 for c3)")
     ap.add_argument("--cpu-per-core", type=int, default=0, help="instances per host process in the CPU baseline")
@@ -312,6 +385,11 @@ def main():
     ap.add_argument("--perturb", type=int, default=1)
     args = ap.parse_args()
     cfg = Config(args.config)
+    osqp = cfg.sparse or args.flavour == "osqp"
+    if osqp:
+        cfg.ref_solver_parity = 2
+        if not cfg.sparse:
+            cfg.workload += ", OSQP-ADMM flavour"
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -339,61 +417,91 @@ def main():
         for k, v in cfg.over.items():
             getattr(o, "set" + k[0].upper() + k[1:])(v)
         o.setPerturbStep(bool(args.perturb))
+        if osqp:
+            o.setOSQPADMM(True)
         return o
 
     batch = args.batch if args.batch > 0 else cfg.default_batch
 
     # ---- inputs: the same family on every rank, instances [rank*batch, (rank+1)*batch) ------------
     from lcqpow_b200 import sharding
+    import ctypes as C
     lo, hi = sharding.shard_range(batch * world, rank, world)
-    pb = cfg.generate(batch * world, lo, hi).normalised()
-    shared = tuple(pb.shared)
     prob = L.LCQProblemBatch(NV, NC, NCOMP, batch, device=local_rank)
     assert prob.setOptions(make_options()) == 0
     prob.setInstanceOffset(lo)   # perturbStep draws are keyed by the global instance index
-
-    # device-resident copies (torch is only the allocator here)
-    dev_t = {}
-    for f in L.api.FIELDS:
-        a = getattr(pb, f)
-        if a is not None:
-            dev_t[f] = torch.from_numpy(a).to(dev)
-    ptrs = {f: t.data_ptr() for f, t in dev_t.items()}
-    # pinned host copies of the per-instance inputs and pinned result buffers for the e2e leg
-    pin = {}
-    for f in L.api.FIELDS:
-        a = getattr(pb, f)
-        if a is None:
-            pin[f] = None
-        elif f in shared:
-            pin[f] = a
-        else:
-            t = torch.from_numpy(a).pin_memory()
-            pin[f] = t.numpy()
-            pin["_keep_" + f] = t
     nD = NV + NC + 2 * NCOMP
     x_pin_t = torch.empty((batch, NV), dtype=torch.float64).pin_memory()
     y_pin_t = torch.empty((batch, nD), dtype=torch.float64).pin_memory()
     st_pin_t = torch.empty((batch, L.api.STATS_DTYPE.itemsize), dtype=torch.uint8).pin_memory()
-    h2d = sum(pin[f].nbytes for f in L.api.FIELDS if pin[f] is not None and f not in shared)
     d2h = x_pin_t.numel() * 8 + y_pin_t.numel() * 8 + st_pin_t.numel()
-
     stream = torch.cuda.current_stream(dev)
 
-    def step_resident():
-        rc = prob.loadDevicePointers(ptrs, batch, shared)
-        assert rc == 0, rc
-        prob.runSolver(stream=stream.cuda_stream, sync=False)
-
-    import ctypes as C
-
-    def step_e2e():
-        rc = prob.loadLCQP(**{f: pin[f] for f in L.api.FIELDS}, batch=batch, shared=shared)
-        assert rc == 0, rc
-        prob.runSolver(stream=0, sync=False)
+    def fetch_results():
         for fn, buf in ((prob.lib.lcqp_cuda_get_primal, x_pin_t), (prob.lib.lcqp_cuda_get_dual, y_pin_t), (prob.lib.lcqp_cuda_get_stats, st_pin_t)):
             rc = fn(prob.h, C.c_void_p(buf.data_ptr()))
             assert rc == 0, rc
+
+    if cfg.sparse:
+        # the CSC door takes host arrays; a load converts and uploads them, the run works on the resident copy
+        pb = cfg.generate(batch * world, lo, hi, dense=False)
+        shared = tuple(pb.shared)
+
+        def load_csc():
+            rc = prob.loadCSC(pb.Q, pb.g, pb.L, pb.R, A=pb.A, lbA=pb.lbA, ubA=pb.ubA, batch=batch, shared=shared)
+            assert rc == 0, prob._err()
+
+        h2d = sum(t[2].nbytes for f, t in (("Q", pb.Q), ("L", pb.L), ("R", pb.R), ("A", pb.A)) if t is not None and f not in shared)
+        h2d += sum(a.nbytes for f, a in (("g", pb.g), ("lbA", pb.lbA), ("ubA", pb.ubA)) if a is not None and f not in shared)
+        load_csc()
+
+        def step_resident():
+            prob.runSolver(stream=stream.cuda_stream, sync=False)
+
+        def step_e2e():
+            load_csc()
+            prob.runSolver(stream=0, sync=False)
+            fetch_results()
+    else:
+        pb = cfg.generate(batch * world, lo, hi).normalised()
+        shared = tuple(pb.shared)
+        # device-resident copies (torch is only the allocator here)
+        dev_t = {}
+        for f in L.api.FIELDS:
+            a = getattr(pb, f)
+            if a is not None:
+                dev_t[f] = torch.from_numpy(a).to(dev)
+        ptrs = {f: t.data_ptr() for f, t in dev_t.items()}
+        # pinned host copies of the per-instance inputs for the e2e leg
+        pin = {}
+        for f in L.api.FIELDS:
+            a = getattr(pb, f)
+            if a is None:
+                pin[f] = None
+            elif f in shared:
+                pin[f] = a
+            else:
+                t = torch.from_numpy(a).pin_memory()
+                pin[f] = t.numpy()
+                pin["_keep_" + f] = t
+        h2d = sum(pin[f].nbytes for f in L.api.FIELDS if pin[f] is not None and f not in shared)
+
+        if osqp:
+            # the OSQP flavour analyses the pattern at load time on the host: load once, the runs work on the resident copy
+            rc = prob.loadLCQP(**{f: pin[f] for f in L.api.FIELDS}, batch=batch, shared=shared)
+            assert rc == 0, prob._err()
+
+        def step_resident():
+            if not osqp:
+                rc = prob.loadDevicePointers(ptrs, batch, shared)
+                assert rc == 0, rc
+            prob.runSolver(stream=stream.cuda_stream, sync=False)
+
+        def step_e2e():
+            rc = prob.loadLCQP(**{f: pin[f] for f in L.api.FIELDS}, batch=batch, shared=shared)
+            assert rc == 0, rc
+            prob.runSolver(stream=0, sync=False)
+            fetch_results()
 
     def barrier():
         if world > 1:
@@ -401,7 +509,8 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident leg ------------------------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
+    n_warm = max(args.warmup, 1) if cfg.sparse else max(args.warmup, 3)
+    for _ in range(n_warm):
         step_resident()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -427,7 +536,7 @@ def main():
     grid, smem_b, mE = prob.lastLaunchInfo()
 
     # ---- e2e leg ------------------------------------------------------------------------------------
-    for _ in range(2):
+    for _ in range(1 if cfg.sparse else 2):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
@@ -445,7 +554,10 @@ def main():
     par = None
     if args.parity > 0 and rank == 0:
         try:
-            par = parity_subset(cfg, L.LCQProblemBatch, L, pb, batch, lo, args.parity, local_rank)
+            if osqp:
+                par = parity_subset_osqp(cfg, L, batch, lo, min(args.parity, 32 if cfg.sparse else 256), local_rank)
+            else:
+                par = parity_subset(cfg, L.LCQProblemBatch, L, pb, batch, lo, args.parity, local_rank)
         except Exception as ex:  # the checker is absent on this box: say so, do not fail the measurement
             par = {"n": 0, "mismatches": None, "error": repr(ex)}
 
@@ -453,7 +565,7 @@ def main():
         nb = batch * world
         ret_hist = {int(k): int(v) for k, v in zip(*np.unique(st["ret"], return_counts=True))}
         # the metric counts SOLVED LCQPs (terminal ReturnValue SUCCESSFUL_RETURN); every step solves the same batch
-        if cfg.name != "c3" and n_solved < 0.5 * nb:
+        if cfg.name != "c3" and n_solved < (0.25 if osqp else 0.5) * nb:
             raise SystemExit(f"bench.py: only {n_solved:.0f} of {nb} instances were solved -- the CUDA path is broken, "
                              "refusing to report a throughput")
         counted = n_solved if cfg.name != "c3" else float(nb)   # c3: the reference ends the perturbed family with 201 too
@@ -462,7 +574,21 @@ def main():
         units_per_launch = n_units / world   # explicit-inverse solves (homotopy steps + polish passes) of one launch on one GPU
         fp64 = C.c_double(0.0)
         prob.lib.lcqp_cuda_measure_fp64_tflops(local_rank, C.byref(fp64))
-        if cfg.name == "c5":
+        if osqp:
+            # SURVEY.md 8(d) row "OSQP-ADMM iteration": HBM bound, bytes per ADMM iteration of one instance =
+            # 16 nnz(L) (values + indices of the factor, forward and backward sweep read it once each as 8 + 8)
+            # + 8 N (the KKT right-hand side / solution) + 8 (3n + 5m) (x, x_prev, x_tilde; z, z_prev, z_tilde, y, rho)
+            oN, onnzL, olev, omode = prob.osqpInfo()
+            m = NC + 2 * NCOMP
+            bytes_per_it = 16.0 * onnzL + 8.0 * oN + 8.0 * (3 * NV + 5 * m)
+            n_admm = float(st["admmIters"].sum())
+            achieved = bytes_per_it * n_admm / (k_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s", "frac": achieved / hbm_gbs, "traffic": None,
+                    "bytes_per_unit": bytes_per_it, "unit_def": "one ADMM iteration of one instance: 16 nnz(L) + 8 N + 8 (3n + 5m) bytes (SURVEY.md 8d)",
+                    "kkt_order": oN, "nnz_L": onnzL, "levels_per_solve": olev, "admm_iters_per_lcqp": n_admm / batch,
+                    "factorisations_per_lcqp": float(st["kktSolves"].sum()) / batch,
+                    "launch_mode": "one warp per instance" if omode else "one thread per instance"}
+        elif cfg.name == "c5":
             # SURVEY.md 8(d) row "Per-instance dense KKT in SMEM": HBM bound, 8 (n^2 + m n + 2n + 2m + n) in + 8 (n + m + 4) out
             m = NC + 2 * NCOMP
             bytes_per_lcqp = 8.0 * (NV * NV + m * NV + 2 * NV + 2 * m + NV) + 8.0 * (NV + m + 4)
@@ -484,15 +610,15 @@ def main():
                     roof["traffic"] = float(tj["dram_bytes_per_lcqp"]) * batch
             except Exception:
                 pass
-        roof.update({"kernel": "lcqp_pas_kernel", "kernel_ms": k_ms, "units_per_launch": units_per_launch,
+        roof.update({"kernel": ("lcqp_osqpw_kernel" if (osqp and roof.get("launch_mode", "").startswith("one warp")) else "lcqp_osqp_kernel") if osqp else "lcqp_pas_kernel", "kernel_ms": k_ms, "units_per_launch": units_per_launch,
                      "peak_source": f"{peak_src} (MEASURED_PEAKS.json); the arithmetic is fp64 SIMT -- see `fp64` for the pipe it runs on",
                      # the work actually done, against the pipes it runs on (model counts of DESIGN.md section 5)
                      "fp64": {"peak_tflops_measured": fp64.value,
                               "note": "fp64 FMA probe of this device (lcqp_cuda_measure_fp64_tflops); DESIGN.md 5 has the MAC model"}})
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": cfg.workload, "instances_per_gpu_per_step": batch, "perturbStep": bool(args.perturb),
+                "config": {"workload": cfg.workload, "instances_per_gpu_per_step": batch, "perturbStep": bool(args.perturb), "warmup_steps": n_warm,
                            "parallelism": f"instance-sharded x{world}, no collective on the data path",
                            "l2": "inputs+outputs per step exceed L2 (%.0f MB)" % ((h2d + d2h) / 1e6), **cfg.over},
                 "clocks": clocks, "gpu_launches": int(launches),
@@ -503,7 +629,7 @@ def main():
                 "mean_subproblem_iters": n_sub / nb, "kkt_solves_per_lcqp": n_units / nb,
                 "launch": {"groups": grid, "smem_bytes_per_cta": smem_b, "eliminated_equality_rows": mE},
                 "parity_subset": par}
-        if cfg.name == "c2":
+        if cfg.name == "c2" and not osqp:
             line["instance0_matches_shipped_solution"] = bool(abs(x[0, 0] - 0.181110968) < 1e-6 and abs(x[0, 1] + 0.983483383) < 1e-6 and st["status"][0] == 4)
         if not args.no_cpu_baseline and world == 1:
             kind = cpu_kind()
