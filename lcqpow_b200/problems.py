@@ -250,10 +250,14 @@ def dense_random_batch(batch: int, n: int = 64, nComp: int = 32, nC: int = 16, s
                      shared=frozenset(("L", "R")), name=f"dense_n{n}")
 
 
-def example_data_batch(data: dict, batch: int = 1, seed0: int = 30000) -> LCQPBatch:
+def example_data_batch(data: dict, batch: int = 1, seed0: int = 30000, perturb_ub: bool = False) -> LCQPBatch:
     """Config C3: examples/example_data (nV=151, nC=50, nComp=100) replicated with
-    perturbed g / lbA=ubA / finite ub; instance 0 unperturbed.  ``data`` maps the file stems
-    (Q,g,L,R,lbL,ubL,lbR,ubR,A,lbA,ubA,lb,ub,x0) to arrays (see tests/golden/example_data.npz)."""
+    perturbed g and constraint bounds lbA=ubA (each entry scaled by 1 + 0.05 N(0,1)); instance 0 unperturbed.
+    ``data`` maps the file stems (Q,g,L,R,lbL,ubL,lbR,ubR,A,lbA,ubA,lb,ub,x0) to arrays (tests/golden/example_data.npz).
+
+    ``perturb_ub`` also scales the finite box bounds ub: that breaks the problem -- the reference (qpOASES) runs every
+    such instance to MAX_PENALTY_PARAMETER_REACHED -- and is kept as the "terminal failure" family of the tests; with
+    the box bounds as shipped the reference solves every instance of the family."""
     nV, nC, nComp = 151, 50, 100
     g = np.tile(np.asarray(data["g"], dtype=np.float64), (batch, 1))
     lbA = np.tile(np.asarray(data["lbA"], dtype=np.float64), (batch, 1))
@@ -263,7 +267,9 @@ def example_data_batch(data: dict, batch: int = 1, seed0: int = 30000) -> LCQPBa
         g[b] *= 1.0 + 0.05 * rng.standard_normal(nV)
         lbA[b] *= 1.0 + 0.05 * rng.standard_normal(nC)
         fin = np.isfinite(ub[b])
-        ub[b, fin] *= 1.0 + 0.05 * rng.standard_normal(int(fin.sum()))
+        du = 1.0 + 0.05 * rng.standard_normal(int(fin.sum()))   # (drawn either way: the same g / lbA in both families)
+        if perturb_ub:
+            ub[b, fin] *= du
     kw = {k: np.asarray(data[k], dtype=np.float64) for k in ("Q", "L", "R", "lbL", "ubL", "lbR", "ubR", "A", "lb", "x0")}
     return LCQPBatch(nV=nV, nC=nC, nComp=nComp, batch=batch, g=g, lbA=lbA, ubA=lbA.copy(), ub=ub,
                      shared=frozenset(kw.keys()), name="example_data", **kw)

@@ -29,7 +29,8 @@ def family_cases(data):
         "dense_bench": (P.dense_random_batch(256), {}, pyref.QPOASES_DENSE),
         "circle_N20": (P.circle_batch(16, N=20), {"stationarityTolerance": 10e-3}, pyref.QPOASES_DENSE),
         "dense_n32": (P.dense_random_batch(32, n=32, nComp=16, nC=8), {}, pyref.QPOASES_DENSE),
-        "example_data_family": (P.example_data_batch(data, 17), {}, pyref.QPOASES_DENSE),
+        "example_data_family": (P.example_data_batch(data, 17, perturb_ub=True), {}, pyref.QPOASES_DENSE),
+        "example_data_bounds": (P.example_data_batch(data, 64), {}, pyref.QPOASES_SPARSE),
     }
 
 

@@ -4,7 +4,7 @@ the C ABI on the B200)."""
 import numpy as np
 import pytest
 
-from conftest import check_against_golden, check_family, family_cases, golden_cases
+from conftest import check_against_golden, check_family, check_family_regularised, family_cases, golden_cases
 
 
 @pytest.fixture(scope="module")
@@ -44,6 +44,16 @@ def test_emu_example_data_family(emu, families, example_data):
     s = emu.solve_batch(pb.slice(0, 4), emu.default_options(perturbStep=0, **over))
     check_family("example_data_family", s.x[:1], {k: s.res[k][:1] for k in ("ret", "status", "iterOuter", "iterTotal")}, families, subset=[0])
     assert (s.res["ret"][1:] != 0).all() and (families["example_data_family/ret"][1:4] != 0).all()
+
+
+def test_emu_example_data_bounds_family(emu, families, example_data):
+    """Config C3 as benchmarked: example_data with perturbed g and lbA = ubA (box bounds as shipped).  The reference solves
+    all 64 instances; so does the device code, with the reference's ReturnValue, stationarity type, penalty updates and x
+    on every instance and its total iteration count on at least 9 of 10."""
+    pb, over = family_cases(example_data)["example_data_bounds"]
+    s = emu.solve_batch(pb.slice(0, 32), emu.default_options(perturbStep=0, **over))
+    off = check_family_regularised("example_data_bounds", s.x, s.res, families, subset=range(32))
+    assert off <= 3, off
 
 
 @pytest.mark.parametrize("perturb", [0, 1])

@@ -63,6 +63,16 @@ def test_cuda_example_data_family(families, example_data):
     assert (st["ret"][1:] != 0).all()
 
 
+def test_cuda_example_data_bounds_family(families, example_data):
+    """Config C3 as benchmarked (example_data with perturbed g and lbA = ubA): all 64 instances end S-stationary with the
+    reference's penalty updates and x; the total iteration count is the reference's on at least 9 of 10 instances."""
+    from conftest import check_family_regularised
+    pb, over = family_cases(example_data)["example_data_bounds"]
+    x, y, st, _ = _solve_cuda(pb, over)
+    off = check_family_regularised("example_data_bounds", x, st, families)
+    assert off <= 6, off
+
+
 def test_stationarity_classification_covers_every_type(golden, example_data):
     """W / C / M / S (LCQProblem.cpp:1412-1453): the four sign patterns of the pair's multipliers, duals included."""
     want = {"S": 4, "M": 3, "C": 2, "W": 1}
