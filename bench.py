@@ -575,6 +575,19 @@ def main():
         units_per_launch = n_units / world   # explicit-inverse solves (homotopy steps + polish passes) of one launch on one GPU
         fp64 = C.c_double(0.0)
         prob.lib.lcqp_cuda_measure_fp64_tflops(local_rank, C.byref(fp64))
+        # the work the parametric active-set kernel actually did in its last launch (counted by the kernel: fp64
+        # multiply-adds of its dense products and the bytes they read / write -- per-instance inverse, Tt columns and
+        # prepared operators, all L2 resident), against the measured fp64 pipe and the measured L2 read bandwidth
+        work = None
+        macs, wbytes, l2gbs = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+        if not osqp and prob.lib.lcqp_cuda_last_work(prob.h, C.byref(macs), C.byref(wbytes)) == 0 and macs.value > 0:
+            prob.lib.lcqp_cuda_measure_l2_gbs(local_rank, C.byref(l2gbs))
+            work = {"fp64_macs_per_lcqp": macs.value / batch, "l2_bytes_per_lcqp": wbytes.value / batch,
+                    "fp64_achieved_tflops": 2.0 * macs.value / (k_ms * 1e-3) / 1e12,
+                    "fp64_frac": (2.0 * macs.value / (k_ms * 1e-3) / 1e12) / fp64.value if fp64.value > 0 else None,
+                    "l2_achieved_gbs": wbytes.value / (k_ms * 1e-3) / 1e9, "l2_peak_gbs_measured": l2gbs.value,
+                    "l2_frac": (wbytes.value / (k_ms * 1e-3) / 1e9) / l2gbs.value if l2gbs.value > 0 else None,
+                    "note": "dense products of the active-set kernel counted on the device (lcqp_cuda_last_work): algorithmic minimum, rank 0's launch"}
         if osqp:
             # SURVEY.md 8(d) row "OSQP-ADMM iteration": HBM bound, bytes per ADMM iteration of one instance =
             # 16 nnz(L) (values + indices of the factor, forward and backward sweep read it once each as 8 + 8)
@@ -615,7 +628,8 @@ def main():
                      "peak_source": f"{peak_src} (MEASURED_PEAKS.json); the arithmetic is fp64 SIMT -- see `fp64` for the pipe it runs on",
                      # the work actually done, against the pipes it runs on (model counts of DESIGN.md section 5)
                      "fp64": {"peak_tflops_measured": fp64.value,
-                              "note": "fp64 FMA probe of this device (lcqp_cuda_measure_fp64_tflops); DESIGN.md 5 has the MAC model"}})
+                              "note": "fp64 FMA probe of this device (lcqp_cuda_measure_fp64_tflops); DESIGN.md 5 has the MAC model"},
+                     "work": work})
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
                 "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",

@@ -183,6 +183,13 @@ int lcqp_cuda_osqp_info(lcqp_cuda_handle h, int* N, int* nnzL, int* levels, int*
 /* fp64 FMA throughput of the device measured by a short probe kernel (TFLOP/s): the denominator bench.py uses for
  * the fp64 SIMT work of the solver */
 int lcqp_cuda_measure_fp64_tflops(int device, double* tflops);
+/* read bandwidth of the L2 (GB/s, 16-byte loads of a 48 MB buffer by every SM): the denominator for the solver's
+ * L2-resident streams (the per-instance inverse of the working-set system and the shared operand Tt) */
+int lcqp_cuda_measure_l2_gbs(int device, double* gbs);
+/* work of the last run of the parametric active-set kernel, summed over the batch: fp64 multiply-adds of its dense
+ * products (per-instance inverse, Tt columns, prepared operators) and the bytes those products read and write --
+ * the algorithmic minimum, counted by the kernel itself.  Waits for the run. */
+int lcqp_cuda_last_work(lcqp_cuda_handle h, double* fp64_macs, double* bytes);
 
 /* ---- (2) plugin door: one convex QP, SubsolverBase semantics ---------------------------------- */
 /* SubsolverQPOASES(int nV, int nC, double* Q, double* A) (SubsolverQPOASES.hpp:44-47): nCtot rows of

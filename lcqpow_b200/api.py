@@ -38,6 +38,7 @@ EXPORTS = (
     "lcqp_cuda_get_stats", "lcqp_cuda_get_device_results", "lcqp_cuda_num_duals", "lcqp_cuda_launch_count",
     "lcqp_cuda_last_run_ms", "lcqp_cuda_last_launch_info", "lcqp_cuda_last_error", "lcqp_cuda_osqp_info", "lcqp_cuda_qp_create", "lcqp_cuda_qp_destroy",
     "lcqp_cuda_qp_set_options", "lcqp_cuda_qp_solve", "lcqp_cuda_qp_get_solution", "lcqp_cuda_measure_fp64_tflops",
+    "lcqp_cuda_measure_l2_gbs", "lcqp_cuda_last_work",
 )
 
 
@@ -114,6 +115,8 @@ def load_library(build_if_missing: bool = False) -> C.CDLL:
     lib.lcqp_cuda_qp_solve.argtypes = [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [dp] * 7
     lib.lcqp_cuda_qp_get_solution.argtypes = [vp, dp, dp]
     lib.lcqp_cuda_measure_fp64_tflops.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.lcqp_cuda_measure_l2_gbs.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    lib.lcqp_cuda_last_work.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
         f = getattr(lib, name)
         if name not in ("lcqp_cuda_default_options", "lcqp_cuda_launch_count", "lcqp_cuda_last_error"):

@@ -219,6 +219,7 @@ struct PasArgs {
     lcqp_cuda_stats* stats;
     unsigned int* counter;
     int* fallback_flag;          // set when an instance's reduced Hessian is not positive definite
+    unsigned long long* work;    // [2]: fp64 multiply-adds and bytes of the run's dense products (pas::PQP::n_mac, n_byte)
     unsigned long long instance_offset;
 };
 
@@ -335,6 +336,8 @@ __global__ void __launch_bounds__(kPasCtaThreads, 1) lcqp_pas_kernel(const __gri
             st.kktSolves = (int)s.n_solve;
             st.rhoOpt = out.rhoOpt; st.admmIters = 0.0;
             a.stats[b] = st;
+            atomicAdd(a.work, (unsigned long long)s.n_mac);
+            atomicAdd(a.work + 1, (unsigned long long)s.n_byte);
             if (!ok) atomicExch(a.fallback_flag, 1);
         }
     }
@@ -698,6 +701,7 @@ struct lcqp_cuda_handle_s {
     signed char* eqmask = nullptr;
     size_t eqmask_cap = 0;
     int* fallback_flag = nullptr;
+    unsigned long long* work = nullptr;   // device, [2] (see PasArgs::work)
     int* fallback_host = nullptr;         // pinned
     bool pas_ready = false;               // prepared for the current load
     bool use_legacy = false;              // reduced Hessian not positive definite: the regularised solver runs
@@ -815,6 +819,7 @@ int lcqp_cuda_create(int nV, int nC, int nComp, int batch_capacity, int device, 
               cudaMalloc(&h->pas_mats, sizeof(pas::PMats)) == cudaSuccess &&
               cudaMallocHost(&h->pas_host, sizeof(pas::PMats)) == cudaSuccess &&
               cudaMalloc(&h->fallback_flag, sizeof(int)) == cudaSuccess &&
+              cudaMalloc(&h->work, 2 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaMallocHost(&h->fallback_host, sizeof(int)) == cudaSuccess &&
               cudaStreamCreateWithFlags(&h->load_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&h->ev0) == cudaSuccess && cudaEventCreate(&h->ev1) == cudaSuccess &&
@@ -833,7 +838,7 @@ int lcqp_cuda_destroy(lcqp_cuda_handle h)
     cudaFree(h->shared_store); cudaFree(h->shared_mats); cudaFree(h->shared_raw);
     cudaFree(h->pool_i); cudaFree(h->pool_d); cudaFree(h->pool_used); cudaFree(h->workspace);
     if (h->host_mats) cudaFreeHost(h->host_mats);
-    cudaFree(h->pas_mats); cudaFree(h->pas_store); cudaFree(h->eqmask); cudaFree(h->fallback_flag);
+    cudaFree(h->pas_mats); cudaFree(h->pas_store); cudaFree(h->eqmask); cudaFree(h->fallback_flag); cudaFree(h->work);
     cudaFree(h->sym_ints);
     for (int k = 0; k < 4; k++) cudaFree(h->csc_vals[k]);
     delete h->sym;
@@ -1264,6 +1269,7 @@ static void pas_fill_args(lcqp_cuda_handle h, PasArgs& a)
     a.pool.ibuf = h->pool_i; a.pool.dbuf = h->pool_d; a.pool.icap = (int)h->pool_cap; a.pool.dcap = (int)h->pool_cap; a.pool.used = h->pool_used;
     a.xout = h->xout; a.yout = h->yout; a.stats = h->stats; a.counter = h->counter;
     a.fallback_flag = h->fallback_flag;
+    a.work = h->work;
     a.instance_offset = h->instance_offset;
 }
 
@@ -1483,6 +1489,7 @@ static int run_pas(lcqp_cuda_handle h, cudaStream_t stream)
     a.workspace = h->workspace;
     CK(cudaMemsetAsync(h->counter, 0, sizeof(unsigned int), stream), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaMemsetAsync(h->fallback_flag, 0, sizeof(int), stream), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaMemsetAsync(h->work, 0, 2 * sizeof(unsigned long long), stream), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
     if (getenv("LCQP_CUDA_VERBOSE"))
@@ -1615,6 +1622,70 @@ int lcqp_cuda_osqp_info(lcqp_cuda_handle h, int* N, int* nnzL, int* levels, int*
     if (nnzL) *nnzL = h->symdev.nnzL;
     if (levels) *levels = h->symdev.nflev + h->symdev.nblev;
     if (mode) *mode = h->osqp_warp_mode;
+    return LCQP_CUDA_OK;
+}
+
+int lcqp_cuda_last_work(lcqp_cuda_handle h, double* fp64_macs, double* bytes)
+{
+    if (!h) return LCQP_CUDA_BAD_HANDLE;
+    if (!h->ran || h->use_legacy || !h->pas_ready || (h->opts.qpSolver == 2 && h->opts.osqp_admm))
+        return fail(h, LCQP_CUDA_NOT_LOADED, "the work counters belong to a run of the parametric active-set kernel");
+    CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
+    CK(cudaStreamSynchronize(h->last_stream), LCQP_CUDA_LAUNCH_FAILED);
+    unsigned long long v[2] = {0, 0};
+    CK(cudaMemcpy(v, h->work, sizeof(v), cudaMemcpyDeviceToHost), LCQP_CUDA_LAUNCH_FAILED);
+    if (fp64_macs) *fp64_macs = (double)v[0];
+    if (bytes) *bytes = (double)v[1];
+    return LCQP_CUDA_OK;
+}
+
+// every thread sums 16-byte loads of a buffer that fits the L2 (volatile: the loads are issued, eight in flight)
+__global__ void l2_read_probe_kernel(const double2* buf, size_t n16, int rounds, double* out)
+{
+    double acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < rounds; r++) {
+        size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+        for (; i + 7 * stride < n16; i += 8 * stride) {
+            double2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) asm volatile("ld.volatile.global.v2.f64 {%0, %1}, [%2];" : "=d"(v[k].x), "=d"(v[k].y) : "l"(buf + i + k * stride));
+#pragma unroll
+            for (int k = 0; k < 8; k++) acc += v[k].x + v[k].y;
+        }
+    }
+    if (acc == 1.2345e-300) out[0] = acc;
+}
+
+int lcqp_cuda_measure_l2_gbs(int device, double* gbs)
+{
+    if (!gbs) return LCQP_CUDA_BAD_ARGUMENT;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LCQP_CUDA_NO_DEVICE;
+    const size_t bytes = 48ull << 20;   // well inside the 126 MB L2 (each half of it holds the buffer)
+    const size_t n16 = bytes / 16;
+    double2* buf = nullptr;
+    double* out = nullptr;
+    if (cudaMalloc(&buf, bytes) != cudaSuccess || cudaMalloc(&out, 8) != cudaSuccess) { cudaGetLastError(); cudaFree(buf); return LCQP_CUDA_OUT_OF_MEMORY; }
+    cudaMemset(buf, 0, bytes);
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, rounds = 16;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    l2_read_probe_kernel<<<blocks, threads>>>(buf, n16, 2, out);   // brings the buffer into the L2
+    float best = 1e30f;
+    for (int r = 0; r < 3; r++) {
+        cudaEventRecord(e0);
+        l2_read_probe_kernel<<<blocks, threads>>>(buf, n16, rounds, out);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return LCQP_CUDA_LAUNCH_FAILED;
+    const size_t per_round = (n16 / ((size_t)blocks * threads * 8)) * ((size_t)blocks * threads * 8) * 16;
+    *gbs = (double)per_round * rounds / (best * 1e-3) / 1e9;
     return LCQP_CUDA_OK;
 }
 

@@ -472,7 +472,15 @@ struct PQP {
     long long n_solve;   // explicit-inverse solves
     long long n_change;
     long long n_polish;
+    // work done on the per-instance inverse and on Tt (the two streams that dominate a homotopy step): fp64
+    // multiply-adds and the bytes they read / write (L2-resident scratch and operands), for the bench's model
+    long long n_mac, n_byte;
 };
+// (thread 0 of the group keeps the books)
+LCQ_DEV void pas_count(PQP& s, long long mac, long long bytes)
+{
+    if (LCQ_TID == 0) { s.n_mac += mac; s.n_byte += bytes; }
+}
 
 inline LCQ_HD int pas_cap(const PDims& d, int mE, int mI)
 {
@@ -618,6 +626,7 @@ LCQ_DEVN double pas_pivot(PQP& s, int k)
     LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) w.va[a] = row[w.widx[a]];
     LCQ_SYNC();
     if (nw > 0) { sym_apply(w.Sinv, w.ld, nw, w.va, 1.0, w.vb, nullptr, nullptr, nullptr); LCQ_SYNC(); }
+    pas_count(s, (long long)nw * nw + nw, 8LL * nw * w.ld + 32LL * nw);
     double part = 0;
     LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) part += w.va[a] * w.vb[a];
     return row[k] - block_sum(part, w.sc);
@@ -630,6 +639,7 @@ LCQ_DEVN void pas_append(PQP& s, int k, int status, double p)
     const int nw = s.nw, ld = w.ld;
     const double ip = 1.0 / p;
     if (nw > 0) rank1_update_full(w.Sinv, ld, nw, w.vb, ip);
+    pas_count(s, (long long)nw * nw, 16LL * nw * ld + 16LL * nw);
     double* row = w.Sinv + (size_t)nw * ld;
     LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) { const double v = -w.vb[a] * ip; row[a] = v; w.Sinv[(size_t)a * ld + nw] = v; }
     LCQ_SYNC();   // every thread has read s.nw
@@ -656,6 +666,7 @@ LCQ_DEVN void pas_remove(PQP& s, int p)
     const double ic = 1.0 / w.va[p];
     rank1_update_full(Si, ld, nw, w.va, -ic);
     LCQ_SYNC();
+    pas_count(s, (long long)nw * nw, 16LL * nw * ld + 56LL * nw);
     const int k = w.widx[p];
     if (p != last) {
         LCQ_LOOP for (int b = LCQ_TID; b < nw; b += LCQ_NT) w.vb[b] = Si[(size_t)last * ld + b];
@@ -755,19 +766,29 @@ LCQ_DEVN void tt_cols_apply(const PQP& s, const double* v, double* out, const do
     LCQ_SYNC();
 }
 
+// one application of a prepared operator: dense rows x cols, or the non-zeros of its CSR form (no L2 bytes when the
+// CSR arrays sit in the CTA's shared-memory operator cache)
+LCQ_DEV void pas_count_op(PQP& s, const Op& op)
+{
+    if (LCQ_TID != 0) return;
+    if (op.rp) { const long long nz = op.rp[op.rows]; s.n_mac += nz; s.n_byte += op.smem ? 0 : 10 * nz; }
+    else { const long long e = (long long)op.rows * op.cols; s.n_mac += e; s.n_byte += 8 * e; }
+}
+
 // c-space image of a gradient change v (n) and an equality-bound change dbE (mE, may be null):  out = Gt v - K dbE
 // (v, dbE, out in shared memory)
-LCQ_DEVN void c_image(const PQP& s, const double* v, const double* dbE, double* out)
+LCQ_DEVN void c_image(PQP& s, const double* v, const double* dbE, double* out)
 {
     const PMats& mt = *s.mt;
     op_mv_s(mt.oGt, v, nullptr, 1.0, out);
     LCQ_SYNC();
-    if (dbE && mt.mE > 0) { op_mv_s(mt.oK, dbE, out, -1.0, out); LCQ_SYNC(); }
+    pas_count_op(s, mt.oGt);
+    if (dbE && mt.mE > 0) { op_mv_s(mt.oK, dbE, out, -1.0, out); LCQ_SYNC(); pas_count_op(s, mt.oK); }
 }
 
 // xq += P (A_I' dyI - dgrad) + N dbE;  dyI: full-order vector in tm2 (zero on the eliminated rows), dgrad (n) and
 // dbE (mE) may be null.   Scratch: tn, stat is NOT touched.
-LCQ_DEVN void x_update(const PQP& s, const double* dgrad, const double* dbE)
+LCQ_DEVN void x_update(PQP& s, const double* dgrad, const double* dbE)
 {
     const PWork& w = *s.w;
     const int n = s.d->n;
@@ -776,7 +797,9 @@ LCQ_DEVN void x_update(const PQP& s, const double* dgrad, const double* dbE)
     if (dgrad) { LCQ_LOOP for (int j = LCQ_TID; j < n; j += LCQ_NT) w.tn[j] -= dgrad[j]; LCQ_SYNC(); }
     op_mv_s(s.mt->oP, w.tn, w.xq, 1.0, w.xq);
     LCQ_SYNC();
-    if (dbE && s.mt->mE > 0) { op_mv_s(s.mt->oN, dbE, w.xq, 1.0, w.xq); LCQ_SYNC(); }
+    pas_count_op(s, s.mt->oAt);
+    pas_count_op(s, s.mt->oP);
+    if (dbE && s.mt->mE > 0) { op_mv_s(s.mt->oN, dbE, w.xq, 1.0, w.xq); LCQ_SYNC(); pas_count_op(s, s.mt->oN); }
 }
 
 // Bring xq, gq and the base duals / equality bounds to the current point of the homotopy: g = g_new - phi dg0.
@@ -821,6 +844,7 @@ LCQ_DEVN void c_from_state(PQP& s)
     LCQ_LOOP for (int a = LCQ_TID; a < s.nw; a += LCQ_NT) w.va[a] = w.y[w.widx[a]];
     LCQ_SYNC();
     tt_cols_apply(s, w.va, w.c, w.z);
+    pas_count(s, (long long)s.nw * s.mt->mI, 8LL * s.nw * s.mt->mI);
 }
 
 // dc = c-image of the remaining gradient step (phi dg0) and of the remaining equality-bound step
@@ -958,6 +982,8 @@ LCQ_DEVN int pas_homotopy(PQP& s)
             sym_apply(w.Sinv, w.ld, nw, w.va, 1.0, w.vb, nullptr, nullptr, nullptr);
             LCQ_SYNC();
             if (LCQ_TID == 0) s.n_solve++;
+            // (dz below: only the inactive rows are needed -- the count is that algorithmic minimum)
+            pas_count(s, (long long)nw * nw + (long long)nw * (mI - nw), 8LL * nw * w.ld + 8LL * nw * (mI - nw));
         }
         LCQ_PROF(w.sc, 1);
         tt_cols_apply(s, w.vb, w.dz, w.dc, true);
@@ -1074,6 +1100,7 @@ LCQ_DEVN void pas_finish(PQP& s, const RawOps& ro)
     LCQ_LOOP for (int pass = 0; pass <= kPolishMax; pass++) {
         op_mv_s(mt.oA, w.xq, nullptr, 1.0, w.tm1);   // A_full xq
         LCQ_SYNC();
+        pas_count_op(s, mt.oA);
         const int nw = s.nw;
         double rn = 0;
         LCQ_LOOP for (int e = LCQ_TID; e < mE; e += LCQ_NT) { const double r = w.bE[e] - w.tm1[mt.Eidx[e]]; w.tE2[e] = r; rn = fmax(rn, fabs(r)); }
@@ -1097,6 +1124,7 @@ LCQ_DEVN void pas_finish(PQP& s, const RawOps& ro)
             LCQ_SYNC();
         }
         if (nw > 0) { sym_apply(w.Sinv, w.ld, nw, w.va, 1.0, w.vb, nullptr, nullptr, nullptr); LCQ_SYNC(); }
+        pas_count(s, (long long)nw * nw, 8LL * nw * w.ld);
         LCQ_LOOP for (int r = LCQ_TID; r < m; r += LCQ_NT) w.tm2[r] = 0.0;
         LCQ_SYNC();
         LCQ_LOOP for (int a = LCQ_TID; a < nw; a += LCQ_NT) { const int i = w.widx[a]; w.tm2[mt.Iidx[i]] = w.vb[a]; w.y[i] += w.vb[a]; }
@@ -1480,7 +1508,7 @@ LCQ_DEVN bool pas_run_instance(PQP& s, PMats& mt, bool mats_shared, const RawOps
     const lcqp_cuda_options& o = *s.o;
     const int nD = d.n + d.mA;
     LCQ_SYNC();
-    if (LCQ_TID == 0) { s.mt = &mt; s.nw = 0; s.n_solve = 0; s.n_change = 0; s.n_polish = 0; s.nwsr = 0; }
+    if (LCQ_TID == 0) { s.mt = &mt; s.nw = 0; s.n_solve = 0; s.n_change = 0; s.n_polish = 0; s.n_mac = 0; s.n_byte = 0; s.nwsr = 0; }
     LCQ_LOOP for (int k = LCQ_TID; k < 8; k += LCQ_NT) w.sc->wph[k] = 0;
     LCQ_SYNC();
     out.ret = 0; out.status = 0; out.iterTotal = 0; out.iterOuter = 0; out.subIter = 0; out.exitFlag = 0; out.rhoOpt = 0;

@@ -211,7 +211,8 @@ static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned share
 // ---- the parametric active-set path (lcqp_pas.cuh), driven the way lcqp_cabi.cu drives it: the equality mask over the
 // batch, batch-level preparation when Q/A/L/R are shared, then pas_run_instance per instance.  Instances whose Hessian is
 // not positive definite (status 1) go to the regularised solver above, as in the product.
-static long long g_last_solves = 0, g_last_changes = 0, g_last_polish = 0;
+static long long g_last_solves = 0, g_last_changes = 0, g_last_polish = 0, g_last_mac = 0, g_last_byte = 0;
+extern "C" void lcqp_emu_last_work(long long* macs, long long* bytes) { *macs = g_last_mac; *bytes = g_last_byte; }
 extern "C" void lcqp_emu_last_counts(long long* solves, long long* changes, long long* polish)
 {
     *solves = g_last_solves; *changes = g_last_changes; *polish = g_last_polish;
@@ -281,7 +282,7 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
     s.d = &d; s.o = o; s.w = &wk; s.mt = &mt;
     const int nD = nV + nC + 2 * nComp;
     int nfail = 0;
-    g_last_solves = g_last_changes = g_last_polish = 0;
+    g_last_solves = g_last_changes = g_last_polish = g_last_mac = g_last_byte = 0;
     for (int b = 0; b < batch; b++) {
         const Inst in = inst(b);
         s.in = &in;
@@ -303,7 +304,7 @@ extern "C" int lcqp_emu_solve_batch(int batch, int nV, int nC, int nComp, unsign
         st.rhoOpt = out.rhoOpt; st.admmIters = 0.0;
         res[b] = st;
         nfail += (out.ret != 0);
-        g_last_solves += s.n_solve; g_last_changes += s.n_change; g_last_polish += s.n_polish;
+        g_last_solves += s.n_solve; g_last_changes += s.n_change; g_last_polish += s.n_polish; g_last_mac += s.n_mac; g_last_byte += s.n_byte;
     }
     return nfail;
 }
