@@ -362,6 +362,28 @@ def parity_subset_osqp(cfg, L, batch, lo_global, n_check, device):
                          "identical and x within 1e-6 relative; instances it fails: a failure code here too; perturbStep off, adaptive_rho_interval 25"}
 
 
+def work_probe(args, cfg):
+    """Child process of the bench (rank 0): the first `--work-probe` instances of the workload through the COUNTING build of
+    the library; prints {"macs_per_lcqp", "bytes_per_lcqp", "l2_gbs", "n"} -- the active-set kernel's own count of its fp64
+    multiply-adds and of the bytes its dense products read / write (lcqp_cuda_last_work), and the L2 read-bandwidth probe."""
+    import ctypes as C
+    import lcqpow_b200 as L
+    n = args.work_probe
+    pb = cfg.generate(n, 0, n).normalised()
+    prob = L.LCQProblemBatch(cfg.nV, cfg.nC, cfg.nComp, n, device=int(os.environ.get("LOCAL_RANK", "0")))
+    o = L.Options()
+    for k, v in cfg.over.items():
+        getattr(o, "set" + k[0].upper() + k[1:])(v)
+    o.setPerturbStep(bool(args.perturb))
+    prob.setOptions(o)
+    assert prob.loadBatch(pb) == 0
+    prob.runSolver()
+    macs, wbytes, l2 = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
+    rc = prob.lib.lcqp_cuda_last_work(prob.h, C.byref(macs), C.byref(wbytes))
+    prob.lib.lcqp_cuda_measure_l2_gbs(int(os.environ.get("LOCAL_RANK", "0")), C.byref(l2))
+    print(json.dumps({"rc": rc, "macs_per_lcqp": macs.value / n, "bytes_per_lcqp": wbytes.value / n, "l2_gbs": l2.value, "n": n}))
+
+
 _PARITY_JOB = None
 
 
@@ -384,8 +406,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--parity", type=int, default=1024, help="instances of the parity subset (0: skip)")
     ap.add_argument("--perturb", type=int, default=1)
+    ap.add_argument("--work-probe", type=int, default=0, help="internal: solve this many instances with the counting build of the "
+                    "library (LCQP_CUDA_LIB = liblcqp_cuda_work.so) and print its work counters per LCQP")
     args = ap.parse_args()
     cfg = Config(args.config)
+    if args.work_probe > 0:
+        work_probe(args, cfg)
+        return
     osqp = cfg.sparse or args.flavour == "osqp"
     if osqp:
         cfg.ref_solver_parity = 2
@@ -579,15 +606,29 @@ def main():
         # multiply-adds of its dense products and the bytes they read / write -- per-instance inverse, Tt columns and
         # prepared operators, all L2 resident), against the measured fp64 pipe and the measured L2 read bandwidth
         work = None
-        macs, wbytes, l2gbs = C.c_double(0.0), C.c_double(0.0), C.c_double(0.0)
-        if not osqp and prob.lib.lcqp_cuda_last_work(prob.h, C.byref(macs), C.byref(wbytes)) == 0 and macs.value > 0:
-            prob.lib.lcqp_cuda_measure_l2_gbs(local_rank, C.byref(l2gbs))
-            work = {"fp64_macs_per_lcqp": macs.value / batch, "l2_bytes_per_lcqp": wbytes.value / batch,
-                    "fp64_achieved_tflops": 2.0 * macs.value / (k_ms * 1e-3) / 1e12,
-                    "fp64_frac": (2.0 * macs.value / (k_ms * 1e-3) / 1e12) / fp64.value if fp64.value > 0 else None,
-                    "l2_achieved_gbs": wbytes.value / (k_ms * 1e-3) / 1e9, "l2_peak_gbs_measured": l2gbs.value,
-                    "l2_frac": (wbytes.value / (k_ms * 1e-3) / 1e9) / l2gbs.value if l2gbs.value > 0 else None,
-                    "note": "dense products of the active-set kernel counted on the device (lcqp_cuda_last_work): algorithmic minimum, rank 0's launch"}
+        work_lib = os.path.join(ROOT, "lcqpow_b200", "lib", "liblcqp_cuda_work.so")
+        if not osqp and cfg.name != "c3" and os.path.exists(work_lib):
+            # the counting build (3-5 % slower: not the one that is timed) on the first instances of the same workload, in a
+            # child process, after the timed region; the counts are a property of the instances, scaled to this launch
+            import subprocess
+            n_probe = min(batch, 8192)
+            try:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), "--config", cfg.name, "--work-probe", str(n_probe), "--perturb", str(args.perturb)],
+                                   env=dict(os.environ, LCQP_CUDA_LIB=work_lib, LOCAL_RANK=str(local_rank), WORLD_SIZE="1", RANK="0"),
+                                   capture_output=True, text=True, timeout=600)
+                wp = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as ex:
+                wp = {"rc": -1, "error": repr(ex)}
+            if wp.get("rc") == 0 and wp["macs_per_lcqp"] > 0:
+                tf = 2.0 * wp["macs_per_lcqp"] * batch / (k_ms * 1e-3) / 1e12
+                gbs = wp["bytes_per_lcqp"] * batch / (k_ms * 1e-3) / 1e9
+                work = {"fp64_macs_per_lcqp": wp["macs_per_lcqp"], "l2_bytes_per_lcqp": wp["bytes_per_lcqp"],
+                        "fp64_achieved_tflops": tf, "fp64_frac": tf / fp64.value if fp64.value > 0 else None,
+                        "l2_achieved_gbs": gbs, "l2_peak_gbs_measured": wp["l2_gbs"], "l2_frac": gbs / wp["l2_gbs"] if wp["l2_gbs"] > 0 else None,
+                        "note": f"dense products of the active-set kernel counted on the device by the counting build (lcqp_cuda_last_work) on the first {n_probe} "
+                                "instances of this workload, per LCQP, times this launch's instances over its kernel time: algorithmic minimum"}
+            else:
+                work = {"error": wp.get("error", "work probe failed"), "rc": wp.get("rc")}
         if osqp:
             # SURVEY.md 8(d) row "OSQP-ADMM iteration": HBM bound, bytes per ADMM iteration of one instance =
             # 16 nnz(L) (values + indices of the factor, forward and backward sweep read it once each as 8 + 8)

@@ -188,7 +188,9 @@ int lcqp_cuda_measure_fp64_tflops(int device, double* tflops);
 int lcqp_cuda_measure_l2_gbs(int device, double* gbs);
 /* work of the last run of the parametric active-set kernel, summed over the batch: fp64 multiply-adds of its dense
  * products (per-instance inverse, Tt columns, prepared operators) and the bytes those products read and write --
- * the algorithmic minimum, counted by the kernel itself.  Waits for the run. */
+ * the algorithmic minimum, counted by the kernel itself.  Waits for the run.  Only the counting build of the library
+ * (liblcqp_cuda_work.so, -DLCQP_COUNT_WORK) keeps these books -- they cost the kernel 3-5 % -- the shipped build returns
+ * LCQP_CUDA_BAD_ARGUMENT. */
 int lcqp_cuda_last_work(lcqp_cuda_handle h, double* fp64_macs, double* bytes);
 
 /* ---- (2) plugin door: one convex QP, SubsolverBase semantics ---------------------------------- */

@@ -14,6 +14,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "liblcqp_cuda.so")
+# the same sources with -DLCQP_COUNT_WORK: the active-set kernel counts its fp64 multiply-adds and L2 bytes
+# (lcqp_cuda_last_work); bench.py runs it on a sub-batch, outside the timed region, for roofline.work
+LIB_WORK = os.path.join(LIBDIR, "liblcqp_cuda_work.so")
 SOURCES = [os.path.join(CSRC, "lcqp_cabi.cu")]
 DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("lcqp_device.cuh", "lcqp_pas.cuh", "lcqp_osqp.cuh", "lcqp_osqp_impl.inc", "lcqp_sparse_host.hpp")] + [os.path.join(HERE, "..", "include", "lcqp_cuda.h")]
 # LCQP_NO_ASSUME: the address-space hints (__builtin_assume(__isShared(p))) of lcqp_device.cuh are off -- with
@@ -31,10 +34,13 @@ def _nvcc() -> str:
 
 
 def up_to_date() -> bool:
-    if not os.path.exists(LIB):
-        return False
-    t = os.path.getmtime(LIB)
-    return all(os.path.getmtime(d) <= t for d in DEPS)
+    for lib in (LIB, LIB_WORK):
+        if not os.path.exists(lib):
+            return False
+        t = os.path.getmtime(lib)
+        if not all(os.path.getmtime(d) <= t for d in DEPS):
+            return False
+    return True
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -42,11 +48,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
-    if verbose or r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed building liblcqp_cuda.so")
+    cmd_work = [_nvcc()] + NVCC_FLAGS + ["-DLCQP_COUNT_WORK", "-o", LIB_WORK] + SOURCES
+    procs = [subprocess.Popen(c, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for c in (cmd, cmd_work)]
+    for pr, name in zip(procs, ("liblcqp_cuda.so", "liblcqp_cuda_work.so")):
+        out, _ = pr.communicate()
+        if verbose or pr.returncode != 0:
+            sys.stderr.write(out)
+        if pr.returncode != 0:
+            raise RuntimeError("nvcc failed building " + name)
     return LIB
 
 

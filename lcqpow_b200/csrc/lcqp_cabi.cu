@@ -336,8 +336,10 @@ __global__ void __launch_bounds__(kPasCtaThreads, 1) lcqp_pas_kernel(const __gri
             st.kktSolves = (int)s.n_solve;
             st.rhoOpt = out.rhoOpt; st.admmIters = 0.0;
             a.stats[b] = st;
+#ifdef LCQP_COUNT_WORK
             atomicAdd(a.work, (unsigned long long)s.n_mac);
             atomicAdd(a.work + 1, (unsigned long long)s.n_byte);
+#endif
             if (!ok) atomicExch(a.fallback_flag, 1);
         }
     }
@@ -1628,6 +1630,9 @@ int lcqp_cuda_osqp_info(lcqp_cuda_handle h, int* N, int* nnzL, int* levels, int*
 int lcqp_cuda_last_work(lcqp_cuda_handle h, double* fp64_macs, double* bytes)
 {
     if (!h) return LCQP_CUDA_BAD_HANDLE;
+#ifndef LCQP_COUNT_WORK
+    return fail(h, LCQP_CUDA_BAD_ARGUMENT, "this build does not count (the counting build is liblcqp_cuda_work.so, -DLCQP_COUNT_WORK)");
+#endif
     if (!h->ran || h->use_legacy || !h->pas_ready || (h->opts.qpSolver == 2 && h->opts.osqp_admm))
         return fail(h, LCQP_CUDA_NOT_LOADED, "the work counters belong to a run of the parametric active-set kernel");
     CK(cudaSetDevice(h->device), LCQP_CUDA_NO_DEVICE);
@@ -1668,7 +1673,7 @@ int lcqp_cuda_measure_l2_gbs(int device, double* gbs)
     double* out = nullptr;
     if (cudaMalloc(&buf, bytes) != cudaSuccess || cudaMalloc(&out, 8) != cudaSuccess) { cudaGetLastError(); cudaFree(buf); return LCQP_CUDA_OUT_OF_MEMORY; }
     cudaMemset(buf, 0, bytes);
-    const int blocks = prop.multiProcessorCount * 4, threads = 512, rounds = 16;
+    const int blocks = prop.multiProcessorCount * 4, threads = 512, rounds = 256;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     l2_read_probe_kernel<<<blocks, threads>>>(buf, n16, 2, out);   // brings the buffer into the L2

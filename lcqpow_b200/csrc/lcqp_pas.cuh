@@ -476,11 +476,16 @@ struct PQP {
     // multiply-adds and the bytes they read / write (L2-resident scratch and operands), for the bench's model
     long long n_mac, n_byte;
 };
-// (thread 0 of the group keeps the books)
+// (thread 0 of the group keeps the books -- only in the counting build, -DLCQP_COUNT_WORK: liblcqp_cuda_work.so; the
+//  bookkeeping costs the shipped kernel 3-5 % on the B200, so the product is built without it)
+#ifdef LCQP_COUNT_WORK
 LCQ_DEV void pas_count(PQP& s, long long mac, long long bytes)
 {
     if (LCQ_TID == 0) { s.n_mac += mac; s.n_byte += bytes; }
 }
+#else
+LCQ_DEV void pas_count(PQP&, long long, long long) {}
+#endif
 
 inline LCQ_HD int pas_cap(const PDims& d, int mE, int mI)
 {
@@ -768,12 +773,16 @@ LCQ_DEVN void tt_cols_apply(const PQP& s, const double* v, double* out, const do
 
 // one application of a prepared operator: dense rows x cols, or the non-zeros of its CSR form (no L2 bytes when the
 // CSR arrays sit in the CTA's shared-memory operator cache)
+#ifdef LCQP_COUNT_WORK
 LCQ_DEV void pas_count_op(PQP& s, const Op& op)
 {
     if (LCQ_TID != 0) return;
     if (op.rp) { const long long nz = op.rp[op.rows]; s.n_mac += nz; s.n_byte += op.smem ? 0 : 10 * nz; }
     else { const long long e = (long long)op.rows * op.cols; s.n_mac += e; s.n_byte += 8 * e; }
 }
+#else
+LCQ_DEV void pas_count_op(PQP&, const Op&) {}
+#endif
 
 // c-space image of a gradient change v (n) and an equality-bound change dbE (mE, may be null):  out = Gt v - K dbE
 // (v, dbE, out in shared memory)

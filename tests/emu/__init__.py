@@ -18,7 +18,7 @@ SOURCES = [os.path.join(HERE, "emu_driver.cpp"), os.path.join(ROOT, "lcqpow_b200
 def build(force: bool = False) -> str:
     if not force and os.path.exists(EMU_SO) and all(os.path.getmtime(s) <= os.path.getmtime(EMU_SO) for s in SOURCES):
         return EMU_SO
-    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DLCQP_HOST_EMU", "-ffp-contract=off",
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DLCQP_HOST_EMU", "-DLCQP_COUNT_WORK", "-ffp-contract=off",
                     "-Wno-unused-function", "-o", EMU_SO, SOURCES[0]], check=True)
     return EMU_SO
 
