@@ -554,6 +554,7 @@ struct OsqpArgs {
     unsigned long long instance_offset;
     int box_given;                               // lb / ub were loaded: INVALID_OSQP_BOX_CONSTRAINTS (LCQProblem.cpp:930-957)
     unsigned smem_bytes;                         // solve / factor scratch per warp in shared memory when that fits, else 0 (global, L2)
+    unsigned ring_offset;                        // mode W, streamed sweeps: byte offset of the bulk-copy ring in the dynamic shared memory (0: none)
 };
 
 LCQ_DEV osq::View osqp_view(const OsqpArgs& a, int b)
@@ -621,6 +622,11 @@ __global__ void __launch_bounds__(32) lcqp_osqpw_kernel(const __grid_constant__ 
     extern __shared__ __align__(16) unsigned char osqp_smem[];
     osqw::Work w;
     osqw::carve(w, a.S, a.workspace + (size_t)blockIdx.x * a.ws_doubles, a.smem_bytes ? reinterpret_cast<double*>(osqp_smem) : nullptr);
+    if (a.ring_offset) {
+        w.ring = osqp_smem + a.ring_offset;
+        w.ring_uses = reinterpret_cast<unsigned*>(w.ring + osq::kStreamStages * osq::stream_stage_bytes() + 8 * osq::kStreamStages);
+        osqw::ring_init(w);
+    }
     const int nV = a.S.n, mA = a.S.m, nD = nV + mA;
     for (;;) {
         unsigned b = 0;
@@ -1330,7 +1336,8 @@ static int osqp_upload_symbolic(lcqp_cuda_handle h)
     constexpr int NV = osq::kSymArrays;
     const std::vector<int>* vs[NV] = {&S.Pp, &S.Pi, &S.Psrc, &S.Ap, &S.Ai, &S.Asrc, &S.Qp, &S.Qi, &S.Qsrc, &S.perm, &S.Kp, &S.Ki, &S.Ksrc,
                                       &S.Lp, &S.Li, &S.rp, &S.rcol, &S.rpos, &S.Pcol, &S.Acol, &S.Qcol,
-                                      &S.ArP, &S.ArE, &S.PrP, &S.PrE, &S.QrP, &S.QrE, &S.LrP, &S.LrC, &S.rposr, &S.flP, &S.flR, &S.blP, &S.blC};
+                                      &S.ArP, &S.ArE, &S.PrP, &S.PrE, &S.QrP, &S.QrE, &S.LrP, &S.LrC, &S.rposr, &S.flP, &S.flR, &S.blP, &S.blC,
+                                      &S.fsI, &S.bsI, &S.fsSrc, &S.bsSrc};
     size_t total = 0;
     size_t off[NV];
     for (int k = 0; k < NV; k++) { off[k] = total; total += (vs[k]->size() + 3) & ~(size_t)3; }
@@ -1348,8 +1355,10 @@ static int osqp_upload_symbolic(lcqp_cuda_handle h)
     D.n = S.n; D.m = S.m; D.N = S.N; D.nC = h->nC; D.nComp = h->nComp;
     D.nnzP = (int)S.Pi.size(); D.nnzA = (int)S.Ai.size(); D.nnzQ = (int)S.Qi.size(); D.nnzK = (int)S.Ki.size(); D.nnzL = (int)S.Li.size();
     D.nflev = (int)S.flP.size() - 1; D.nblev = (int)S.blP.size() - 1;
+    D.fsChunks = S.fsChunks; D.bsChunks = S.bsChunks; D.stream = S.stream;
     const int** dst[NV] = {&D.Pp, &D.Pi, &D.Psrc, &D.Ap, &D.Ai, &D.Asrc, &D.Qp, &D.Qi, &D.Qsrc, &D.perm, &D.Kp, &D.Ki, &D.Ksrc, &D.Lp, &D.Li, &D.rp, &D.rcol, &D.rpos,
-                           &D.Pcol, &D.Acol, &D.Qcol, &D.ArP, &D.ArE, &D.PrP, &D.PrE, &D.QrP, &D.QrE, &D.LrP, &D.LrC, &D.rposr, &D.flP, &D.flR, &D.blP, &D.blC};
+                           &D.Pcol, &D.Acol, &D.Qcol, &D.ArP, &D.ArE, &D.PrP, &D.PrE, &D.QrP, &D.QrE, &D.LrP, &D.LrC, &D.rposr, &D.flP, &D.flR, &D.blP, &D.blC,
+                           &D.fsI, &D.bsI, &D.fsSrc, &D.bsSrc};
     for (int k = 0; k < NV; k++) *dst[k] = h->sym_ints + off[k];
     h->osqp_nnzL = (long long)S.Li.size();
     return LCQP_CUDA_OK;
@@ -1402,10 +1411,22 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     const size_t sm_need = osq::sm_len(a.S) * lanes * sizeof(double);
     a.smem_bytes = (sm_need <= (size_t)kSmemMax - 1024) ? (unsigned)sm_need : 0u;
     if (tune_env("LCQP_CUDA_OSQP_NOSMEM")) a.smem_bytes = 0;
+    // streamed triangular solves (one warp per instance): the ring that cp.async.bulk fills sits behind the scratch vector
+    size_t dyn_smem = a.smem_bytes;
+    a.ring_offset = 0;
+    if (!warp_mode) a.S.stream = 0;   // (one thread per instance reads L in place; its workspace holds no streams)
+    // (they pay when a sweep is a long chain of small levels -- C4: 334 levels of ~6 rows; with a handful of wide levels
+    //  -- C2: 4 levels -- reading L in place is faster: 1.66k against 1.13k LCQP/s, r2p)
+    if (warp_mode && a.S.stream && a.S.nflev + a.S.nblev >= 32 && !tune_env("LCQP_CUDA_OSQP_NOSTREAM")) {
+        const size_t off = a.smem_bytes ? ((size_t)a.smem_bytes + 127) & ~(size_t)127 : 128;
+        if (off + osq::stream_ring_bytes() <= (size_t)kSmemMax - 1024) { a.ring_offset = (unsigned)off; dyn_smem = off + osq::stream_ring_bytes(); }
+    }
+    if (!a.ring_offset) a.S.stream = 0;
+    a.ws_doubles = (osq::ws_doubles(a.S) + 1) & ~(size_t)1;
     auto kern = warp_mode ? lcqp_osqpw_kernel : lcqp_osqp_kernel;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem), LCQP_CUDA_LAUNCH_FAILED);
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, a.smem_bytes), LCQP_CUDA_LAUNCH_FAILED);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 32, dyn_smem), LCQP_CUDA_LAUNCH_FAILED);
     if (per_sm < 1) return fail(h, LCQP_CUDA_TOO_LARGE, "kernel cannot be resident");
     if (per_sm > 16) per_sm = 16;
     // one warp per CTA; as many resident warps as there are work items, up to per_sm per SM and a quarter of the device memory
@@ -1431,18 +1452,18 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     CK(cudaEventRecord(h->ev0, stream), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev1, stream), LCQP_CUDA_LAUNCH_FAILED);
     if (getenv("LCQP_CUDA_VERBOSE"))
-        fprintf(stderr, "lcqp_cuda (OSQP flavour, %s): %lld warps (%d per SM), N %d, nnz(L) %d, nnz(K) %d, levels %d + %d, workspace %.2f MB/warp, smem %u B/warp, factor flops %lld\n",
+        fprintf(stderr, "lcqp_cuda (OSQP flavour, %s): %lld warps (%d per SM), N %d, nnz(L) %d, nnz(K) %d, levels %d + %d, workspace %.2f MB/warp, smem %zu B/warp, factor flops %lld, streamed sweeps %s (%d + %d chunks)\n",
                 warp_mode ? "one warp per instance" : "one thread per instance", warps, per_sm, a.S.N, a.S.nnzL, a.S.nnzK, a.S.nflev, a.S.nblev, per_warp / 1.0e6,
-                a.smem_bytes, h->sym ? h->sym->factor_flops : 0ll);
+                dyn_smem, h->sym ? h->sym->factor_flops : 0ll, a.S.stream ? "on" : "off", a.S.fsChunks, a.S.bsChunks);
     h->osqp_warp_mode = warp_mode ? 1 : 0;
-    if (warp_mode) lcqp_osqpw_kernel<<<(unsigned)warps, 32, a.smem_bytes, stream>>>(a);
-    else lcqp_osqp_kernel<<<(unsigned)warps, 32, a.smem_bytes, stream>>>(a);
+    if (warp_mode) lcqp_osqpw_kernel<<<(unsigned)warps, 32, dyn_smem, stream>>>(a);
+    else lcqp_osqp_kernel<<<(unsigned)warps, 32, dyn_smem, stream>>>(a);
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
     h->last_stream = stream;
     h->last_grid = (int)warps;
-    h->last_smem = (int)a.smem_bytes;
+    h->last_smem = (int)dyn_smem;
     h->last_mE = -1;
     h->ran = true;
     return LCQP_CUDA_OK;

@@ -39,6 +39,7 @@
 #pragma once
 
 #include "lcqp_device.cuh"
+#include "lcqp_sparse_host.hpp"   // kStreamVals, kStreamIdx (and the host-side analysis itself)
 
 namespace lcqp {
 namespace osq {
@@ -54,10 +55,15 @@ enum { OSQP_SOLVED = 1, OSQP_SOLVED_INACCURATE = 2, OSQP_PRIMAL_INFEASIBLE_INACC
 // device view of osq::Symbolic (lcqp_sparse_host.hpp)
 struct SymDev {
     int n, m, N, nC, nComp, nnzP, nnzA, nnzQ, nnzK, nnzL, nflev, nblev;
+    int fsChunks, bsChunks, stream;   // streamed triangular solves (lcqp_sparse_host.hpp: Symbolic::fsI ...), warp mode only
     const int *Pp, *Pi, *Psrc, *Ap, *Ai, *Asrc, *Qp, *Qi, *Qsrc, *perm, *Kp, *Ki, *Ksrc, *Lp, *Li, *rp, *rcol, *rpos, *Pcol, *Acol, *Qcol,
-        *ArP, *ArE, *PrP, *PrE, *QrP, *QrE, *LrP, *LrC, *rposr, *flP, *flR, *blP, *blC;
+        *ArP, *ArE, *PrP, *PrE, *QrP, *QrE, *LrP, *LrC, *rposr, *flP, *flR, *blP, *blC, *fsI, *bsI, *fsSrc, *bsSrc;
 };
-constexpr int kSymArrays = 34;
+constexpr int kSymArrays = 38;
+// shared-memory ring of the streamed sweeps: kStreamStages x (value chunk + index chunk) + one mbarrier per stage
+constexpr int kStreamStages = 2;
+LCQ_HD inline size_t stream_stage_bytes() { return (size_t)kStreamVals * sizeof(double) + (size_t)kStreamIdx * sizeof(unsigned short); }
+LCQ_HD inline size_t stream_ring_bytes() { return kStreamStages * stream_stage_bytes() + 64; }
 
 // one instance's inputs (value arrays as the caller laid them out; NULL = absent)
 struct View {
@@ -75,7 +81,8 @@ struct State {
 LCQ_HD inline size_t sm_len(const SymDev& S) { return (size_t)S.N + 8; }   // solve / factor scratch (+ a few scalars)
 LCQ_HD inline size_t ws_doubles(const SymDev& S)
 {
-    return (size_t)S.nnzP + S.nnzA + 4 * (size_t)S.nnzL + 2 * (size_t)S.N + 17 * (size_t)S.n + 17 * (size_t)S.m + 2 * (size_t)S.N + sm_len(S);
+    return (size_t)S.nnzP + S.nnzA + 4 * (size_t)S.nnzL + 2 * (size_t)S.N + 17 * (size_t)S.n + 17 * (size_t)S.m + 2 * (size_t)S.N + sm_len(S)
+           + (S.stream ? 2 * ((size_t)S.fsChunks + S.bsChunks) * kStreamVals + 2 : 0);
 }
 
 LCQ_DEV double osq_limit(double d) { d = d < kMinScaling ? 1.0 : d; return d > kMaxScaling ? kMaxScaling : d; }   // scaling.c:7-14

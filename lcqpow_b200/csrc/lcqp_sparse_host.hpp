@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <cstdint>
 #include <cstring>
+#include <utility>
 #include <vector>
 
 namespace lcqp {
@@ -49,7 +50,71 @@ struct Symbolic {
     // level sets of the triangular solves: rows (forward) / columns (backward) of one level do not depend on each other
     std::vector<int> flP, flR, blP, blC;
     long long factor_flops = 0;        // multiply-subtracts of one numeric factorisation
+    // STREAMED triangular solves (one warp per instance, lcqp_osqp_impl.inc stream_sweep): the entries of L in the order
+    // in which a level-by-level sweep consumes them, cut into chunks of kStreamVals values that a warp brings into shared
+    // memory ahead of use (cp.async.bulk + mbarrier), so that the only dependent loads of a sweep are shared-memory ones.
+    //   index chunk c (kStreamIdx 16-bit words, shared by the batch): [nlev] then per level [r][E][r rows][E x r columns]
+    //       a level here has r <= 32 independent rows (lane j owns row j) padded to E entries each; entry e of lane j is
+    //       value slot voff + e * r + j of value chunk c (voff runs over the chunk), its column is the matching index word;
+    //       padding entries carry value 0 and column N + 2 (a scratch slot that holds 0)
+    //   value chunk c (kStreamVals doubles, per instance): filled after every numeric factorisation from the row-major
+    //       (forward sweep) / column-major (backward sweep) copy of L through fsSrc / bsSrc (-1: padding)
+    // stream = 0 when a level does not fit a chunk (the sweeps then read L in place, level by level).
+    std::vector<int> fsI, bsI;         // index chunks, two 16-bit words per int
+    std::vector<int> fsSrc, bsSrc;     // kStreamVals per chunk
+    int fsChunks = 0, bsChunks = 0, stream = 0;
 };
+constexpr int kStreamVals = 512;       // doubles per value chunk (4 KB)
+constexpr int kStreamIdx = 1280;       // 16-bit words per index chunk (2.5 KB)
+
+// rows[k] = (row id, entries as (source slot, column)) of one sweep, grouped by level through lvP
+struct StreamRow { int id; std::vector<std::pair<int, int>> ent; };
+inline bool build_stream(int N, const std::vector<std::vector<StreamRow>>& levels, std::vector<int>& Ipack, std::vector<int>& Src, int& nchunks)
+{
+    std::vector<unsigned short> I;
+    Src.clear();
+    nchunks = 0;
+    if (N + 3 > 65535) return false;
+    size_t ibase = 0, vbase = 0;
+    int iused = 0, vused = 0, nlev = 0;
+    auto open_chunk = [&]() {
+        ibase = I.size(); vbase = Src.size();
+        I.resize(ibase + kStreamIdx, 0); Src.resize(vbase + kStreamVals, -1);
+        iused = 1; vused = 0; nlev = 0; nchunks++;
+    };
+    auto close_chunk = [&]() { I[ibase] = (unsigned short)nlev; };
+    bool open = false;
+    for (const auto& lv : levels) {
+        std::vector<const StreamRow*> rows;
+        for (const auto& r : lv) if (!r.ent.empty()) rows.push_back(&r);
+        std::stable_sort(rows.begin(), rows.end(), [](const StreamRow* a, const StreamRow* b) { return a->ent.size() > b->ent.size(); });
+        for (size_t g = 0; g < rows.size();) {
+            const int E = (int)rows[g]->ent.size();   // the longest of the group (rows are sorted by length)
+            // at most 32 rows (one per lane), fewer when the rows are long: the group must fit one chunk
+            int r = (int)std::min<size_t>(32, rows.size() - g);
+            while (r > 1 && (r * E > kStreamVals || 1 + 2 + r + r * E > kStreamIdx)) r--;
+            const int ineed = 2 + r + r * E, vneed = r * E;
+            if (1 + ineed > kStreamIdx || vneed > kStreamVals) return false;
+            if (!open || iused + ineed > kStreamIdx || vused + vneed > kStreamVals) { if (open) close_chunk(); open_chunk(); open = true; }
+            unsigned short* ip = I.data() + ibase + iused;
+            ip[0] = (unsigned short)r; ip[1] = (unsigned short)E;
+            for (int j = 0; j < r; j++) ip[2 + j] = (unsigned short)rows[g + j]->id;
+            for (int e = 0; e < E; e++)
+                for (int j = 0; j < r; j++) {
+                    const auto& en = rows[g + j]->ent;
+                    const bool real = e < (int)en.size();
+                    ip[2 + r + e * r + j] = (unsigned short)(real ? en[e].second : N + 2);
+                    Src[vbase + vused + e * r + j] = real ? en[e].first : -1;
+                }
+            iused += ineed; vused += vneed; nlev++;
+            g += r;
+        }
+    }
+    if (open) close_chunk();
+    Ipack.assign((I.size() + 1) / 2, 0);
+    if (!I.empty()) std::memcpy(Ipack.data(), I.data(), I.size() * sizeof(unsigned short));
+    return true;
+}
 
 // minimum-degree ordering of a symmetric pattern given as adjacency lists (no self loops)
 inline std::vector<int> min_degree_order(int N, const std::vector<std::vector<int>>& adj)
@@ -266,6 +331,27 @@ inline void analyse_with(int n, int m, const std::vector<Trip>& Qpat, const std:
         for (int l = 1; l <= maxl; l++) { for (int i = 0; i < N; i++) if (lev[i] == l) S.flR.push_back(i); S.flP.push_back((int)S.flR.size()); }
         S.blP.assign(1, 0); S.blC.clear();
         for (int l = 1; l <= maxb; l++) { for (int i = N - 1; i >= 0; i--) if (blev[i] == l) S.blC.push_back(i); S.blP.push_back((int)S.blC.size()); }
+    }
+    {
+        // the streamed form of the two sweeps: forward = rows of a level, entries L(i, c) in ascending c (slot of the row-major
+        // copy); backward = columns of a level, entries L(r, i) in ascending r (slot of the column-major array)
+        std::vector<std::vector<StreamRow>> fw(S.flP.size() - 1), bw(S.blP.size() - 1);
+        for (size_t l = 0; l + 1 < S.flP.size(); l++)
+            for (int q = S.flP[l]; q < S.flP[l + 1]; q++) {
+                StreamRow r; r.id = S.flR[q];
+                for (int sl = S.LrP[r.id]; sl < S.LrP[r.id + 1]; sl++) r.ent.push_back({sl, S.LrC[sl]});
+                fw[l].push_back(std::move(r));
+            }
+        for (size_t l = 0; l + 1 < S.blP.size(); l++)
+            for (int q = S.blP[l]; q < S.blP[l + 1]; q++) {
+                StreamRow r; r.id = S.blC[q];
+                for (int p = S.Lp[r.id]; p < S.Lp[r.id + 1]; p++) r.ent.push_back({p, S.Li[p]});
+                bw[l].push_back(std::move(r));
+            }
+        const bool okf = build_stream(N, fw, S.fsI, S.fsSrc, S.fsChunks);
+        const bool okb = okf && build_stream(N, bw, S.bsI, S.bsSrc, S.bsChunks);
+        S.stream = (okf && okb) ? 1 : 0;
+        if (!S.stream) { S.fsI.clear(); S.bsI.clear(); S.fsSrc.clear(); S.bsSrc.clear(); S.fsChunks = S.bsChunks = 0; }
     }
     S.Lcol.assign(S.Li.size(), 0);
     S.Lrev.clear();

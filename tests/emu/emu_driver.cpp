@@ -131,6 +131,8 @@ static int legacy_solve_batch(int batch, int nV, int nC, int nComp, unsigned sha
 // ---- the OSQP flavour (lcqp_osqp.cuh): pattern analysis on the host, then one scalar run per instance ------------
 static long long g_osqp_nnzL = 0, g_osqp_factor_flops = 0;
 extern "C" void lcqp_emu_osqp_info(long long* nnzL, long long* factor_flops) { *nnzL = g_osqp_nnzL; *factor_flops = g_osqp_factor_flops; }
+static int g_osqp_stream[3] = {0, 0, 0};
+extern "C" void lcqp_emu_osqp_stream(int* on, int* fwd_chunks, int* bwd_chunks) { *on = g_osqp_stream[0]; *fwd_chunks = g_osqp_stream[1]; *bwd_chunks = g_osqp_stream[2]; }
 
 static void sym_to_dev(const osq::Symbolic& S, int nC, int nComp, osq::SymDev& D)
 {
@@ -143,6 +145,9 @@ static void sym_to_dev(const osq::Symbolic& S, int nC, int nComp, osq::SymDev& D
     D.Pcol = S.Pcol.data(); D.Acol = S.Acol.data(); D.Qcol = S.Qcol.data();
     D.ArP = S.ArP.data(); D.ArE = S.ArE.data(); D.PrP = S.PrP.data(); D.PrE = S.PrE.data(); D.QrP = S.QrP.data(); D.QrE = S.QrE.data();
     D.LrP = S.LrP.data(); D.LrC = S.LrC.data(); D.rposr = S.rposr.data(); D.flP = S.flP.data(); D.flR = S.flR.data(); D.blP = S.blP.data(); D.blC = S.blC.data();
+    // streamed sweeps (the warp build reads the streams in place; LCQP_EMU_NOSTREAM: the level-by-level sweeps)
+    D.stream = getenv("LCQP_EMU_NOSTREAM") ? 0 : S.stream; D.fsChunks = S.fsChunks; D.bsChunks = S.bsChunks;
+    D.fsI = S.fsI.data(); D.bsI = S.bsI.data(); D.fsSrc = S.fsSrc.data(); D.bsSrc = S.bsSrc.data();
 }
 
 // osqp_admm = 1: the one-thread-per-instance build of the solver; osqp_admm = 2 (test only): the one-warp-per-instance
@@ -178,6 +183,7 @@ static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned share
     osq::Symbolic S;
     osq::analyse(nV, mA, Qpat, Apat, S);
     g_osqp_nnzL = (long long)S.Li.size(); g_osqp_factor_flops = S.factor_flops;
+    g_osqp_stream[0] = S.stream; g_osqp_stream[1] = S.fsChunks; g_osqp_stream[2] = S.bsChunks;
     osq::SymDev D;
     sym_to_dev(S, nC, nComp, D);
     std::vector<double> ws(osq::ws_doubles(D) + 8);
