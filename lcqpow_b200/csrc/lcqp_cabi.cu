@@ -627,6 +627,12 @@ __global__ void __launch_bounds__(32) lcqp_osqpw_kernel(const __grid_constant__ 
         w.ring_uses = reinterpret_cast<unsigned*>(w.ring + osq::kStreamStages * osq::stream_stage_bytes() + 8 * osq::kStreamStages);
         osqw::ring_init(w);
     }
+#ifdef LCQP_PROFILE
+    __shared__ long long oprof[16];
+    if (lane == 0) { for (int k = 0; k < 16; k++) oprof[k] = 0; oprof[14] = clock64(); }
+    w.prof = oprof;
+    __syncwarp();
+#endif
     const int nV = a.S.n, mA = a.S.m, nD = nV + mA;
     for (;;) {
         unsigned b = 0;
@@ -649,6 +655,10 @@ __global__ void __launch_bounds__(32) lcqp_osqpw_kernel(const __grid_constant__ 
         if (lane == 0) a.stats[b] = osqp_stats(out, st, mA);
         __syncwarp();
     }
+#ifdef LCQP_PROFILE
+    OSQ_PROF(w, 0);
+    if (lane == 0) for (int k = 0; k < 14; k++) atomicAdd(&g_prof[k], (unsigned long long)oprof[k]);
+#endif
 }
 
 }  // namespace lcqp
@@ -1461,6 +1471,27 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     h->launches++;
     CK(cudaGetLastError(), LCQP_CUDA_LAUNCH_FAILED);
     CK(cudaEventRecord(h->ev2, stream), LCQP_CUDA_LAUNCH_FAILED);
+#ifdef LCQP_PROFILE
+    if (getenv("LCQP_CUDA_VERBOSE") && warp_mode) {
+        cudaStreamSynchronize(stream);
+        unsigned long long pr[16];
+        cudaMemcpyFromSymbol(pr, g_prof, sizeof(pr));
+        unsigned long long z[16] = {};
+        cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+        double tot = 0;
+        for (int k = 0; k < 14; k++) tot += (double)pr[k];
+        static const char* nm[14] = {"outer loop / other", "factor: elimination", "factor: pack streams", "solve: permute/scale", "solve: forward sweep", "solve: backward sweep",
+                                     "admm: vector updates", "admm: residuals/term.", "polish (its own part)", "sweeps: waiting for a chunk", "-", "-", "-", "-"};
+        fprintf(stderr, "lcqp_cuda OSQP-flavour profile (warp cycles per LCQP, %% of total):\n");
+        for (int k = 0; k < 10; k++) fprintf(stderr, "   %-28s %14.0f  %5.1f%%\n", nm[k], (double)pr[k] / h->batch, 100.0 * pr[k] / (tot > 0 ? tot : 1));
+        if (h->sym && h->sym->stream) {
+            long long lf = 0, lb = 0;
+            for (int c = 0; c < h->sym->fsChunks; c++) lf += (unsigned short)(h->sym->fsI[(size_t)c * osq::kStreamIdx / 2] & 0xffff);
+            for (int c = 0; c < h->sym->bsChunks; c++) lb += (unsigned short)(h->sym->bsI[(size_t)c * osq::kStreamIdx / 2] & 0xffff);
+            fprintf(stderr, "   stream levels: forward %lld, backward %lld\n", lf, lb);
+        }
+    }
+#endif
     h->last_stream = stream;
     h->last_grid = (int)warps;
     h->last_smem = (int)dyn_smem;

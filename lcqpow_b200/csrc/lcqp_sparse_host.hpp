@@ -89,7 +89,9 @@ inline bool build_stream(int N, const std::vector<std::vector<StreamRow>>& level
         for (const auto& r : lv) if (!r.ent.empty()) rows.push_back(&r);
         std::stable_sort(rows.begin(), rows.end(), [](const StreamRow* a, const StreamRow* b) { return a->ent.size() > b->ent.size(); });
         for (size_t g = 0; g < rows.size();) {
-            const int E = (int)rows[g]->ent.size();   // the longest of the group (rows are sorted by length)
+            // the longest of the group (rows are sorted by length), padded to a multiple of four: the device sweep loads the
+            // entries of a row four at a time ahead of the (sequential) subtractions
+            const int E = (((int)rows[g]->ent.size() + 3) / 4) * 4;
             // at most 32 rows (one per lane), fewer when the rows are long: the group must fit one chunk
             int r = (int)std::min<size_t>(32, rows.size() - g);
             while (r > 1 && (r * E > kStreamVals || 1 + 2 + r + r * E > kStreamIdx)) r--;

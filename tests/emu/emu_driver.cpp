@@ -132,6 +132,18 @@ static int legacy_solve_batch(int batch, int nV, int nC, int nComp, unsigned sha
 static long long g_osqp_nnzL = 0, g_osqp_factor_flops = 0;
 extern "C" void lcqp_emu_osqp_info(long long* nnzL, long long* factor_flops) { *nnzL = g_osqp_nnzL; *factor_flops = g_osqp_factor_flops; }
 static int g_osqp_stream[3] = {0, 0, 0};
+static long long g_osqp_sstat[8] = {0};   // per direction: levels, rows, padded entries, max E
+extern "C" void lcqp_emu_osqp_stream_stats(long long* out) { for (int k = 0; k < 8; k++) out[k] = g_osqp_sstat[k]; }
+static void stream_stats(const std::vector<int>& Ipack, int nchunks, long long* o)
+{
+    const unsigned short* I = reinterpret_cast<const unsigned short*>(Ipack.data());
+    o[0] = o[1] = o[2] = o[3] = 0;
+    for (int c = 0; c < nchunks; c++) {
+        const unsigned short* ic = I + (size_t)c * lcqp::osq::kStreamIdx;
+        int p = 1;
+        for (int lv = 0; lv < ic[0]; lv++) { const int r = ic[p], E = ic[p + 1]; o[0]++; o[1] += r; o[2] += r * E; if (E > o[3]) o[3] = E; p += 2 + r + r * E; }
+    }
+}
 extern "C" void lcqp_emu_osqp_stream(int* on, int* fwd_chunks, int* bwd_chunks) { *on = g_osqp_stream[0]; *fwd_chunks = g_osqp_stream[1]; *bwd_chunks = g_osqp_stream[2]; }
 
 static void sym_to_dev(const osq::Symbolic& S, int nC, int nComp, osq::SymDev& D)
@@ -184,6 +196,7 @@ static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned share
     osq::analyse(nV, mA, Qpat, Apat, S);
     g_osqp_nnzL = (long long)S.Li.size(); g_osqp_factor_flops = S.factor_flops;
     g_osqp_stream[0] = S.stream; g_osqp_stream[1] = S.fsChunks; g_osqp_stream[2] = S.bsChunks;
+    if (S.stream) { stream_stats(S.fsI, S.fsChunks, g_osqp_sstat); stream_stats(S.bsI, S.bsChunks, g_osqp_sstat + 4); }
     osq::SymDev D;
     sym_to_dev(S, nC, nComp, D);
     std::vector<double> ws(osq::ws_doubles(D) + 8);
