@@ -1347,7 +1347,7 @@ static int osqp_upload_symbolic(lcqp_cuda_handle h)
     const std::vector<int>* vs[NV] = {&S.Pp, &S.Pi, &S.Psrc, &S.Ap, &S.Ai, &S.Asrc, &S.Qp, &S.Qi, &S.Qsrc, &S.perm, &S.Kp, &S.Ki, &S.Ksrc,
                                       &S.Lp, &S.Li, &S.rp, &S.rcol, &S.rpos, &S.Pcol, &S.Acol, &S.Qcol,
                                       &S.ArP, &S.ArE, &S.PrP, &S.PrE, &S.QrP, &S.QrE, &S.LrP, &S.LrC, &S.rposr, &S.flP, &S.flR, &S.blP, &S.blC,
-                                      &S.fsI, &S.bsI, &S.fsSrc, &S.bsSrc};
+                                      &S.fsI, &S.bsI, &S.fsSrc, &S.bsSrc, &S.sOff, &S.fpIdx, &S.fpLi, &S.fpStep, &S.rowPair};
     size_t total = 0;
     size_t off[NV];
     for (int k = 0; k < NV; k++) { off[k] = total; total += (vs[k]->size() + 3) & ~(size_t)3; }
@@ -1368,7 +1368,7 @@ static int osqp_upload_symbolic(lcqp_cuda_handle h)
     D.fsChunks = S.fsChunks; D.bsChunks = S.bsChunks; D.stream = S.stream;
     const int** dst[NV] = {&D.Pp, &D.Pi, &D.Psrc, &D.Ap, &D.Ai, &D.Asrc, &D.Qp, &D.Qi, &D.Qsrc, &D.perm, &D.Kp, &D.Ki, &D.Ksrc, &D.Lp, &D.Li, &D.rp, &D.rcol, &D.rpos,
                            &D.Pcol, &D.Acol, &D.Qcol, &D.ArP, &D.ArE, &D.PrP, &D.PrE, &D.QrP, &D.QrE, &D.LrP, &D.LrC, &D.rposr, &D.flP, &D.flR, &D.blP, &D.blC,
-                           &D.fsI, &D.bsI, &D.fsSrc, &D.bsSrc};
+                           &D.fsI, &D.bsI, &D.fsSrc, &D.bsSrc, &D.sOff, &D.fpIdx, &D.fpLi, &D.fpStep, &D.rowPair};
     for (int k = 0; k < NV; k++) *dst[k] = h->sym_ints + off[k];
     h->osqp_nnzL = (long long)S.Li.size();
     return LCQP_CUDA_OK;

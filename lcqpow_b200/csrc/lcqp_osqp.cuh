@@ -57,9 +57,10 @@ struct SymDev {
     int n, m, N, nC, nComp, nnzP, nnzA, nnzQ, nnzK, nnzL, nflev, nblev;
     int fsChunks, bsChunks, stream;   // streamed triangular solves (lcqp_sparse_host.hpp: Symbolic::fsI ...), warp mode only
     const int *Pp, *Pi, *Psrc, *Ap, *Ai, *Asrc, *Qp, *Qi, *Qsrc, *perm, *Kp, *Ki, *Ksrc, *Lp, *Li, *rp, *rcol, *rpos, *Pcol, *Acol, *Qcol,
-        *ArP, *ArE, *PrP, *PrE, *QrP, *QrE, *LrP, *LrC, *rposr, *flP, *flR, *blP, *blC, *fsI, *bsI, *fsSrc, *bsSrc;
+        *ArP, *ArE, *PrP, *PrE, *QrP, *QrE, *LrP, *LrC, *rposr, *flP, *flR, *blP, *blC, *fsI, *bsI, *fsSrc, *bsSrc,
+        *sOff, *fpIdx, *fpLi, *fpStep, *rowPair;
 };
-constexpr int kSymArrays = 38;
+constexpr int kSymArrays = 43;
 // shared-memory ring of the streamed sweeps: kStreamStages x (value chunk + index chunk) + one mbarrier per stage
 constexpr int kStreamStages = 2;
 LCQ_HD inline size_t stream_stage_bytes() { return (size_t)kStreamVals * sizeof(double) + (size_t)kStreamIdx * sizeof(unsigned short); }

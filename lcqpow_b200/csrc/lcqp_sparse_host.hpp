@@ -60,6 +60,11 @@ struct Symbolic {
     //   value chunk c (kStreamVals doubles, per instance): filled after every numeric factorisation from the row-major
     //       (forward sweep) / column-major (backward sweep) copy of L through fsSrc / bsSrc (-1: padding)
     // stream = 0 when a level does not fit a chunk (the sweeps then read L in place, level by level).
+    // the numeric factorisation's updates ("pairs"), listed in the order the row programs perform them: step t of the row
+    // programs subtracts L(i, c) * y_c for the entries p in [Lp[c], rpos[t]) of column c = rcol[t]; pair q in
+    // [sOff[t], sOff[t+1]) is one of them: fpIdx[q] = p, fpLi[q] = Li[p], fpStep[q] = t - rp[row].  rowPair[k] = sOff[rp[k]].
+    // (the warp build prefetches a row's steps and pairs in two rounds of loads instead of three per step)
+    std::vector<int> sOff, fpIdx, fpLi, fpStep, rowPair;
     std::vector<int> fsI, bsI;         // index chunks, two 16-bit words per int
     std::vector<int> fsSrc, bsSrc;     // kStreamVals per chunk
     int fsChunks = 0, bsChunks = 0, stream = 0;
@@ -354,6 +359,21 @@ inline void analyse_with(int n, int m, const std::vector<Trip>& Qpat, const std:
         const bool okb = okf && build_stream(N, bw, S.bsI, S.bsSrc, S.bsChunks);
         S.stream = (okf && okb) ? 1 : 0;
         if (!S.stream) { S.fsI.clear(); S.bsI.clear(); S.fsSrc.clear(); S.bsSrc.clear(); S.fsChunks = S.bsChunks = 0; }
+    }
+    {
+        S.sOff.assign(S.rcol.size() + 1, 0);
+        S.fpIdx.clear(); S.fpLi.clear(); S.fpStep.clear();
+        S.rowPair.assign(N + 1, 0);
+        for (int k = 0; k < N; k++) {
+            S.rowPair[k] = (int)S.fpIdx.size();
+            for (int t = S.rp[k]; t < S.rp[k + 1]; t++) {
+                S.sOff[t] = (int)S.fpIdx.size();
+                const int c = S.rcol[t];
+                for (int p = S.Lp[c]; p < S.rpos[t]; p++) { S.fpIdx.push_back(p); S.fpLi.push_back(S.Li[p]); S.fpStep.push_back(t - S.rp[k]); }
+            }
+        }
+        S.sOff[S.rcol.size()] = (int)S.fpIdx.size();
+        S.rowPair[N] = (int)S.fpIdx.size();
     }
     S.Lcol.assign(S.Li.size(), 0);
     S.Lrev.clear();

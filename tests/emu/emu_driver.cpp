@@ -160,6 +160,7 @@ static void sym_to_dev(const osq::Symbolic& S, int nC, int nComp, osq::SymDev& D
     // streamed sweeps (the warp build reads the streams in place; LCQP_EMU_NOSTREAM: the level-by-level sweeps)
     D.stream = getenv("LCQP_EMU_NOSTREAM") ? 0 : S.stream; D.fsChunks = S.fsChunks; D.bsChunks = S.bsChunks;
     D.fsI = S.fsI.data(); D.bsI = S.bsI.data(); D.fsSrc = S.fsSrc.data(); D.bsSrc = S.bsSrc.data();
+    D.sOff = S.sOff.data(); D.fpIdx = S.fpIdx.data(); D.fpLi = S.fpLi.data(); D.fpStep = S.fpStep.data(); D.rowPair = S.rowPair.data();
 }
 
 // osqp_admm = 1: the one-thread-per-instance build of the solver; osqp_admm = 2 (test only): the one-warp-per-instance
