@@ -99,7 +99,7 @@ class Config:
             sb = P.sparse_banded_batch(hi - lo, lo=lo)
             return sb.to_dense(0, hi - lo) if dense else sb
         if self.name == "c2":
-            return P.circle_batch_fast(n).slice(lo, hi)
+            return P.circle_batch_fast(n, lo=lo, hi=hi)   # (only the shard's g / x0 are materialised)
         if self.name == "c5":
             return P.dense_random_batch(hi, seed_lo=lo) if lo else P.dense_random_batch(hi)
         data = dict(np.load(os.path.join(ROOT, "tests", "golden", "example_data.npz")))

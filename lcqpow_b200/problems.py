@@ -187,11 +187,16 @@ def circle_batch(batch: int = 1, N: int = 100, seed0: int = 20000) -> LCQPBatch:
                      x0=x0, shared=frozenset(("Q", "L", "R", "A", "lbA", "ubA")), name=f"circle_N{N}")
 
 
-def circle_batch_fast(batch: int, N: int = 100, seed0: int = 20000) -> LCQPBatch:
+def circle_batch_fast(batch: int, N: int = 100, seed0: int = 20000, lo: int = 0, hi: int | None = None) -> LCQPBatch:
     """Same family as ``circle_batch`` but vectorised (one generator, seed ``seed0``) for bench-sized
     batches; instance 0 is still the shipped one.  Used for throughput only; parity subsets use
-    ``circle_batch`` (per-instance seeds)."""
+    ``circle_batch`` (per-instance seeds).
+
+    ``lo``/``hi``: build only instances [lo, hi) of the family of ``batch`` instances (a shard of a multi-GPU run: the
+    reference points of the whole family are drawn -- 16 bytes per instance -- the 3.2 KB of g and x0 per instance only
+    for the shard)."""
     nV, nC, nComp, Q, L, R, A, lbA, ubA = circle_shared(N)
+    hi = batch if hi is None else hi
     rng = np.random.default_rng(seed0)
     xr = np.empty((batch, 2))
     filled = 0
@@ -201,12 +206,14 @@ def circle_batch_fast(batch: int, N: int = 100, seed0: int = 20000) -> LCQPBatch
         xr[filled:filled + len(cand)] = cand
         filled += len(cand)
     xr[0] = (0.5, -0.6)
-    g = np.zeros((batch, nV))
+    xr = xr[lo:hi]
+    nb = hi - lo
+    g = np.zeros((nb, nV))
     g[:, 0] = -(17.0 * xr[:, 0] + -15.0 * xr[:, 1])
     g[:, 1] = -(-15.0 * xr[:, 0] + 17.0 * xr[:, 1])
-    x0 = np.ones((batch, nV))
+    x0 = np.ones((nb, nV))
     x0[:, 0:2] = xr
-    return LCQPBatch(nV=nV, nC=nC, nComp=nComp, batch=batch, Q=Q, g=g, L=L, R=R, A=A, lbA=lbA, ubA=ubA,
+    return LCQPBatch(nV=nV, nC=nC, nComp=nComp, batch=nb, Q=Q, g=g, L=L, R=R, A=A, lbA=lbA, ubA=ubA,
                      x0=x0, shared=frozenset(("Q", "L", "R", "A", "lbA", "ubA")), name=f"circle_N{N}")
 
 
