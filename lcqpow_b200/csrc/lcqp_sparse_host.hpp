@@ -54,7 +54,7 @@ struct Symbolic {
     // in which a level-by-level sweep consumes them, cut into chunks of kStreamVals values that a warp brings into shared
     // memory ahead of use (cp.async.bulk + mbarrier), so that the only dependent loads of a sweep are shared-memory ones.
     //   index chunk c (kStreamIdx 16-bit words, shared by the batch): [nlev] then per level [r][E][r rows][E x r columns]
-    //       a level here has r <= 32 independent rows (lane j owns row j) padded to E entries each; entry e of lane j is
+    //       a level here has r <= 32 independent chains (lane j owns chain j) of up to E entries each; entry e of lane j is
     //       value slot voff + e * r + j of value chunk c (voff runs over the chunk), its column is the matching index word;
     //       padding entries carry value 0 and column N + 2 (a scratch slot that holds 0)
     //   value chunk c (kStreamVals doubles, per instance): filled after every numeric factorisation from the row-major
@@ -94,9 +94,9 @@ inline bool build_stream(int N, const std::vector<std::vector<StreamRow>>& level
         for (const auto& r : lv) if (!r.ent.empty()) rows.push_back(&r);
         std::stable_sort(rows.begin(), rows.end(), [](const StreamRow* a, const StreamRow* b) { return a->ent.size() > b->ent.size(); });
         for (size_t g = 0; g < rows.size();) {
-            // the longest of the group (rows are sorted by length), padded to a multiple of four: the device sweep loads the
-            // entries of a row four at a time ahead of the (sequential) subtractions
-            const int E = (((int)rows[g]->ent.size() + 3) / 4) * 4;
+            // the longest of the group (rows are sorted by length); shorter rows are padded with no-op entries
+            const int E = (int)rows[g]->ent.size();
+            if (E > 4) return false;   // (the device loop keeps a level's entries in registers: four per chain)
             // at most 32 rows (one per lane), fewer when the rows are long: the group must fit one chunk
             int r = (int)std::min<size_t>(32, rows.size() - g);
             while (r > 1 && (r * E > kStreamVals || 1 + 2 + r + r * E > kStreamIdx)) r--;
@@ -340,21 +340,62 @@ inline void analyse_with(int n, int m, const std::vector<Trip>& Qpat, const std:
         for (int l = 1; l <= maxb; l++) { for (int i = N - 1; i >= 0; i--) if (blev[i] == l) S.blC.push_back(i); S.blP.push_back((int)S.blC.size()); }
     }
     {
-        // the streamed form of the two sweeps: forward = rows of a level, entries L(i, c) in ascending c (slot of the row-major
-        // copy); backward = columns of a level, entries L(r, i) in ascending r (slot of the column-major array)
-        std::vector<std::vector<StreamRow>> fw(S.flP.size() - 1), bw(S.blP.size() - 1);
-        for (size_t l = 0; l + 1 < S.flP.size(); l++)
-            for (int q = S.flP[l]; q < S.flP[l + 1]; q++) {
-                StreamRow r; r.id = S.flR[q];
-                for (int sl = S.LrP[r.id]; sl < S.LrP[r.id + 1]; sl++) r.ent.push_back({sl, S.LrC[sl]});
-                fw[l].push_back(std::move(r));
+        // The streamed form of the two sweeps.  Unknown i of a sweep is a chain of subtractions x_i -= L(.,.) x_c in a fixed
+        // order (forward: the entries of row i of L, ascending c; backward: the entries of column i, ascending row) and an
+        // entry may be applied as soon as ITS x_c is final -- a row need not wait for its last column as in a level set.
+        // Greedy step schedule: in every step each unfinished chain whose next entry is ready takes up to B consecutive ready
+        // entries (at most 32 chains per step, one per lane); a step is one "level" of the stream, a chain appears in as many
+        // levels as it takes steps (its partial sum lives in the unknown's own slot).  C4: the forward sweep takes 367 steps
+        // of ~27 entries instead of 345 levels of ~3 rows x 13 entries, the backward sweep 705 steps (B = 4) instead of a
+        // critical path of 2 647 single entries.  B is chosen per sweep by a cost model of the device loop.
+        std::vector<std::vector<std::pair<int, int>>> fent(N), bent(N);
+        for (int i = 0; i < N; i++) for (int sl = S.LrP[i]; sl < S.LrP[i + 1]; sl++) fent[i].push_back({sl, S.LrC[sl]});
+        for (int i = 0; i < N; i++) for (int p = S.Lp[i]; p < S.Lp[i + 1]; p++) bent[i].push_back({p, S.Li[p]});
+        auto schedule = [&](const std::vector<std::vector<std::pair<int, int>>>& ent, int B, bool descending, std::vector<std::vector<StreamRow>>& out) {
+            std::vector<int> pos(N, 0), finstep(N, -1);
+            std::vector<char> done(N, 0);
+            int remaining = 0;
+            for (int i = 0; i < N; i++) { if (ent[i].empty()) done[i] = 1; else remaining++; }
+            out.clear();
+            double cost = 0.0;
+            for (int step = 0; remaining > 0; step++) {
+                std::vector<StreamRow> lv;
+                int Emax = 0;
+                for (int ii = 0; ii < N && (int)lv.size() < 32; ii++) {
+                    const int i = descending ? N - 1 - ii : ii;
+                    if (done[i]) continue;
+                    int c = 0;
+                    while (c < B && pos[i] + c < (int)ent[i].size()) {
+                        const int d = ent[i][pos[i] + c].second;
+                        if (done[d] && finstep[d] < step) c++; else break;
+                    }
+                    if (c == 0) continue;
+                    StreamRow r; r.id = i;
+                    r.ent.assign(ent[i].begin() + pos[i], ent[i].begin() + pos[i] + c);
+                    lv.push_back(std::move(r));
+                    Emax = std::max(Emax, c);
+                }
+                if (lv.empty()) { out.clear(); return -1.0; }   // (cannot happen: L is triangular)
+                for (const auto& r : lv) {
+                    pos[r.id] += (int)r.ent.size();
+                    if (pos[r.id] == (int)ent[r.id].size()) { done[r.id] = 1; finstep[r.id] = step; remaining--; }
+                }
+                cost += 110.0 + 45.0 * Emax;   // cycles of a level in the device loop (header + row, then the entries)
+                out.push_back(std::move(lv));
             }
-        for (size_t l = 0; l + 1 < S.blP.size(); l++)
-            for (int q = S.blP[l]; q < S.blP[l + 1]; q++) {
-                StreamRow r; r.id = S.blC[q];
-                for (int p = S.Lp[r.id]; p < S.Lp[r.id + 1]; p++) r.ent.push_back({p, S.Li[p]});
-                bw[l].push_back(std::move(r));
+            return cost;
+        };
+        auto best = [&](const std::vector<std::vector<std::pair<int, int>>>& ent, bool descending, std::vector<std::vector<StreamRow>>& out) {
+            double bc = -1.0;
+            for (int B : {1, 2, 4}) {
+                std::vector<std::vector<StreamRow>> cand;
+                const double c = schedule(ent, B, descending, cand);
+                if (c >= 0.0 && (bc < 0.0 || c < bc)) { bc = c; out = std::move(cand); }
             }
+        };
+        std::vector<std::vector<StreamRow>> fw, bw;
+        best(fent, false, fw);
+        best(bent, true, bw);
         const bool okf = build_stream(N, fw, S.fsI, S.fsSrc, S.fsChunks);
         const bool okb = okf && build_stream(N, bw, S.bsI, S.bsSrc, S.bsChunks);
         S.stream = (okf && okb) ? 1 : 0;
