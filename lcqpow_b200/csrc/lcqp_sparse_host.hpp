@@ -394,9 +394,11 @@ inline void analyse_with(int n, int m, const std::vector<Trip>& Qpat, const std:
             }
         };
         std::vector<std::vector<StreamRow>> fw, bw;
-        best(fent, false, fw);
-        best(bent, true, bw);
-        const bool okf = build_stream(N, fw, S.fsI, S.fsSrc, S.fsChunks);
+        if (N + 3 <= 65535) {   // (16-bit index words; beyond that the sweeps read L in place and no schedule is needed)
+            best(fent, false, fw);
+            best(bent, true, bw);
+        }
+        const bool okf = !fw.empty() && !bw.empty() && build_stream(N, fw, S.fsI, S.fsSrc, S.fsChunks);
         const bool okb = okf && build_stream(N, bw, S.bsI, S.bsSrc, S.bsChunks);
         S.stream = (okf && okb) ? 1 : 0;
         if (!S.stream) { S.fsI.clear(); S.bsI.clear(); S.fsSrc.clear(); S.bsSrc.clear(); S.fsChunks = S.bsChunks = 0; }
