@@ -76,3 +76,20 @@ def test_two_rank_sharding_is_bit_identical_to_one_rank():
     assert same_x and same_it
     assert tmax == 2.0 and nsum == total
     assert solved >= total - 1
+
+
+def test_bench_family_shard_is_generated_without_the_rest():
+    """bench.py gives every rank only its own shard of the C2 family (8 x 2^20 instances would be 27 GB of g / x0 per rank):
+    circle_batch_fast(n, lo, hi) must be instances [lo, hi) of circle_batch_fast(n), instance 0 the shipped one."""
+    import numpy as np
+    from lcqpow_b200 import problems as P
+    from lcqpow_b200 import sharding
+    n, world = 4096, 4
+    full = P.circle_batch_fast(n)
+    assert tuple(full.x0[0, :2]) == (0.5, -0.6)
+    for rank in range(world):
+        lo, hi = sharding.shard_range(n, rank, world)
+        part = P.circle_batch_fast(n, lo=lo, hi=hi)
+        assert part.batch == hi - lo
+        assert np.array_equal(part.g, full.g[lo:hi]) and np.array_equal(part.x0, full.x0[lo:hi])
+        assert part.shared == full.shared
