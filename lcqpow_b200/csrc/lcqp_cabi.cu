@@ -1427,7 +1427,7 @@ static int run_osqp(lcqp_cuda_handle h, cudaStream_t stream)
     if (!warp_mode) a.S.stream = 0;   // (one thread per instance reads L in place; its workspace holds no streams)
     // (they pay when a sweep is a long chain of small levels -- C4: 334 levels of ~6 rows; with a handful of wide levels
     //  -- C2: 4 levels -- reading L in place is faster: 1.66k against 1.13k LCQP/s, r2p)
-    if (warp_mode && a.S.stream && a.S.nflev + a.S.nblev >= 32 && !tune_env("LCQP_CUDA_OSQP_NOSTREAM")) {
+    if (warp_mode && a.S.stream && (a.S.nflev + a.S.nblev >= 32 || tune_env("LCQP_CUDA_OSQP_FORCESTREAM")) && !tune_env("LCQP_CUDA_OSQP_NOSTREAM")) {
         const size_t off = a.smem_bytes ? ((size_t)a.smem_bytes + 127) & ~(size_t)127 : 128;
         if (off + osq::stream_ring_bytes() <= (size_t)kSmemMax - 1024) { a.ring_offset = (unsigned)off; dyn_smem = off + osq::stream_ring_bytes(); }
     }
