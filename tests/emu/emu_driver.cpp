@@ -134,6 +134,19 @@ extern "C" void lcqp_emu_osqp_info(long long* nnzL, long long* factor_flops) { *
 static int g_osqp_stream[3] = {0, 0, 0};
 static long long g_osqp_sstat[8] = {0};   // per direction: levels, rows, padded entries, max E
 extern "C" void lcqp_emu_osqp_stream_stats(long long* out) { for (int k = 0; k < 8; k++) out[k] = g_osqp_sstat[k]; }
+static std::vector<int> g_osqp_streamI[2];
+static int g_osqp_N = 0;
+// the raw index stream of the last analysis (dir 0 forward, 1 backward): 16-bit words, kStreamIdx per chunk; returns the
+// number of words (copies at most cap), *N = order of the KKT system
+extern "C" long long lcqp_emu_osqp_stream_words(int dir, unsigned short* out, long long cap, int* N, int* words_per_chunk)
+{
+    const std::vector<int>& v = g_osqp_streamI[dir ? 1 : 0];
+    const long long n = (long long)v.size() * 2;
+    if (out) std::memcpy(out, v.data(), (size_t)std::min(n, cap) * sizeof(unsigned short));
+    if (N) *N = g_osqp_N;
+    if (words_per_chunk) *words_per_chunk = lcqp::osq::kStreamIdx;
+    return n;
+}
 static void stream_stats(const std::vector<int>& Ipack, int nchunks, long long* o)
 {
     const unsigned short* I = reinterpret_cast<const unsigned short*>(Ipack.data());
@@ -198,6 +211,7 @@ static int osqp_solve_batch(int batch, int nV, int nC, int nComp, unsigned share
     g_osqp_nnzL = (long long)S.Li.size(); g_osqp_factor_flops = S.factor_flops;
     g_osqp_stream[0] = S.stream; g_osqp_stream[1] = S.fsChunks; g_osqp_stream[2] = S.bsChunks;
     if (S.stream) { stream_stats(S.fsI, S.fsChunks, g_osqp_sstat); stream_stats(S.bsI, S.bsChunks, g_osqp_sstat + 4); }
+    g_osqp_streamI[0] = S.fsI; g_osqp_streamI[1] = S.bsI; g_osqp_N = S.N;
     osq::SymDev D;
     sym_to_dev(S, nC, nComp, D);
     std::vector<double> ws(osq::ws_doubles(D) + 8);
